@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- AVE clips/sec of the DG-SCT adapter hot path (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic clips: the 48 ``VisualAdapter.forward`` calls
+of one AVE forward (12 paired layers x {audio,visual} x {p1,p2}, DG-SCT/AVE/nets/net_trans.py:878-906) at the
+reference geometry (Swin-V2-L/192 + HTS-AT/256 token shapes), B clips x T frames per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            engine arm (CUDA, C ABI)
+  python bench.py --impl reference [...]                         reference arm: the CPU oracle on host cores
+
+Under torchrun (N>1) every rank processes its own B clips (weak scaling, no data-path collective in the
+forward); the timed region is bracketed by barrier + synchronize and the max over ranks is reported.
+"""
+import argparse
+import dataclasses
+import json
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAIRS = [0, 0, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3]                       # stage of each paired layer (net_trans.py:882-885)
+VIS = [(192, 2304), (384, 576), (768, 144), (1536, 36)]            # (C, N) per Swin-V2-L/192 stage
+AUD = [(96, 4096), (192, 1024), (384, 256), (768, 64)]             # (C, N) per HTS-AT/256 stage
+ADAPTER_CFG = dict(K=32, r=8, g=2, T=10, alpha=0.3, beta=0.05, gamma=0.0, resampler="conv", ln_before=True,
+                   ln_post=True, gate_before_ln=False, use_bn=True, use_gate=True, temporal=False)
+
+
+def layer_list():
+    out = []
+    for li, s in enumerate(PAIRS):
+        for pos in ("p1", "p2"):
+            out.append(("aud", li, pos, s))
+            out.append(("vis", li, pos, s))
+    return out
+
+
+def dims(kind, s):
+    (C, N), (Co, No) = (VIS[s], AUD[s]) if kind == "vis" else (AUD[s], VIS[s])
+    return C, N, Co, No
+
+
+def alg_bytes(C, N, Co, No, BT, K=32, r=8, g=2, s_act=2, s_w=2):
+    P = (N * No + N + Co * C + C + 2 * (C * C + C) + 3 * (C * C // 2 + C // 2) + C // 2 + 1 + C * C // 2 + C
+         + K * C + 3 + 2 * C * (C // r) // g + 2 * (C // r) + 6 * C)
+    return s_act * BT * (2 * N * C + No * Co + N) + s_w * P
+
+
+def alg_flops(C, N, Co, No, BT, K=32, r=8, g=2):
+    return (2 * BT * (N * No * Co + N * Co * C) + 8 * BT * K * N * C + 2 * BT * N * C * C + BT * N * C * C
+            + 4 * BT * N * C * (C // r) // g)
+
+
+def init_param(shape, fan_in, gen, kind):
+    if kind == "gate":
+        return torch.rand(shape, generator=gen) * 0.75 + 0.25
+    if kind == "tokens":
+        return torch.rand(shape, generator=gen)
+    if kind == "var":
+        return torch.rand(shape, generator=gen) + 0.5
+    if kind == "mean":
+        return torch.randn(shape, generator=gen) * 0.1
+    if kind == "one":
+        return 1.0 + 0.1 * torch.randn(shape, generator=gen)
+    if kind == "zero":
+        return 0.1 * torch.randn(shape, generator=gen)
+    b = 1.0 / max(fan_in, 1) ** 0.5
+    return (torch.rand(shape, generator=gen) * 2 - 1) * b
+
+
+def make_params(C, N, Co, No, gen, K=32, r=8, g=2):
+    """Reference initialisers with gates / BN buffers randomised (SURVEY.md §8d 'Synthetic inputs')."""
+    H, Cd = C // 2, C // r
+    spec = {
+        "conv_adapter.weight": ((N, No, 1, 1), No, "w"), "conv_adapter.bias": ((N,), No, "w"),
+        "fc.weight": ((C, Co), Co, "w"), "fc.bias": ((C,), Co, "w"),
+        "fc_affine_audio_1.weight": ((C, C), C, "w"), "fc_affine_audio_1.bias": ((C,), C, "w"),
+        "fc_affine_video_1.weight": ((C, C), C, "w"), "fc_affine_video_1.bias": ((C,), C, "w"),
+        "fc_affine_bottleneck.weight": ((H, C), C, "w"), "fc_affine_bottleneck.bias": ((H,), C, "w"),
+        "fc_affine_video_2.weight": ((H, C), C, "w"), "fc_affine_video_2.bias": ((H,), C, "w"),
+        "fc_affine_audio_2.weight": ((H, C), C, "w"), "fc_affine_audio_2.bias": ((H,), C, "w"),
+        "fc_affine_v_s_att.weight": ((1, H), H, "w"), "fc_affine_v_s_att.bias": ((1,), H, "w"),
+        "fc_affine_v_c_att.weight": ((C, H), H, "w"), "fc_affine_v_c_att.bias": ((C,), H, "w"),
+        "my_tokens": ((K, C), 0, "tokens"), "gate_av": ((1,), 0, "gate"), "gate": ((1,), 0, "gate"),
+        "down_sampler.weight": ((Cd, C // g, 1, 1), C // g, "w"), "up_sampler.weight": ((C, Cd // g, 1, 1), Cd // g, "w"),
+        "bn1.weight": ((Cd,), 0, "one"), "bn1.bias": ((Cd,), 0, "zero"), "bn2.weight": ((C,), 0, "one"), "bn2.bias": ((C,), 0, "zero"),
+        "bn1.running_mean": ((Cd,), 0, "mean"), "bn1.running_var": ((Cd,), 0, "var"),
+        "bn2.running_mean": ((C,), 0, "mean"), "bn2.running_var": ((C,), 0, "var"),
+        "ln_before.weight": ((C,), 0, "one"), "ln_before.bias": ((C,), 0, "zero"),
+        "ln_post.weight": ((C,), 0, "one"), "ln_post.bias": ((C,), 0, "zero"),
+    }
+    return {k: init_param(shp, fan, gen, kind) for k, (shp, fan, kind) in spec.items()}
+
+
+def make_tokens(B, T, gen, dtype):
+    BT = B * T
+    vis = [torch.randn(BT, N, C, generator=gen).to(dtype) for (C, N) in VIS]
+    aud = [torch.randn(BT, N, C, generator=gen).to(dtype) for (C, N) in AUD]
+    return vis, aud
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            txt = self.p.communicate(timeout=5)[0]
+        except Exception:
+            txt = ""
+        sm, mx, reasons = [], [], set()
+        for line in txt.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (the oracle restatement pinned to the reference's
+    classes by tests/golden), all host threads, one clip (B=1, T=10 -> BT=10) per step."""
+    if rank != 0:
+        return
+    from oracle import dgsct_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(43)
+    Bs = 1
+    vis, aud = make_tokens(Bs, args.T, gen, torch.float32)
+    stack = []
+    for kind, li, pos, s in layer_list():
+        C, N, Co, No = dims(kind, s)
+        stack.append((kind, s, O.make_config("ave", C, N, Co, No), make_params(C, N, Co, No, gen)))
+
+    def step():
+        with torch.no_grad():
+            for kind, s, cfg, p in stack:
+                x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
+                O.adapter_forward(cfg, p, x, o, training=False)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = Bs / dt
+    line = {"metric": "AVE adapter-stack clips/sec (48 VisualAdapter.forward, B=8 T=10 workload)", "value": v, "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": workload_config(args, "cpu"),
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"B={Bs} clip (BT={Bs * args.T}) per step, 48 adapters, fp32 eval, torch CPU ({cores} threads)"},
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, where):
+    return {"workload": f"AVE adapter stack fwd: 48 VisualAdapter.forward calls, Swin-V2-L/192 + HTS-AT/256 token shapes, "
+                        f"B={args.B} clips x T={args.T} frames per GPU, K=32 r=8 g=2, eval-mode BN",
+            "B_per_gpu": args.B, "T": args.T, "adapters": 48, "adapter_params": 188.5e6, "mode": args.mode,
+            "l2": "per-step working set (754 MB fp32 parameters + 250 MB tokens) exceeds the 126 MB L2; no explicit flush",
+            "device": where}
+
+
+# ------------------------------------------------------------------------------------------------ engine arm
+def run_engine(args, rank, world, local_rank):
+    import dgsct_b200
+    from dgsct_b200 import _lib as L
+    from dgsct_b200.adapter import adapter_forward_raw
+
+    assert torch.cuda.is_available(), "the engine arm needs a B200; there is no CPU fallback"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist_.init_process_group("nccl", device_id=dev)
+        dist = dist_
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    gen = torch.Generator().manual_seed(43 + rank)
+    vis_h, aud_h = make_tokens(args.B, args.T, gen, dtype)
+    vis_h = [t.pin_memory() for t in vis_h]
+    aud_h = [t.pin_memory() for t in aud_h]
+    vis = [t.to(dev) for t in vis_h]
+    aud = [t.to(dev) for t in aud_h]
+    pgen = torch.Generator().manual_seed(1234)          # identical (replicated) parameters on every rank
+    stack = []
+    import types
+    opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=2, is_before_layernorm=1, is_post_layernorm=1)
+    modules = []
+    for kind, li, pos, s in layer_list():
+        C, N, Co, No = dims(kind, s)
+        p = {k: v.to(dev) for k, v in make_params(C, N, Co, No, pgen).items()}
+        stack.append((kind, s, p))
+        m = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, use_bn=True, use_gate=True, num_tk=32,
+                                     conv_dim_in=No, conv_dim_out=N, linear_in=Co, linear_out=C)
+        m.load_state_dict(p, strict=False)
+        modules.append(m.to(dev).eval())
+    BT = args.B * args.T
+
+    def step_resident():
+        for kind, s, p in stack:
+            x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
+            adapter_forward_raw(ADAPTER_CFG, p, x, o, training=False)
+
+    h2d = sum(t.numel() * t.element_size() for t in vis_h + aud_h)
+    last_maps = [None, None]
+    checksum = torch.zeros(1, device=dev)
+    d2h_buf = torch.empty(2 * BT * 64 + 1, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        # public API with HOST buffers: H2D of this step's token tensors, 48 module forwards, D2H of the result
+        v = [t.to(dev, non_blocking=True) for t in vis_h]
+        a = [t.to(dev, non_blocking=True) for t in aud_h]
+        acc = None
+        with torch.no_grad():
+            for (kind, s, p), m in zip(stack, modules):
+                x, o = (v[s], a[s]) if kind == "vis" else (a[s], v[s])
+                out, smap = m(x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
+                last_maps[0 if kind == "aud" else 1] = smap
+            res = torch.cat([last_maps[0].reshape(-1).float()[:BT * 64], last_maps[1].reshape(-1).float()[:BT * 36],
+                             out.float().sum().reshape(1)])
+        d2h_buf[:res.numel()].copy_(res, non_blocking=True)
+        return res.numel() * 4
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = L.launch_count()
+    ms_step = timed(step_resident, args.steps, args.warmup)
+    launches = (L.launch_count() - n0) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop() if sampler else None
+    d2h = step_e2e()
+    ms_e2e = timed(step_e2e, max(3, args.steps // 2), 3)
+
+    # per-stage device time (CUDA events inside the library, on the launching stream) for the roofline
+    roof = None
+    cpu_base = None
+    stage_ms = None
+    if rank == 0:
+        L.profile_enable(True)
+        psteps = 3
+        for _ in range(psteps):
+            step_resident()
+        torch.cuda.synchronize(dev)
+        prof = L.profile_collect()
+        L.profile_enable(False)
+        stage_ms = {k: round(v[0] / psteps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured" if peaks else "fallback"
+        # dominant kernel: the token-resampler contraction (conv_adapter as a GEMM), 48 launches per step
+        flops_conv = sum(2 * BT * dims(k, s)[1] * dims(k, s)[3] * dims(k, s)[2] for k, _, _, s in layer_list())
+        t_conv = prof.get("resample_conv", (0.0, 0))[0] / psteps * 1e-3
+        ach = flops_conv / t_conv / 1e12 if t_conv > 0 else 0.0
+        roof = {"kernel": "resample_conv (token resampler GEMM, 48 launches/step)", "bound": "tensor", "achieved": ach,
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": (t_conv * 1e3) / max(sum(v[0] for v in prof.values()) / psteps, 1e-9)}
+        tot_bytes = sum(alg_bytes(*dims(k, s), BT) for k, _, _, s in layer_list())
+        tot_flops = sum(alg_flops(*dims(k, s), BT) for k, _, _, s in layer_list())
+        roof["stack"] = {"algorithmic_GB": tot_bytes / 1e9, "algorithmic_TFLOP": tot_flops / 1e12,
+                         "hbm_GBps": tot_bytes / (ms_step * 1e-3) / 1e9, "hbm_frac": tot_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                         "tensor_TFLOPs": tot_flops / (ms_step * 1e-3) / 1e12,
+                         "tensor_frac": tot_flops / (ms_step * 1e-3) / 1e12 / tf_peak}
+        cpu_base = cpu_baseline(args)
+
+    if rank == 0:
+        value = world * args.B / (ms_step * 1e-3)
+        line = {"metric": "AVE adapter-stack clips/sec (48 VisualAdapter.forward, B=8 T=10 workload)", "value": value,
+                "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "impl": "engine", "config": workload_config(args, torch.cuda.get_device_name(dev)),
+                "e2e": {"value": world * args.B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+                "stage_ms_per_step": stage_ms}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args):
+    """Oracle on the host cores, bounded sample: one clip (BT=T) through the 48 adapters, best of 3."""
+    from oracle import dgsct_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(43)
+    vis, aud = make_tokens(1, args.T, gen, torch.float32)
+    stack = []
+    for kind, li, pos, s in layer_list():
+        C, N, Co, No = dims(kind, s)
+        stack.append((kind, s, O.make_config("ave", C, N, Co, No), make_params(C, N, Co, No, gen)))
+    best = 1e30
+    with torch.no_grad():
+        for it in range(4):
+            t0 = time.perf_counter()
+            for kind, s, cfg, p in stack:
+                x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
+                O.adapter_forward(cfg, p, x, o, training=False)
+            dt = time.perf_counter() - t0
+            if it:
+                best = min(best, dt)
+    return {"value": 1.0 / best, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"1 clip (BT={args.T}) through the 48 adapters, fp32 eval, torch CPU {cores} threads, best of 3"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--B", type=int, default=8)
+    ap.add_argument("--T", type=int, default=10)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--mode", default="fwd", choices=["fwd"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_engine(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

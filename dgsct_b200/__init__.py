@@ -1,0 +1,11 @@
+"""dgsct_b200 -- B200-native (sm_100a) engine for the DG-SCT cross-modal adapter.
+
+Public surface mirrors the reference's call boundary (DG-SCT/AVE/nets/net_trans.py:433-674):
+
+    from dgsct_b200 import VisualAdapter          # same constructor, state_dict and forward contract
+    dgsct_b200.patch(nets.net_trans, "ave")       # swap the class inside a reference task module
+"""
+from .adapter import VisualAdapter, patch, adapter_forward_raw, VARIANT_DEFAULTS  # noqa: F401
+from ._lib import build, lib  # noqa: F401
+
+__all__ = ["VisualAdapter", "patch", "adapter_forward_raw", "build", "lib", "VARIANT_DEFAULTS"]

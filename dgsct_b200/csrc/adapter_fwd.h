@@ -1,0 +1,21 @@
+// Internal interface between the C ABI (api.cu) and the forward pipelines.
+#pragma once
+#include "common.cuh"
+
+namespace dgsct {
+
+// byte offsets into the caller-provided workspace (all 256-B aligned)
+struct FwdPlan {
+  size_t bufA, bufV, bufX1, bufL, Tp, Z;
+  size_t acc_begin, osum, qsum, ssum, bn1_sum, bn1_sq, bn2_sum, bn2_sq, acc_end;
+  size_t aq1, aq2, h, m, tau, sig, bn1_scale, bn1_shift, bn2_scale, bn2_shift;
+  size_t total;
+};
+
+int validate_desc(const dgsct_desc* d);
+FwdPlan make_fwd_plan(const dgsct_desc& d);
+
+int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, const void* other, void* out,
+                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st);
+
+}  // namespace dgsct

@@ -1,0 +1,98 @@
+// C ABI of libdgsct.so (see include/dgsct.h).
+#include <math.h>
+#include <string.h>
+
+#include "adapter_fwd.h"
+
+namespace dgsct {
+static thread_local char g_err[512] = "";
+void set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+}  // namespace dgsct
+
+using namespace dgsct;
+
+extern "C" {
+
+int dgsct_version(void) { return DGSCT_VERSION; }
+
+const char* dgsct_status_string(int s) {
+  switch (s) {
+    case DGSCT_OK: return "ok";
+    case DGSCT_ERR_BAD_DESC: return "bad descriptor";
+    case DGSCT_ERR_NULL: return "null pointer";
+    case DGSCT_ERR_WORKSPACE: return "workspace too small or misaligned";
+    case DGSCT_ERR_CUDA: return "CUDA error";
+    case DGSCT_ERR_UNSUPPORTED: return "unsupported";
+    case DGSCT_ERR_ARCH: return "device is not sm_100";
+    default: return "unknown status";
+  }
+}
+
+const char* dgsct_last_cuda_error(void) { return g_err; }
+
+size_t dgsct_workspace_bytes(const dgsct_desc* desc) {
+  if (validate_desc(desc) != DGSCT_OK) return 0;
+  return make_fwd_plan(*desc).total;
+}
+
+int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const void* x, const void* other, void* out,
+                      void* spatial_map, float* temporal_map, const dgsct_taps* taps, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  int rc = validate_desc(desc);
+  if (rc != DGSCT_OK) return rc;
+  if (!params || !x || !other || !out || !spatial_map || !workspace) return DGSCT_ERR_NULL;
+  const dgsct_desc& d = *desc;
+  const dgsct_params& P = *params;
+  if (!P.resample_w || !P.fc_w || !P.fc_b || !P.a1_w || !P.a1_b || !P.v1_w || !P.v1_b || !P.bott_w || !P.bott_b ||
+      !P.v2_w || !P.v2_b || !P.a2_w || !P.a2_b || !P.s_w || !P.s_b || !P.c_w || !P.c_b || !P.tokens || !P.gate_av ||
+      !P.down_w || !P.up_w)
+    return DGSCT_ERR_NULL;
+  if (!(d.flags & DGSCT_F_NO_CONV_BIAS) && !P.resample_b) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_USE_GATE) && !P.gate) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_USE_BN) &&
+      (!P.bn1_w || !P.bn1_b || !P.bn2_w || !P.bn2_b || !P.bn1_rm || !P.bn1_rv || !P.bn2_rm || !P.bn2_rv))
+    return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_LN_BEFORE) && (!P.lnb_w || !P.lnb_b)) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_LN_POST) && (!P.lnp_w || !P.lnp_b)) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_TEMPORAL) && (!P.t_w || !P.t_b)) return DGSCT_ERR_NULL;
+  if (workspace_bytes < make_fwd_plan(d).total || ((uintptr_t)workspace & 255)) return DGSCT_ERR_WORKSPACE;
+  return adapter_fwd_simt(d, P, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream);
+}
+
+// Cubic convolution coefficients (A = -0.75), the kernel torch uses for mode='bicubic'.
+static void cubic_coeffs(double t, double w[4]) {
+  const double A = -0.75;
+  auto c1 = [&](double x) { return ((A + 2) * x - (A + 3)) * x * x + 1; };          // |x| <= 1
+  auto c2 = [&](double x) { return ((A * x - 5 * A) * x + 8 * A) * x - 4 * A; };    // 1 < |x| < 2
+  w[0] = c2(t + 1.0); w[1] = c1(t); w[2] = c1(1.0 - t); w[3] = c2(2.0 - t);
+}
+
+int dgsct_bicubic_matrix(int n_in, int n_out, float* w) {
+  if (n_in <= 0 || n_out <= 0 || !w) return DGSCT_ERR_BAD_DESC;
+  const size_t cols = (size_t)n_in * n_in;
+  memset(w, 0, sizeof(float) * cols * (size_t)n_out * n_out);
+  const double scale = (double)n_in / (double)n_out;   // align_corners = False
+  for (int oy = 0; oy < n_out; ++oy) {
+    const double sy = scale * (oy + 0.5) - 0.5;
+    const int iy = (int)floor(sy);
+    double wy[4]; cubic_coeffs(sy - iy, wy);
+    for (int ox = 0; ox < n_out; ++ox) {
+      const double sx = scale * (ox + 0.5) - 0.5;
+      const int ix = (int)floor(sx);
+      double wx[4]; cubic_coeffs(sx - ix, wx);
+      float* row = w + ((size_t)oy * n_out + ox) * cols;
+      for (int a = 0; a < 4; ++a) {
+        int yy = iy - 1 + a; yy = yy < 0 ? 0 : (yy >= n_in ? n_in - 1 : yy);   // border clamp
+        for (int b = 0; b < 4; ++b) {
+          int xx = ix - 1 + b; xx = xx < 0 ? 0 : (xx >= n_in ? n_in - 1 : xx);
+          row[(size_t)yy * n_in + xx] += (float)(wy[a] * wx[b]);
+        }
+      }
+    }
+  }
+  return DGSCT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+/* dgsct.h -- C ABI of the B200-native DG-SCT adapter engine (libdgsct.so).
+ *
+ * The reference (haoyi-duan/DG-SCT) has no native code and no FFI: its boundary for this path is the
+ * Python call  VisualAdapter.forward(x, vis_token)  (DG-SCT/AVE/nets/net_trans.py:552-674 and the per-task
+ * copies listed in SURVEY.md section 2.1).  This header is what a ctypes binding of that call binds to;
+ * `dgsct_b200/adapter.py` is that binding and INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted; no allocation and
+ *     no synchronisation happen inside any call; work is enqueued on `stream` (a cudaStream_t).
+ *   - activations are token-major: x (BT,N,C), other (BT,No,Co), out (BT,N,C), spatial_map (BT,N),
+ *     temporal_map (BT/T, T).  The reference's (BT,C,N,1) tensors are permuted views of these buffers
+ *     (net_trans.py:891), so the binding passes them through without a copy.
+ *   - parameters are the fp32 master tensors of the module's state_dict, contiguous.
+ *   - return value: 0 on success, a negative dgsct_status otherwise; nothing throws across the ABI.
+ */
+#ifndef DGSCT_H_
+#define DGSCT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGSCT_VERSION 100  /* 0.1.0 */
+
+typedef enum dgsct_status {
+  DGSCT_OK = 0,
+  DGSCT_ERR_BAD_DESC = -1,      /* inconsistent dimensions / unsupported flag combination          */
+  DGSCT_ERR_NULL = -2,          /* a required pointer is NULL                                       */
+  DGSCT_ERR_WORKSPACE = -3,     /* workspace too small or misaligned (256 B)                        */
+  DGSCT_ERR_CUDA = -4,          /* a CUDA runtime/driver call failed (see dgsct_last_cuda_error)    */
+  DGSCT_ERR_UNSUPPORTED = -5,   /* valid request the engine does not implement (yet)                */
+  DGSCT_ERR_ARCH = -6           /* device is not sm_100                                             */
+} dgsct_status;
+
+typedef enum dgsct_dtype { DGSCT_F32 = 0, DGSCT_BF16 = 1 } dgsct_dtype;
+
+/* flag bits of dgsct_desc.flags */
+#define DGSCT_F_TRAIN          (1u << 0)  /* BatchNorm uses batch statistics and updates running stats */
+#define DGSCT_F_USE_BN         (1u << 1)  /* use_bn   (net_trans.py:507,632,640)                        */
+#define DGSCT_F_USE_GATE       (1u << 2)  /* use_gate (net_trans.py:460,670)                            */
+#define DGSCT_F_LN_BEFORE      (1u << 3)  /* opt.is_before_layernorm (net_trans.py:626)                 */
+#define DGSCT_F_LN_POST        (1u << 4)  /* opt.is_post_layernorm   (net_trans.py:667)                 */
+#define DGSCT_F_GATE_BEFORE_LN (1u << 5)  /* AVS order: gate, then ln_post (PVT_AVSModel.py:308-313)    */
+#define DGSCT_F_TEMPORAL       (1u << 6)  /* compute temporal_att_maps (few-shot/nets/net_trans.py:534) */
+#define DGSCT_F_NO_CONV_BIAS   (1u << 7)  /* resampling matrix has no bias (bicubic variant)            */
+#define DGSCT_F_FORCE_SIMT     (1u << 8)  /* debugging: never take the tcgen05 kernels                  */
+
+typedef struct dgsct_desc {
+  int32_t BT;       /* frames in the batch (clips x T)                        */
+  int32_t T;        /* frames per clip (temporal gate only; BT % T == 0)      */
+  int32_t C, N;     /* width / tokens of the adapted stream                   */
+  int32_t Co, No;   /* width / tokens of the other (prompt) stream            */
+  int32_t K;        /* latent tokens (rows of my_tokens)                      */
+  int32_t r, g;     /* bottleneck reduction factor, conv groups               */
+  int32_t io_dtype; /* dgsct_dtype of x, other, out, spatial_map              */
+  uint32_t flags;
+  float alpha, beta, gamma;   /* gate mixing weights (net_trans.py:611; few-shot :537-549) */
+  float eps_ln, eps_bn, bn_momentum;
+} dgsct_desc;
+
+/* fp32 master parameters, same names as the reference state_dict.
+ * `resample_w` is conv_adapter.weight viewed (N,No) -- or, for the bicubic variant, the dense
+ * interpolation matrix built by the binding; `resample_b` may be NULL with DGSCT_F_NO_CONV_BIAS. */
+typedef struct dgsct_params {
+  const float *resample_w, *resample_b;        /* (N,No), (N)            conv_adapter            */
+  const float *fc_w, *fc_b;                    /* (C,Co), (C)            fc                      */
+  const float *a1_w, *a1_b;                    /* (C,C), (C)             fc_affine_audio_1       */
+  const float *v1_w, *v1_b;                    /* (C,C), (C)             fc_affine_video_1       */
+  const float *bott_w, *bott_b;                /* (C/2,C), (C/2)         fc_affine_bottleneck    */
+  const float *v2_w, *v2_b;                    /* (C/2,C), (C/2)         fc_affine_video_2       */
+  const float *a2_w, *a2_b;                    /* (C/2,C), (C/2)         fc_affine_audio_2       */
+  const float *s_w, *s_b;                      /* (1,C/2), (1)           fc_affine_v_s_att       */
+  const float *c_w, *c_b;                      /* (C,C/2), (C)           fc_affine_v_c_att       */
+  const float *tokens;                         /* (K,C)                  my_tokens               */
+  const float *gate_av;                        /* (1)                                            */
+  const float *gate;                           /* (1) or NULL                                    */
+  const float *down_w, *up_w;                  /* (C/r, C/g), (C, C/(r g))  grouped 1x1 convs    */
+  const float *bn1_w, *bn1_b, *bn2_w, *bn2_b;  /* (C/r) x2, (C) x2  or NULL                      */
+  float *bn1_rm, *bn1_rv, *bn2_rm, *bn2_rv;    /* running stats, updated in place when TRAIN     */
+  const float *lnb_w, *lnb_b, *lnp_w, *lnp_b;  /* (C) each or NULL                               */
+  const float *t_w, *t_b;                      /* (1,C), (1)  temporal_gated.0 or NULL           */
+} dgsct_params;
+
+/* Optional taps of intermediate tensors (fp32, token-major) for stage-by-stage parity tests.
+ * Any pointer may be NULL. */
+typedef struct dgsct_taps {
+  float *V;      /* (BT,N,C)  resampled prompt tokens          */
+  float *Tp;     /* (BT,K,C)  updated latent tokens            */
+  float *X1;     /* (BT,N,C)  x after latent-token attention   */
+  float *obar;   /* (BT,C)    mean_n V                         */
+  float *m;      /* (BT,C)    channel gate                     */
+  float *s;      /* (BT,N)    spatial logits incl. bias        */
+  float *Y;      /* (BT,N,C)  gated (+ln_before) activations   */
+  float *Z;      /* (BT,N,C/r) bottleneck pre-BN               */
+} dgsct_taps;
+
+int dgsct_version(void);
+const char *dgsct_status_string(int status);
+/* text of the last CUDA error seen by the calling thread (host pointer, never NULL) */
+const char *dgsct_last_cuda_error(void);
+
+/* bytes of scratch the forward needs for `desc` (0 if desc is invalid) */
+size_t dgsct_workspace_bytes(const dgsct_desc *desc);
+
+/* VisualAdapter.forward.  x,other,out,spatial_map are `io_dtype`; temporal_map is fp32 or NULL.
+ * `taps` may be NULL. */
+int dgsct_adapter_fwd(const dgsct_desc *desc, const dgsct_params *params, const void *x, const void *other,
+                      void *out, void *spatial_map, float *temporal_map, const dgsct_taps *taps,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Stage profiler (used by bench.py for the per-kernel roofline).  When enabled every pipeline stage is
+ * bracketed by CUDA events on the launching stream; collect() synchronises on them, writes accumulated
+ * milliseconds and call counts per stage (arrays of >= dgsct_num_stages() entries) and clears the log. */
+int dgsct_num_stages(void);
+const char *dgsct_stage_name(int stage);
+int dgsct_profile_enable(int on);
+int dgsct_profile_collect(double *ms_per_stage, long long *calls_per_stage, int n);
+/* kernels launched by the engine since the library was loaded (bench.py's gpu_launches) */
+long long dgsct_launch_count(void);
+
+/* Host helper: dense (n_out^2, n_in^2) matrix of bicubic (A=-0.75, align_corners=False) interpolation
+ * on a square token grid, written to HOST memory `w` (row-major).  Used for the AVS-S4 resampler
+ * (PVT_AVSModel.py:190-197). */
+int dgsct_bicubic_matrix(int n_in_side, int n_out_side, float *w_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGSCT_H_ */

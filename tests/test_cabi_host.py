@@ -1,0 +1,122 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/dgsct.h declares, and the
+host-only entry points behave (no kernel is launched here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import dgsct_b200
+from dgsct_b200 import _lib as L
+from oracle import dgsct_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(L._SO):
+        L.build()
+    return L.lib()
+
+
+def test_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "dgsct.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dgsct_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dgsct.h but not exported"
+    assert declared == set(L.EXPORTS)
+    assert lib.dgsct_version() == 100
+
+
+def test_struct_layouts_match_header():
+    hdr = open(os.path.join(ROOT, "include", "dgsct.h")).read()
+    body = hdr[hdr.index("typedef struct dgsct_params {"):hdr.index("} dgsct_params;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.replace("const", "").replace("float", "").replace("typedef struct dgsct_params {", "")
+        names += [n.strip().lstrip("*") for n in decl.split(",") if n.strip()]
+    assert names == L.PARAM_FIELDS
+    body = hdr[hdr.index("typedef struct dgsct_taps {"):hdr.index("} dgsct_taps;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    assert re.findall(r"float \*(\w+);", body) == L.TAP_FIELDS
+    assert C.sizeof(L.Desc) == 17 * 4
+
+
+def _desc(**kw):
+    d = L.Desc()
+    base = dict(BT=10, T=10, C=192, N=2304, Co=96, No=4096, K=32, r=8, g=2, io_dtype=L.DT_BF16, flags=0,
+                alpha=0.3, beta=0.05, gamma=0.0, eps_ln=1e-5, eps_bn=1e-5, bn_momentum=0.1)
+    base.update(kw)
+    for k, v in base.items():
+        setattr(d, k, v)
+    return d
+
+
+def test_workspace_bytes_and_validation(lib):
+    n = lib.dgsct_workspace_bytes(C.byref(_desc()))
+    assert n > 10 * 2304 * 192 * 2 * 3
+    assert lib.dgsct_workspace_bytes(C.byref(_desc(C=191))) == 0           # odd width
+    assert lib.dgsct_workspace_bytes(C.byref(_desc(r=7))) == 0             # C % r
+    assert lib.dgsct_workspace_bytes(C.byref(_desc(io_dtype=5))) == 0
+    assert lib.dgsct_workspace_bytes(C.byref(_desc(flags=L.F_TEMPORAL, BT=12))) == 0   # BT % T
+    assert lib.dgsct_workspace_bytes(None) == 0
+    # null pointers are reported, not dereferenced
+    rc = lib.dgsct_adapter_fwd(C.byref(_desc()), None, None, None, None, None, None, None, None, 0, None)
+    assert rc == -2 and lib.dgsct_status_string(rc) == b"null pointer"
+
+
+@pytest.mark.parametrize("n_in,n_out", [(6, 4), (4, 6), (8, 8), (16, 12), (12, 48)])
+def test_bicubic_matrix_matches_torch_interpolate(lib, n_in, n_out):
+    w = torch.empty(n_out * n_out, n_in * n_in, dtype=torch.float32)
+    assert lib.dgsct_bicubic_matrix(n_in, n_out, C.c_void_p(w.data_ptr())) == 0
+    ref = O.bicubic_matrix(n_in, n_out)
+    assert float((w.double() - ref).abs().max()) < 2e-6
+    assert torch.allclose(w.sum(1), torch.ones(n_out * n_out), atol=1e-5)
+
+
+def test_module_surface_matches_reference_state_dict():
+    import types
+    from tests.golden_util import case_names, load_case
+    variant_of = dict(ave_vis="ave", ave_aud="ave", ave_nobn="ave", avqa_vis="avqa", avvp_vis="avvp", s4_down="s4",
+                      s4_up="s4", ms3_vis="ms3", pretrain_vis="pretrain", fewshot_aud="fewshot")
+    for name in case_names():
+        cfg, meta, params, t = load_case(name)
+        opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=cfg.g, is_before_layernorm=1, is_post_layernorm=1,
+                                    num_tokens=cfg.K, alpha=cfg.alpha, beta=cfg.beta, gamma=cfg.gamma)
+        ad = dgsct_b200.VisualAdapter(cfg.C, cfg.C, "bottleneck", reduction_factor=cfg.r, opt=opt, use_bn=cfg.use_bn,
+                                      use_gate=cfg.use_gate, num_tk=cfg.K, conv_dim_in=cfg.No, conv_dim_out=cfg.N,
+                                      linear_in=cfg.Co, linear_out=cfg.C, variant=variant_of[name])
+        sd = ad.state_dict()
+        ref_keys = set(params) | set(meta["extra_state_keys"])
+        if variant_of[name] in ("s4", "ms3"):            # reference builds ln_before only if the option is set
+            ref_keys |= {"ln_before.weight", "ln_before.bias"}
+        assert set(sd) == ref_keys, (name, set(sd) ^ ref_keys)
+        for k, v in params.items():
+            assert tuple(sd[k].shape) == tuple(v.shape), (name, k)
+        c = ad._cfg()
+        for k in ("alpha", "beta", "gamma", "resampler", "ln_before", "ln_post", "gate_before_ln", "temporal", "K", "r", "g"):
+            assert c[k] == getattr(cfg, k), (name, k, c[k], getattr(cfg, k))
+        missing = ad.load_state_dict({k: v.float() for k, v in params.items()}, strict=False)
+        assert not missing.unexpected_keys
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    import types
+    opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=2, is_before_layernorm=1, is_post_layernorm=1)
+    ad = dgsct_b200.VisualAdapter(32, 32, "bottleneck", reduction_factor=8, opt=opt, num_tk=4, conv_dim_in=25,
+                                  conv_dim_out=16, linear_in=16, linear_out=32)
+    x = torch.randn(2, 32, 16, 1)
+    o = torch.randn(2, 16, 25, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        with torch.no_grad():
+            ad(x, o)
+    with pytest.raises(NotImplementedError):
+        dgsct_b200.VisualAdapter(32, 32, "basic", reduction_factor=8, opt=opt)
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            ad(x.squeeze(-1), o)
