@@ -127,7 +127,8 @@ def test_module_contract_and_strided_inputs():
         # genuinely channel-major (contiguous (BT,C,N,1)) inputs must give the same answer
         out2, smap2 = ad(f_v.permute(0, 2, 1).contiguous().unsqueeze(-1), f_a.permute(0, 2, 1).contiguous().unsqueeze(-1))
     assert out.shape == (10, C, N, 1) and smap.shape == (10, 1, N)
-    assert torch.equal(out, out2) and torch.equal(smap, smap2)
+    # (not bit-equal: the per-frame reductions use fp32 atomics, so summation order varies run to run)
+    assert rel_l2(out, out2) < 1e-5 and rel_l2(smap, smap2) < 1e-5
     ro, rs, _, _ = O.adapter_forward(cfg, params, f_v.cpu(), f_a.cpu())
     assert rel_l2(out.squeeze(-1).permute(0, 2, 1).cpu(), ro) < 5e-5
     # a fresh adapter (zero gates) outputs exactly zero, as in the reference (SURVEY.md §7 hard part 6)
