@@ -221,7 +221,9 @@ def run_engine(args, rank, world, local_rank):
     for kind, li, pos, s in layer_list():
         C, N, Co, No = dims(kind, s)
         p = {k: v.to(dev) for k, v in make_params(C, N, Co, No, pgen).items()}
-        stack.append((kind, s, p))
+        x0, o0 = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
+        pk = adapter_forward_raw(ADAPTER_CFG, p, x0, o0, pack_only=True) if dtype == torch.bfloat16 else None
+        stack.append((kind, s, p, pk))
         m = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, use_bn=True, use_gate=True, num_tk=32,
                                      conv_dim_in=No, conv_dim_out=N, linear_in=Co, linear_out=C)
         m.load_state_dict(p, strict=False)
@@ -229,9 +231,9 @@ def run_engine(args, rank, world, local_rank):
     BT = args.B * args.T
 
     def step_resident():
-        for kind, s, p in stack:
+        for kind, s, p, pk in stack:
             x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
-            adapter_forward_raw(ADAPTER_CFG, p, x, o, training=False)
+            adapter_forward_raw(ADAPTER_CFG, p, x, o, training=False, packed=pk)
 
     h2d = sum(t.numel() * t.element_size() for t in vis_h + aud_h)
     last_maps = [None, None]
@@ -244,7 +246,7 @@ def run_engine(args, rank, world, local_rank):
         a = [t.to(dev, non_blocking=True) for t in aud_h]
         acc = None
         with torch.no_grad():
-            for (kind, s, p), m in zip(stack, modules):
+            for (kind, s, p, pk), m in zip(stack, modules):
                 x, o = (v[s], a[s]) if kind == "vis" else (a[s], v[s])
                 out, smap = m(x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
                 last_maps[0 if kind == "aud" else 1] = smap

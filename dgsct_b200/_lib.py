@@ -38,8 +38,10 @@ class Taps(C.Structure):
 
 
 EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgsct_workspace_bytes",
+           "dgsct_packed_bytes", "dgsct_pack_params",
            "dgsct_adapter_fwd", "dgsct_bicubic_matrix", "dgsct_num_stages", "dgsct_stage_name",
-           "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count"]
+           "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
+           "dgsct_tc_error_flag"]
 
 _lib = None
 
@@ -71,7 +73,11 @@ def lib() -> C.CDLL:
     L.dgsct_workspace_bytes.argtypes = [C.POINTER(Desc)]
     L.dgsct_adapter_fwd.restype = C.c_int
     L.dgsct_adapter_fwd.argtypes = [C.POINTER(Desc), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]
+                                    C.c_void_p, C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]
+    L.dgsct_packed_bytes.restype = C.c_size_t
+    L.dgsct_packed_bytes.argtypes = [C.POINTER(Desc)]
+    L.dgsct_pack_params.restype = C.c_int
+    L.dgsct_pack_params.argtypes = [C.POINTER(Desc), C.POINTER(Params), C.c_void_p, C.c_void_p]
     L.dgsct_bicubic_matrix.restype = C.c_int
     L.dgsct_bicubic_matrix.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.dgsct_num_stages.restype = C.c_int
@@ -80,6 +86,9 @@ def lib() -> C.CDLL:
     L.dgsct_profile_enable.argtypes = [C.c_int]
     L.dgsct_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     L.dgsct_launch_count.restype = C.c_longlong
+    L.dgsct_debug_gemm_bf16.restype = C.c_int
+    L.dgsct_debug_gemm_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_longlong] * 4 + [C.c_int] * 3 + [C.c_void_p]
+    L.dgsct_tc_error_flag.argtypes = [C.c_int]
     _lib = L
     return L
 

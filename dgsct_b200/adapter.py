@@ -78,7 +78,8 @@ def bicubic_matrix(n_in_side: int, n_out_side: int, device) -> torch.Tensor:
 
 
 def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor,
-                        training: bool = False, want_taps: bool = False, force_simt: bool = False):
+                        training: bool = False, want_taps: bool = False, force_simt: bool = False,
+                        packed: Optional[torch.Tensor] = None, pack_only: bool = False):
     """Token-major entry: x (BT,N,C), other (BT,No,Co) contiguous CUDA tensors (fp32 or bf16); ``params`` maps
     reference state_dict names to fp32 CUDA tensors.  ``cfg`` keys: K, r, g, T, alpha, beta, gamma, resampler,
     ln_before, ln_post, gate_before_ln, use_bn, use_gate, temporal, eps_ln, eps_bn, bn_momentum.
@@ -147,6 +148,13 @@ def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Ten
     if nbytes == 0:
         raise ValueError(f"dgsct: invalid adapter description C={Cc} N={N} Co={Co} No={No} K={d.K} r={d.r} g={d.g} T={d.T} BT={BT}")
     stream = torch.cuda.current_stream(dev).cuda_stream
+    if pack_only:
+        pb = lib.dgsct_packed_bytes(C.byref(d))
+        buf = torch.empty(pb + 256, dtype=torch.uint8, device=dev)
+        off = (-buf.data_ptr()) % 256
+        with torch.cuda.device(dev):
+            L.check(lib.dgsct_pack_params(C.byref(d), C.byref(P), C.c_void_p(buf.data_ptr() + off), C.c_void_p(stream)), "pack_params")
+        return buf[off:off + pb]
     ws = _workspace(dev, stream, nbytes + 256)
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
     out = torch.empty_like(x)
@@ -164,7 +172,8 @@ def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Ten
         for k, v in taps_t.items():
             setattr(taps, k, v.data_ptr())
     with torch.cuda.device(dev):
-        rc = lib.dgsct_adapter_fwd(C.byref(d), C.byref(P), C.c_void_p(x.data_ptr()), C.c_void_p(other.data_ptr()),
+        rc = lib.dgsct_adapter_fwd(C.byref(d), C.byref(P), C.c_void_p(packed.data_ptr() if packed is not None else 0),
+                                   C.c_void_p(x.data_ptr()), C.c_void_p(other.data_ptr()),
                                    C.c_void_p(out.data_ptr()), C.c_void_p(smap.data_ptr()),
                                    C.c_void_p(tmap.data_ptr() if tmap is not None else 0),
                                    C.byref(taps) if taps is not None else None,
@@ -267,6 +276,21 @@ class VisualAdapter(nn.Module):
         sd.update(dict(self.named_buffers()))
         return {k: v.detach() for k, v in sd.items() if k in _PARAM_MAP}
 
+    _PACKED_SOURCES = ("conv_adapter.weight", "fc.weight", "my_tokens", "fc_affine_video_1.weight",
+                       "fc_affine_video_2.weight", "down_sampler.weight", "up_sampler.weight")
+
+    def _packed_weights(self, cfg, params, xt, ot):
+        """bf16 operand copies for the tensor-core path, re-packed only when a source parameter changed
+        (torch bumps ``_version`` on every in-place update, e.g. optimizer.step / load_state_dict)."""
+        if xt.dtype != torch.bfloat16:
+            return None
+        key = (tuple((params[n].data_ptr(), params[n]._version) for n in self._PACKED_SOURCES if n in params),
+               tuple(xt.shape), tuple(ot.shape), str(xt.device))
+        if getattr(self, "_packed_key", None) != key:
+            self._packed_buf = adapter_forward_raw(cfg, params, xt, ot, pack_only=True)
+            self._packed_key = key
+        return self._packed_buf
+
     def forward(self, x, vis_token=None, caption=None, is_temporal=False):
         if caption is not None:
             raise NotImplementedError("the caption branch is dead code in the reference and is not implemented")
@@ -282,7 +306,9 @@ class VisualAdapter(nn.Module):
         if need_grad:
             res = _AdapterFn.apply(self, xt, ot, *[p for p in self.parameters()])
         else:
-            res = adapter_forward_raw(self._cfg(), self._param_dict(), xt, ot, training=self.training)
+            cfg, params = self._cfg(), self._param_dict()
+            res = adapter_forward_raw(cfg, params, xt, ot, training=self.training,
+                                      packed=self._packed_weights(cfg, params, xt, ot))
         out, smap = res[0], res[1]
         tmap = res[2] if len(res) > 2 else None
         if self.training and self.use_bn:

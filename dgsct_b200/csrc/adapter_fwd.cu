@@ -4,7 +4,9 @@
 #include "adapter_fwd.h"
 
 #include "epilogues.cuh"
+#include "pack.cuh"
 #include "profile.h"
+#include "tc_epilogues.cuh"
 #include "rowwise.cuh"
 
 namespace dgsct {
@@ -42,6 +44,13 @@ FwdPlan make_fwd_plan(const dgsct_desc& d) {
   p.tau = take(BT * 4); p.sig = take(BT * N * 4);
   p.bn1_scale = take(Cd * 4); p.bn1_shift = take(Cd * 4);
   p.bn2_scale = take(C * 4); p.bn2_shift = take(C * 4);
+  if (d.io_dtype == DGSCT_BF16) {
+    p.Pb = take(BT * N * K * 2);
+    p.TpB = take(BT * K * C * 2);
+    p.Zr = take(BT * N * (size_t)pad8((int)Cd) * 2);
+    p.Uo32 = take(BT * N * C * 4);                    // up-sampler output stays fp32 until ln_post
+    p.packed = take(make_pack_plan(d).total);
+  }
   p.total = off;
   return p;
 }
@@ -240,6 +249,335 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
     { StageScope _sc(ST_OUT_LN, st); count_launch();
   out_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
     DGSCT_LAUNCH_CHECK("out_ln"); }
+  }
+  return DGSCT_OK;
+}
+
+}  // namespace dgsct
+
+// =====================================================================================================
+// bf16 tensor-core pipeline
+// =====================================================================================================
+namespace dgsct {
+
+size_t packed_bytes(const dgsct_desc& d) { return make_pack_plan(d).total; }
+
+int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaStream_t st) {
+  const PackPlan pp = make_pack_plan(d);
+  const int N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2;
+  StageScope _sc(ST_MISC, st);
+  auto rows = [&](const float* src, int r, int c, size_t off, int ld) {
+    const size_t n = (size_t)r * ld;
+    count_launch();
+    pack_rows_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(src, r, c, (bf16*)(packed + off), ld);
+  };
+  rows(P.resample_w, N, No, pp.res, pp.ld_res);
+  rows(P.fc_w, C, Co, pp.fc, pp.ld_fc);
+  rows(P.tokens, K, C, pp.tok, pp.ld_c);
+  rows(P.v1_w, C, C, pp.v1, pp.ld_c);
+  rows(P.v2_w, H, C, pp.v2, pp.ld_c);
+  count_launch(2);
+  pack_grouped_kernel<<<ceil_div(Cd * pp.ld_c, 256), 256, 0, st>>>(P.down_w, Cd, C, d.g, (bf16*)(packed + pp.down), pp.ld_c);
+  pack_grouped_kernel<<<ceil_div(C * pp.ld_up, 256), 256, 0, st>>>(P.up_w, C, Cd, d.g, (bf16*)(packed + pp.up), pp.ld_up);
+  DGSCT_LAUNCH_CHECK("pack_params");
+  return DGSCT_OK;
+}
+
+// one product through the tcgen05 kernel, or through the SIMT kernel when TMA cannot describe the operands
+template <typename TE, typename SE>
+static int gemm_auto(int stage, const char* name, bool allow_tc, const tc::OperandDesc& A, const tc::OperandDesc& B, int M, int N,
+                     int K, int batch, TE te, SE se, cudaStream_t st) {
+  StageScope _sc(stage, st);
+  count_launch();
+  if (allow_tc) {
+    tc::Params p;
+    const int rc = tc::make_params(p, A, B, M, N, K, batch);
+    if (rc == DGSCT_OK) {
+      cudaError_t e = tc::launch(p, te, st);
+      if (e != cudaSuccess) { set_cuda_error(e, name); return DGSCT_ERR_CUDA; }
+      return DGSCT_OK;
+    }
+    if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
+  }
+  GemmShape sh{M, N, K, batch, 1};
+  GemmOperand a{A.ptr, A.mn_major ? 1 : A.ld, A.mn_major ? A.ld : 1, A.batch_stride, 0, 1};
+  GemmOperand b{B.ptr, B.mn_major ? 1 : B.ld, B.mn_major ? B.ld : 1, B.batch_stride, 0, 1};
+  cudaError_t e = launch_gemm_simt(sh, a, b, AxIdentity{}, se, st);
+  if (e != cudaSuccess) { set_cuda_error(e, name); return DGSCT_ERR_CUDA; }
+  return DGSCT_OK;
+}
+
+static tc::OperandDesc kmaj(const void* p, int rows, int cols, long long ld, long long bs) {
+  return tc::OperandDesc{p, 0, ld, bs, rows, cols};
+}
+static tc::OperandDesc mnmaj(const void* p, int k_rows, int mn_cols, long long ld, long long bs) {
+  return tc::OperandDesc{p, 1, ld, bs, k_rows, mn_cols};
+}
+static tc::EpiStore tc_store(void* out, int out_bf16, long long ld, long long sb) {
+  tc::EpiStore e{}; e.out = out; e.out_bf16 = out_bf16; e.ld = ld; e.sb = sb; e.alpha = 1.f; e.act = ACT_NONE;
+  return e;
+}
+
+// file-scope epilogue functors used only by the tensor-core pipeline
+struct SimtTokUpdate {
+  bf16* o; float* o2; const float* tok; int C, K;
+  __device__ void operator()(int b, int, int m, int n, float (&acc)[4][4], int M, int Nn) const {
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+      const int c = m + i, k = n + j;
+      if (c < M && k < Nn) {
+        const float v = acc[i][j] + tok[(long long)k * C + c];
+        o[(long long)b * K * C + (long long)k * C + c] = __float2bfloat16_rn(v);
+        o2[(long long)b * K * C + (long long)k * C + c] = v;
+      }
+    }
+  }
+};
+struct TcAffineRelu {   // zr[b,m,n] = relu(acc*scale[n] + shift[n]) (bf16) ; optional fp32 tap of acc
+  bf16* zr; long long ldz, sbz; const float* scale; const float* shift; float* ztap; int Cd;
+  __device__ void begin(int, int, bool) {}
+  __device__ void end(int, int, bool) {}
+  __device__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int Nn) {
+    if (!row_ok) return;
+    for (int j = 0; j < 16; ++j) {
+      const int n = n0 + j;
+      if (n < Nn) {
+        if (ztap) ztap[((long long)b * (sbz / ldz) + m) * Cd + n] = v[j];
+        zr[(long long)b * sbz + (long long)m * ldz + n] = __float2bfloat16_rn(fmaxf(fmaf(v[j], scale[n], shift[n]), 0.f));
+      }
+    }
+  }
+};
+struct SimtAffineRelu {
+  bf16* zr; long long ldz, sbz; const float* scale; const float* shift; float* ztap; int Cd;
+  __device__ void operator()(int b, int, int m, int n, float (&acc)[4][4], int M, int Nn) const {
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j)
+      if (m + i < M && n + j < Nn) {
+        if (ztap) ztap[((long long)b * (sbz / ldz) + m + i) * Cd + n + j] = acc[i][j];
+        zr[(long long)b * sbz + (long long)(m + i) * ldz + n + j] =
+            __float2bfloat16_rn(fmaxf(fmaf(acc[i][j], scale[n + j], shift[n + j]), 0.f));
+      }
+  }
+};
+
+#define DGSCT_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packed_in, const void* x, const void* other,
+                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st) {
+  const FwdPlan pl = make_fwd_plan(d);
+  const PackPlan pp = make_pack_plan(d);
+  const int BT = d.BT, N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2;
+  const int ldz = pad8(Cd);
+  const bool train = d.flags & DGSCT_F_TRAIN, use_bn = d.flags & DGSCT_F_USE_BN;
+  bf16* U = (bf16*)(ws + pl.bufA); bf16* V = (bf16*)(ws + pl.bufV); bf16* X1 = (bf16*)(ws + pl.bufX1);
+  float* L = (float*)(ws + pl.bufL); float* Tp = (float*)(ws + pl.Tp); float* Z = (float*)(ws + pl.Z);
+  bf16* Pb = (bf16*)(ws + pl.Pb); bf16* TpB = (bf16*)(ws + pl.TpB); bf16* Zr = (bf16*)(ws + pl.Zr);
+  float* Uo = (float*)(ws + pl.Uo32);
+  float* osum = (float*)(ws + pl.osum); float* qsum = (float*)(ws + pl.qsum); float* ssum = (float*)(ws + pl.ssum);
+  double* bn1_sum = (double*)(ws + pl.bn1_sum); double* bn1_sq = (double*)(ws + pl.bn1_sq);
+  double* bn2_sum = (double*)(ws + pl.bn2_sum); double* bn2_sq = (double*)(ws + pl.bn2_sq);
+  float* aq1 = (float*)(ws + pl.aq1); float* aq2 = (float*)(ws + pl.aq2); float* hbuf = (float*)(ws + pl.h);
+  float* mvec = (float*)(ws + pl.m); float* tau = (float*)(ws + pl.tau); float* sig = (float*)(ws + pl.sig);
+  float* bn1_scale = (float*)(ws + pl.bn1_scale); float* bn1_shift = (float*)(ws + pl.bn1_shift);
+  float* bn2_scale = (float*)(ws + pl.bn2_scale); float* bn2_shift = (float*)(ws + pl.bn2_shift);
+  const float invN = 1.f / (float)N;
+  const long long rowsBT = (long long)BT * N;
+
+  const char* pk = (const char*)packed_in;
+  if (!pk) {
+    DGSCT_RC(pack_params(d, P, ws + pl.packed, st));
+    pk = ws + pl.packed;
+  }
+  const bf16* Wres = (const bf16*)(pk + pp.res); const bf16* Wfc = (const bf16*)(pk + pp.fc);
+  const bf16* Wtok = (const bf16*)(pk + pp.tok); const bf16* Wv1 = (const bf16*)(pk + pp.v1);
+  const bf16* Wv2 = (const bf16*)(pk + pp.v2); const bf16* Wdn = (const bf16*)(pk + pp.down);
+  const bf16* Wup = (const bf16*)(pk + pp.up);
+
+  { StageScope _sc(ST_MISC, st);
+    DGSCT_CUDA_CHECK(cudaMemsetAsync(ws + pl.acc_begin, 0, pl.acc_end - pl.acc_begin, st)); }
+
+  // (R1) U[b] (N,Co) = Wres (N,No) . other[b] (No,Co) + b_res[n]
+  {
+    tc::EpiStore te = tc_store(U, 1, Co, (long long)N * Co);
+    EpiBiasStore se = epi_store(U, 1, Co, (long long)N * Co);
+    te.bias_m = se.bias_m = (d.flags & DGSCT_F_NO_CONV_BIAS) ? nullptr : P.resample_b;
+    DGSCT_RC(gemm_auto(ST_RESAMPLE_CONV, "resample_conv", true, kmaj(Wres, N, No, pp.ld_res, 0),
+                       mnmaj(other, No, Co, Co, (long long)No * Co), N, Co, No, BT, te, se, st));
+  }
+  // (R2) V = U . Wfc^T + b_fc ; osum[b,c] = sum_n V
+  {
+    tc::EpiStore te = tc_store(V, 1, C, (long long)N * C);
+    EpiBiasStore se = epi_store(V, 1, C, (long long)N * C);
+    te.bias_n = se.bias_n = P.fc_b; te.colsum = se.colsum = osum; te.ncols_total = se.ncols_total = C;
+    DGSCT_RC(gemm_auto(ST_RESAMPLE_FC, "resample_fc", true, kmaj(U, N, Co, Co, (long long)N * Co), kmaj(Wfc, C, Co, pp.ld_fc, 0),
+                       N, C, Co, BT, te, se, st));
+  }
+  if (taps) DGSCT_RC(tap(V, 1, taps->V, (size_t)BT * N * C, st));
+  const bool tok_tc = (K == 32);
+  // (T1) L[b,n,k] = V[b,n,:] . tok[k,:]  (fp32) ; P = softmax over tokens (bf16)
+  {
+    tc::EpiStore te = tc_store(L, 0, K, (long long)N * K);
+    EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);
+    DGSCT_RC(gemm_auto(ST_TOK_LOGITS, "tok_logits", tok_tc, kmaj(V, N, C, C, (long long)N * C), kmaj(Wtok, K, C, pp.ld_c, 0),
+                       N, K, C, BT, te, se, st));
+    StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
+    if (K <= 256) {
+      const int groups = 256 / K;
+      col_softmax_bf16_kernel<<<BT, 256, (size_t)groups * K * 4, st>>>(L, Pb, N, K);
+    } else {
+      return DGSCT_ERR_UNSUPPORTED;
+    }
+    DGSCT_LAUNCH_CHECK("col_softmax_bf16");
+  }
+  // (T3) Tp[b,k,c] = tok[k,c] + sum_n P[b,n,k] V[b,n,c]     computed as D(c,k): both operands token-major
+  {
+    tc::EpiStore te = tc_store(TpB, 1, C, (long long)K * C);
+    te.transposed = 1; te.add_t = P.tokens; te.add_ld = C; te.out2 = Tp; te.ld2 = C; te.sb2 = (long long)K * C;
+    // SIMT twin computes the same D(c,k) orientation: rows m = c, columns n = k
+    SimtTokUpdate se{TpB, Tp, P.tokens, C, K};
+    DGSCT_RC(gemm_auto(ST_TOK_UPDATE, "tok_update", tok_tc, mnmaj(V, N, C, C, (long long)N * C), mnmaj(Pb, N, K, K, (long long)N * K),
+                       C, K, N, BT, te, se, st));
+  }
+  if (taps && taps->Tp) DGSCT_RC(tap(Tp, 0, taps->Tp, (size_t)BT * K * C, st));
+  // (T4a) Q[b,n,:] = softmax_k(x[b,n,:] . Tp[b,k,:])  (bf16, reuses the P buffer)
+  if (tok_tc) {
+    tc::EpiRowSoftmax32 te{}; te.out = Pb; te.out_bf16 = 1; te.ld = K; te.sb = (long long)N * K;
+    EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);   // unused twin (operands are always TMA-describable here)
+    DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", true, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
+                       N, K, C, BT, te, se, st));
+  } else {
+    tc::EpiStore te = tc_store(L, 0, K, (long long)N * K);
+    EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);
+    DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", false, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
+                       N, K, C, BT, te, se, st));
+    StageScope _sc(ST_ROW_SOFTMAX, st); count_launch(2);
+    row_softmax_kernel<<<(unsigned)((rowsBT + 7) / 8), 256, 0, st>>>(L, rowsBT, K);
+    // Q as bf16 for the next product
+    pack_rows_kernel<<<(unsigned)(((size_t)rowsBT * K + 255) / 256 > 4096 ? 4096 : ((size_t)rowsBT * K + 255) / 256), 256, 0, st>>>(
+        L, (int)rowsBT, K, Pb, K);
+    DGSCT_LAUNCH_CHECK("row_softmax");
+  }
+  // (T4b) X1 = x + gate_av * Q . Tp
+  {
+    tc::EpiResidual te{X1, x, 1, C, (long long)N * C, P.gate_av, 0.f};
+    EpiResidual se{X1, x, 1, C, (long long)N * C, P.gate_av};
+    DGSCT_RC(gemm_auto(ST_X_UPDATE, "x_update", tok_tc, kmaj(Pb, N, K, K, (long long)N * K), mnmaj(TpB, K, C, C, (long long)K * C),
+                       N, C, K, BT, te, se, st));
+  }
+  if (taps) DGSCT_RC(tap(X1, 1, taps->X1, (size_t)BT * N * C, st));
+  // (C1) small per-frame linears (fp32 SIMT): aq1, aq2, tau
+  {
+    GemmShape sh{BT, C, C, 1, 1};
+    EpiBiasStore e = epi_store(aq1, 0, C, 0); e.bias_n = P.a1_b; e.alpha = invN; e.act = ACT_RELU;
+    DGSCT_GEMM(ST_SMALL_LINEAR, sh, op(osum, C, 1, 0, 0), op(P.a1_w, C, 1, 0, 0), AxIdentity{}, e, "aq1");
+    GemmShape sh2{BT, H, C, 1, 1};
+    EpiBiasStore e2 = epi_store(aq2, 0, H, 0); e2.bias_n = P.a2_b; e2.alpha = invN; e2.act = ACT_RELU;
+    DGSCT_GEMM(ST_SMALL_LINEAR, sh2, op(osum, C, 1, 0, 0), op(P.a2_w, C, 1, 0, 0), AxIdentity{}, e2, "aq2");
+    if (d.flags & DGSCT_F_TEMPORAL) {
+      GemmShape sh3{BT, 1, C, 1, 1};
+      EpiBiasStore e3 = epi_store(tau, 0, 1, 0); e3.bias_n = P.t_b; e3.alpha = invN; e3.act = ACT_SIGMOID;
+      DGSCT_GEMM(ST_SMALL_LINEAR, sh3, op(osum, C, 1, 0, 0), op(P.t_w, C, 1, 0, 0), AxIdentity{}, e3, "tau");
+      if (tmap) DGSCT_CUDA_CHECK(cudaMemcpyAsync(tmap, tau, (size_t)BT * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (taps && taps->obar) DGSCT_RC(tap(osum, 0, taps->obar, (size_t)BT * C, st));
+  }
+  // (C2) qsum[b,c] = sum_n aq1[b,c] relu(X1[b,n,:] . Wv1[c,:] + b)
+  {
+    tc::EpiReluMulColsum te{P.v1_b, aq1, qsum, C};
+    EpiReluMulColsum se{P.v1_b, aq1, qsum, C};
+    DGSCT_RC(gemm_auto(ST_CHANNEL_QUERY, "channel_query", true, kmaj(X1, N, C, C, (long long)N * C), kmaj(Wv1, C, C, pp.ld_c, 0),
+                       N, C, C, BT, te, se, st));
+  }
+  // (C3) m = sigmoid(Wc relu(Wb q + bb) + bc)
+  {
+    GemmShape sh{BT, H, C, 1, 1};
+    EpiBiasStore e = epi_store(hbuf, 0, H, 0); e.bias_n = P.bott_b; e.alpha = invN; e.act = ACT_RELU;
+    DGSCT_GEMM(ST_SMALL_LINEAR, sh, op(qsum, C, 1, 0, 0), op(P.bott_w, C, 1, 0, 0), AxIdentity{}, e, "channel_bottleneck");
+    GemmShape sh2{BT, C, H, 1, 1};
+    EpiBiasStore e2 = epi_store(mvec, 0, C, 0); e2.bias_n = P.c_b; e2.act = ACT_SIGMOID;
+    DGSCT_GEMM(ST_SMALL_LINEAR, sh2, op(hbuf, H, 1, 0, 0), op(P.c_w, H, 1, 0, 0), AxIdentity{}, e2, "channel_gate");
+  }
+  if (taps && taps->m) DGSCT_RC(tap(mvec, 0, taps->m, (size_t)BT * C, st));
+  // (S1) Xc = X1 (1+m) (bf16, in the U buffer) ; ssum[b,n] = sum_j ws[j] aq2[b,j] relu(Xc[b,n,:] . Wv2[j,:] + b)
+  {
+    bf16* Xc = U;
+    { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
+      scale_cols_kernel<<<2048, 256, 0, st>>>(X1, mvec, Xc, rowsBT, N, C);
+      DGSCT_LAUNCH_CHECK("scale_cols"); }
+    tc::EpiSpatialRowsum te{P.v2_b, aq2, P.s_w, ssum, H, N, 0.f};
+    EpiSpatialRowsum se{P.v2_b, aq2, P.s_w, ssum, H, N};
+    DGSCT_RC(gemm_auto(ST_SPATIAL_QUERY, "spatial_query", true, kmaj(Xc, N, C, C, (long long)N * C), kmaj(Wv2, H, C, pp.ld_c, 0),
+                       N, H, C, BT, te, se, st));
+  }
+  { StageScope _sc(ST_SPATIAL_MAP, st); count_launch();
+    spatial_map_kernel<<<BT, 256, 0, st>>>(ssum, P.s_b, N, sig, smap, 1, taps ? taps->s : nullptr);
+    DGSCT_LAUNCH_CHECK("spatial_map"); }
+  // (B1) Y = LN_before(X1 * (alpha m + beta sig + gamma tau + 1 - alpha))  -> V buffer
+  {
+    GateLnArgs a{};
+    a.x1 = X1; a.in_bf16 = 1; a.y = V; a.out_bf16 = 1; a.m = mvec; a.sig = sig;
+    a.tau = ((d.flags & DGSCT_F_TEMPORAL) && d.gamma != 0.f) ? tau : nullptr;
+    const bool lnb = d.flags & DGSCT_F_LN_BEFORE;
+    a.ln_w = lnb ? P.lnb_w : nullptr; a.ln_b = lnb ? P.lnb_b : nullptr;
+    a.alpha = d.alpha; a.beta = d.beta; a.gamma = d.gamma; a.eps = d.eps_ln; a.N = N; a.C = C;
+    a.rows = rowsBT; a.y_tap = taps ? taps->Y : nullptr;
+    const int wpb = 4;
+    StageScope _sc(ST_GATE_LN, st); count_launch();
+    gate_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
+    DGSCT_LAUNCH_CHECK("gate_ln");
+  }
+  const double count = (double)BT * (double)N;
+  const bool fuse_bn1 = !(train && use_bn);     // bn1 affine known before the down projection
+  if (fuse_bn1) {
+    StageScope _sc(ST_BN_FINALIZE, st); count_launch();
+    bn_finalize_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, use_bn, 0, bn1_sum, bn1_sq, count, P.bn1_w, P.bn1_b, P.bn1_rm,
+                                                           P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift);
+    DGSCT_LAUNCH_CHECK("bn1_finalize");
+  }
+  // (B2) Z = Y . Wdown^T (dense block-diagonal) ; eval: Zr = relu(bn1(Z)) fused into the epilogue
+  {
+    if (fuse_bn1) {
+      TcAffineRelu te{Zr, ldz, (long long)N * ldz, bn1_scale, bn1_shift, taps ? taps->Z : nullptr, Cd};
+      SimtAffineRelu se{Zr, ldz, (long long)N * ldz, bn1_scale, bn1_shift, taps ? taps->Z : nullptr, Cd};
+      DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(V, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
+                         N, Cd, C, BT, te, se, st));
+    } else {
+      tc::EpiStore te = tc_store(Z, 0, Cd, (long long)N * Cd);
+      EpiBiasStore se = epi_store(Z, 0, Cd, (long long)N * Cd);
+      te.stat_sum = se.stat_sum = bn1_sum; te.stat_sq = se.stat_sq = bn1_sq;
+      DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(V, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
+                         N, Cd, C, BT, te, se, st));
+      if (taps && taps->Z) DGSCT_RC(tap(Z, 0, taps->Z, (size_t)BT * N * Cd, st));
+      StageScope _sc(ST_BN_FINALIZE, st); count_launch(2);
+      bn_finalize_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, use_bn, 1, bn1_sum, bn1_sq, count, P.bn1_w, P.bn1_b, P.bn1_rm,
+                                                             P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift);
+      bn_relu_kernel<<<2048, 256, 0, st>>>(Z, bn1_scale, bn1_shift, Zr, rowsBT, Cd, ldz);
+      DGSCT_LAUNCH_CHECK("bn1_finalize");
+    }
+  }
+  // (B3) Uo = Zr . Wup^T (dense block-diagonal) ; bn2 batch statistics in train mode
+  {
+    tc::EpiStore te = tc_store(Uo, 0, C, (long long)N * C);
+    EpiBiasStore se = epi_store(Uo, 0, C, (long long)N * C);
+    if (train && use_bn) { te.stat_sum = se.stat_sum = bn2_sum; te.stat_sq = se.stat_sq = bn2_sq; }
+    DGSCT_RC(gemm_auto(ST_UP, "up_sampler", true, kmaj(Zr, N, Cd, ldz, (long long)N * ldz), kmaj(Wup, C, Cd, pp.ld_up, 0),
+                       N, C, Cd, BT, te, se, st));
+  }
+  { StageScope _sc(ST_BN_FINALIZE, st); count_launch();
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, use_bn, train, bn2_sum, bn2_sq, count, P.bn2_w, P.bn2_b, P.bn2_rm,
+                                                          P.bn2_rv, d.eps_bn, d.bn_momentum, bn2_scale, bn2_shift);
+    DGSCT_LAUNCH_CHECK("bn2_finalize"); }
+  {
+    OutLnArgs a{};
+    a.u = Uo; a.in_bf16 = 0; a.out = out; a.out_bf16 = 1; a.scale = bn2_scale; a.shift = bn2_shift;
+    const bool lnp = d.flags & DGSCT_F_LN_POST;
+    a.ln_w = lnp ? P.lnp_w : nullptr; a.ln_b = lnp ? P.lnp_b : nullptr;
+    a.gate = (d.flags & DGSCT_F_USE_GATE) ? P.gate : nullptr;
+    a.gate_before_ln = (d.flags & DGSCT_F_GATE_BEFORE_LN) ? 1 : 0;
+    a.eps = d.eps_ln; a.C = C; a.rows = rowsBT;
+    const int wpb = 4;
+    StageScope _sc(ST_OUT_LN, st); count_launch();
+    out_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
+    DGSCT_LAUNCH_CHECK("out_ln");
   }
   return DGSCT_OK;
 }

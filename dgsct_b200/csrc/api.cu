@@ -37,9 +37,24 @@ size_t dgsct_workspace_bytes(const dgsct_desc* desc) {
   return make_fwd_plan(*desc).total;
 }
 
-int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const void* x, const void* other, void* out,
-                      void* spatial_map, float* temporal_map, const dgsct_taps* taps, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+size_t dgsct_packed_bytes(const dgsct_desc* desc) {
+  if (validate_desc(desc) != DGSCT_OK) return 0;
+  return packed_bytes(*desc);
+}
+
+int dgsct_pack_params(const dgsct_desc* desc, const dgsct_params* params, void* packed, void* stream) {
+  int rc = validate_desc(desc);
+  if (rc != DGSCT_OK) return rc;
+  if (!params || !packed) return DGSCT_ERR_NULL;
+  const dgsct_params& P = *params;
+  if (!P.resample_w || !P.fc_w || !P.tokens || !P.v1_w || !P.v2_w || !P.down_w || !P.up_w) return DGSCT_ERR_NULL;
+  if ((uintptr_t)packed & 255) return DGSCT_ERR_WORKSPACE;
+  return pack_params(*desc, P, (char*)packed, (cudaStream_t)stream);
+}
+
+int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const void* packed, const void* x,
+                      const void* other, void* out, void* spatial_map, float* temporal_map, const dgsct_taps* taps,
+                      void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate_desc(desc);
   if (rc != DGSCT_OK) return rc;
   if (!params || !x || !other || !out || !spatial_map || !workspace) return DGSCT_ERR_NULL;
@@ -58,6 +73,9 @@ int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const 
   if ((d.flags & DGSCT_F_LN_POST) && (!P.lnp_w || !P.lnp_b)) return DGSCT_ERR_NULL;
   if ((d.flags & DGSCT_F_TEMPORAL) && (!P.t_w || !P.t_b)) return DGSCT_ERR_NULL;
   if (workspace_bytes < make_fwd_plan(d).total || ((uintptr_t)workspace & 255)) return DGSCT_ERR_WORKSPACE;
+  if (packed && ((uintptr_t)packed & 255)) return DGSCT_ERR_WORKSPACE;
+  if (d.io_dtype == DGSCT_BF16 && !(d.flags & DGSCT_F_FORCE_SIMT))
+    return adapter_fwd_tc(d, P, packed, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream);
   return adapter_fwd_simt(d, P, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,48 @@
+// Debug / bring-up entry points of the C ABI (used by tests/test_gpu_gemm_tc.py).
+#include "epilogues.cuh"
+#include "tc_epilogues.cuh"
+
+using namespace dgsct;
+
+extern "C" {
+
+// D[b] (M,N) fp32 = A[b] . B[b]^T with bf16 operands.  K-major operand: element (row, k) at row*ld + k;
+// MN-major operand: element (row, k) at k*ld + row.  batch strides in elements (0 = shared).
+int dgsct_debug_gemm_bf16(const void* A, const void* B, float* D, int M, int N, int K, int batch, int a_mn_major,
+                          int b_mn_major, long long lda, long long ldb, long long sa, long long sb, int use_tc,
+                          int bn_hint, int stages_hint, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!A || !B || !D) return DGSCT_ERR_NULL;
+  if (use_tc) {
+    tc::OperandDesc a{A, a_mn_major, lda, sa, a_mn_major ? K : M, a_mn_major ? M : K};
+    tc::OperandDesc b{B, b_mn_major, ldb, sb, b_mn_major ? K : N, b_mn_major ? N : K};
+    tc::Params p;
+    int rc = tc::make_params(p, a, b, M, N, K, batch, bn_hint, stages_hint);
+    if (rc) return rc;
+    tc::EpiStore e{};
+    e.out = D; e.out_bf16 = 0; e.ld = N; e.sb = (long long)M * N; e.alpha = 1.f;
+    cudaError_t err = tc::launch(p, e, st);
+    if (err != cudaSuccess) { set_cuda_error(err, "debug_gemm_tc"); return DGSCT_ERR_CUDA; }
+    return DGSCT_OK;
+  }
+  GemmShape sh{M, N, K, batch, 1};
+  GemmOperand a{A, a_mn_major ? 1 : lda, a_mn_major ? lda : 1, sa, 0, 1};
+  GemmOperand b{B, b_mn_major ? 1 : ldb, b_mn_major ? ldb : 1, sb, 0, 1};
+  EpiBiasStore e{};
+  e.out = D; e.out_bf16 = 0; e.ld = N; e.sb = (long long)M * N; e.alpha = 1.f;
+  cudaError_t err = launch_gemm_simt(sh, a, b, AxIdentity{}, e, st);
+  if (err != cudaSuccess) { set_cuda_error(err, "debug_gemm_simt"); return DGSCT_ERR_CUDA; }
+  return DGSCT_OK;
+}
+
+// reads (and optionally clears) the device flag set when a bounded mbarrier wait expired; synchronises
+int dgsct_tc_error_flag(int reset) {
+  int* p = tc::tc_err_flag_device_ptr();
+  if (!p) return -1;
+  int v = 0;
+  if (cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (reset) { int z = 0; cudaMemcpy(p, &z, sizeof(int), cudaMemcpyHostToDevice); }
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B/64B-swizzled shared memory ->
+// tcgen05.mma (UMMA, cta_group::1, M=128) with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+//   D[b](m, n) = sum_k A[b](m, k) * B[b](n, k)          m < M, n < N, k < K, b < batch
+//
+// Either operand may be K-major (rows of K, e.g. activations (tokens, C) and nn.Linear weights (out, in)) or
+// MN-major (rows of M/N, e.g. other[b] (No, Co) used as the B operand of the token resampler); the choice is a
+// run-time field of the shared-memory and instruction descriptors.  Ragged edges are handled by TMA
+// out-of-bounds zero fill on loads and by predication in the epilogue functor.
+//
+// One CTA computes one 128 x BN output tile: warp 0 (one lane) is the TMA producer, warp 1 (one lane) issues
+// the MMAs, then all four warps drain their 32 TMEM lanes through the epilogue functor.  Several CTAs are
+// resident per SM so the epilogue of one tile overlaps the main loop of another.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dgsct {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int THREADS = 128;
+constexpr int MAX_STAGES = 8;
+
+struct Params {
+  CUtensorMap mapA, mapB;
+  int M, N, K, batch;
+  int a_mn_major, b_mn_major;   // 0: K-major, 1: MN-major
+  int a_sw, b_sw;               // swizzle span in bytes (128 or 64)
+  int a_batched, b_batched;     // tensor-map coordinate 2 is the batch index (else 0)
+  int BN;                       // instruction / tile N (multiple of 16, <= 256)
+  int BK;                       // K elements per pipeline stage (64 or 32)
+  int stages;
+  int a_stage_bytes, b_stage_bytes;
+  int a_boxes, b_boxes, a_box_bytes, b_box_bytes;
+  uint32_t tmem_cols;
+  int* err_flag;                // device int set to non-zero when a bounded wait expires
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// bounded wait: ~2 s of SM clocks, then flag the error and let every role drain (no hang, no trap)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err_flag) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, 1);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (tcgen05): start address, leading/stride byte offsets (16-B units),
+// descriptor version 1, swizzle mode in bits [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int sw_bytes) {
+  const uint64_t layout = sw_bytes == 128 ? 2ull : (sw_bytes == 64 ? 4ull : (sw_bytes == 32 ? 6ull : 0ull));
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout << 61);
+}
+// instruction descriptor: bf16 x bf16 -> fp32, M=128
+__host__ __device__ inline uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// sum over the 32 lanes of each of 16 per-lane values in 16 shuffles (recursive halving); on return lane l
+// holds the total of column (l >> 1) in v[0]
+__device__ __forceinline__ float warp_colsum16(float (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8];
+      const float keep = up ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4];
+      const float keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2];
+      const float keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+// column owned by `lane` after warp_colsum16: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1
+__device__ __forceinline__ int colsum16_owner_col(int lane) {
+  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------
+// EPI interface:
+//   void begin(int b, int m, bool row_ok)                       once per thread (row m of batch b)
+//   void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N)   16 consecutive columns, warp-convergent
+//   void end(int b, int m, bool row_ok)
+template <typename EPI>
+__global__ void __launch_bounds__(THREADS) gemm_tc_kernel(const __grid_constant__ Params p, EPI epi) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y, b = blockIdx.z;
+  const int m0 = m_blk * BM, n0 = n_blk * p.BN;
+  const int num_k = (p.K + p.BK - 1) / p.BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.mapA);
+    prefetch_tmap(&p.mapB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    const int a_atom = p.a_sw / 2, b_atom = p.b_sw / 2;   // elements per swizzle row
+    bool ok = true;
+    for (int kb = 0; kb < num_k && ok; ++kb) {
+      const int s = kb % p.stages;
+      const uint32_t ph = (kb / p.stages) & 1;
+      ok = mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, p.err_flag);
+      if (!ok) break;
+      const uint32_t fb = smem_u32(&full_bar[s]);
+      mbar_expect_tx(fb, (uint32_t)(p.a_boxes * p.a_box_bytes + p.b_boxes * p.b_box_bytes));
+      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t sb = sa + p.a_stage_bytes;
+      const int k0 = kb * p.BK;
+      if (p.a_mn_major) {
+        for (int j = 0; j < p.a_boxes; ++j)
+          tma_load_3d(sa + j * p.a_box_bytes, &p.mapA, m0 + j * a_atom, k0, p.a_batched ? b : 0, fb);
+      } else {
+        tma_load_3d(sa, &p.mapA, k0, m0, p.a_batched ? b : 0, fb);
+      }
+      if (p.b_mn_major) {
+        for (int j = 0; j < p.b_boxes; ++j)
+          tma_load_3d(sb + j * p.b_box_bytes, &p.mapB, n0 + j * b_atom, k0, p.b_batched ? b : 0, fb);
+      } else {
+        tma_load_3d(sb, &p.mapB, k0, n0, p.b_batched ? b : 0, fb);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc(p.BN, p.a_mn_major, p.b_mn_major);
+    // per-operand descriptor recipe
+    const uint32_t a_lbo = p.a_mn_major ? (uint32_t)p.a_box_bytes : 16u;
+    const uint32_t a_sbo = 8u * (uint32_t)p.a_sw;
+    const uint32_t a_kstep = p.a_mn_major ? 16u * (uint32_t)p.a_sw : 32u;   // bytes per UMMA_K (16 elements)
+    const uint32_t b_lbo = p.b_mn_major ? (uint32_t)p.b_box_bytes : 16u;
+    const uint32_t b_sbo = 8u * (uint32_t)p.b_sw;
+    const uint32_t b_kstep = p.b_mn_major ? 16u * (uint32_t)p.b_sw : 32u;
+    bool ok = true;
+    for (int kb = 0; kb < num_k && ok; ++kb) {
+      const int s = kb % p.stages;
+      const uint32_t ph = (kb / p.stages) & 1;
+      ok = mbar_wait(smem_u32(&full_bar[s]), ph, p.err_flag);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t sb = sa + p.a_stage_bytes;
+      const int ksteps = p.BK / 16;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, p.a_sw);
+        const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, p.b_sw);
+        umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage once these MMAs have read it
+    }
+    umma_commit(smem_u32(tmem_full_bar));     // accumulator complete
+  }
+  __syncwarp();
+
+  // ===== epilogue: all 4 warps, warp w owns TMEM lanes [32w, 32w+32) =====
+  const bool acc_ok = mbar_wait(smem_u32(tmem_full_bar), 0, p.err_flag);
+  __syncwarp();
+  tc_fence_after();
+  const int m = m0 + warp * 32 + lane;
+  const bool row_ok = acc_ok && (m < p.M);
+  epi.begin(b, m, row_ok);
+  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int c = 0; c < p.BN; c += 16) {
+    float v[16];
+    tmem_ld16(lane_base + (uint32_t)c, v);
+    epi.chunk(b, m, n0 + c, v, row_ok, p.N);
+  }
+  epi.end(b, m, row_ok);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+struct OperandDesc {
+  const void* ptr;        // bf16
+  int mn_major;           // 0: (rows = M|N, cols = K) K contiguous; 1: (rows = K, cols = M|N) MN contiguous
+  long long ld;           // elements between consecutive rows
+  long long batch_stride; // elements between batches; 0 => shared
+  int rows, cols;         // logical extents of the stored matrix: rows x cols (cols contiguous)
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
+int* tc_err_flag_device_ptr();
+
+// Fills `p` (tensor maps, tile recipe) for D = A . B^T.  Returns DGSCT_OK, or DGSCT_ERR_UNSUPPORTED when the
+// operands cannot be described to TMA (alignment) so the caller can take the SIMT kernel instead.
+int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint = 0,
+                int stages_hint = 0);
+size_t smem_bytes(const Params& p);
+bool operands_ok(const OperandDesc& A, const OperandDesc& B, int K);
+
+template <typename EPI>
+inline cudaError_t launch(const Params& p, EPI epi, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = smem_bytes(p);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.N, p.BN), ceil_div(p.M, BM), p.batch);
+  gemm_tc_kernel<EPI><<<grid, THREADS, smem, st>>>(p, epi);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace dgsct

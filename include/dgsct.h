@@ -106,10 +106,17 @@ const char *dgsct_last_cuda_error(void);
 /* bytes of scratch the forward needs for `desc` (0 if desc is invalid) */
 size_t dgsct_workspace_bytes(const dgsct_desc *desc);
 
-/* VisualAdapter.forward.  x,other,out,spatial_map are `io_dtype`; temporal_map is fp32 or NULL.
- * `taps` may be NULL. */
-int dgsct_adapter_fwd(const dgsct_desc *desc, const dgsct_params *params, const void *x, const void *other,
-                      void *out, void *spatial_map, float *temporal_map, const dgsct_taps *taps,
+/* bf16 operand copies of the weights for the tensor-core path ("packed weights"): size of the buffer and the
+ * conversion itself (device buffer, 256-B aligned).  Re-pack whenever the fp32 masters change. */
+size_t dgsct_packed_bytes(const dgsct_desc *desc);
+int dgsct_pack_params(const dgsct_desc *desc, const dgsct_params *params, void *packed, void *stream);
+
+/* VisualAdapter.forward.  x,other,out,spatial_map are `io_dtype`; temporal_map is fp32 or NULL; `taps` may be
+ * NULL.  io_dtype fp32 runs exact fp32 SIMT kernels; io_dtype bf16 runs the tcgen05 tensor-core kernels
+ * with fp32 accumulation and fp32 softmax/LayerNorm/BatchNorm statistics.  `packed` is the buffer filled by
+ * dgsct_pack_params for these parameters, or NULL to convert the weights inside the call (bf16 only). */
+int dgsct_adapter_fwd(const dgsct_desc *desc, const dgsct_params *params, const void *packed, const void *x,
+                      const void *other, void *out, void *spatial_map, float *temporal_map, const dgsct_taps *taps,
                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* Stage profiler (used by bench.py for the per-kernel roofline).  When enabled every pipeline stage is
@@ -121,6 +128,15 @@ int dgsct_profile_enable(int on);
 int dgsct_profile_collect(double *ms_per_stage, long long *calls_per_stage, int n);
 /* kernels launched by the engine since the library was loaded (bench.py's gpu_launches) */
 long long dgsct_launch_count(void);
+
+/* Bring-up entry (tests): D[b] (M,N) fp32 = A[b] . B[b]^T with bf16 operands through the tcgen05 kernel
+ * (use_tc=1) or the SIMT kernel (use_tc=0).  K-major operand: element (row,k) at row*ld + k; MN-major operand:
+ * element (row,k) at k*ld + row; batch strides in elements, 0 = shared.  bn_hint: low 16 bits tile N (0 = auto). */
+int dgsct_debug_gemm_bf16(const void *A, const void *B, float *D, int M, int N, int K, int batch, int a_mn_major,
+                          int b_mn_major, long long lda, long long ldb, long long a_batch_stride,
+                          long long b_batch_stride, int use_tc, int bn_hint, int stages_hint, void *stream);
+/* value of the device flag raised when a bounded pipeline wait expired (0 = healthy); synchronises */
+int dgsct_tc_error_flag(int reset);
 
 /* Host helper: dense (n_out^2, n_in^2) matrix of bicubic (A=-0.75, align_corners=False) interpolation
  * on a square token grid, written to HOST memory `w` (row-major).  Used for the AVS-S4 resampler

@@ -66,7 +66,7 @@ def test_workspace_bytes_and_validation(lib):
     assert lib.dgsct_workspace_bytes(C.byref(_desc(flags=L.F_TEMPORAL, BT=12))) == 0   # BT % T
     assert lib.dgsct_workspace_bytes(None) == 0
     # null pointers are reported, not dereferenced
-    rc = lib.dgsct_adapter_fwd(C.byref(_desc()), None, None, None, None, None, None, None, None, 0, None)
+    rc = lib.dgsct_adapter_fwd(C.byref(_desc()), None, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -2 and lib.dgsct_status_string(rc) == b"null pointer"
 
 

@@ -94,7 +94,47 @@ def test_real_shapes_bf16(shape):
     assert rel_l2(smap, rs) < TOL_BF16, rel_l2(smap, rs)
 
 
-@pytest.mark.parametrize("shape,dtype", [("vis_s2", torch.float32), ("aud_s2", torch.bfloat16), ("vis_s3", torch.bfloat16)])
+@pytest.mark.parametrize("shape", ["vis_s0", "vis_s2", "aud_s1", "aud_s3", "clip"])
+def test_bf16_tensor_core_taps(shape):
+    """Stage-by-stage parity of the tcgen05 pipeline (bf16 I/O) against oracle intermediates."""
+    C, N, Co, No = SHAPES[shape]
+    BT = 4 if N >= 2304 else 10
+    cfg = O.make_config("ave", C, N, Co, No)
+    params = O.random_params(cfg, seed=5)
+    x, other = O.random_inputs(cfg, BT, seed=6)
+    xq, oq = x.bfloat16(), other.bfloat16()
+    p = to_dev(params)
+    out, smap, tmap, taps = adapter_forward_raw(cfg_dict(cfg), p, xq.cuda(), oq.cuda(), want_taps=True)
+    torch.cuda.synchronize()
+    from dgsct_b200 import _lib as L
+    assert L.lib().dgsct_tc_error_flag(1) == 0
+    ro, rs, _, _, inter = O.adapter_forward(cfg, params, xq.float(), oq.float(), want=True)
+    errs = {k: rel_l2(taps[k].cpu(), inter[k]) for k in ("V", "Tp", "X1", "obar", "m", "s", "Y")}
+    errs["out"] = rel_l2(out.float().cpu(), ro)
+    errs["smap"] = rel_l2(smap.float().cpu(), rs.reshape(smap.shape))
+    print(shape, {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v < TOL_BF16, (k, errs)
+
+
+@pytest.mark.parametrize("shape", ["vis_s1", "aud_s2"])
+def test_bf16_tensor_core_vs_simt_twin(shape):
+    C, N, Co, No = SHAPES[shape]
+    cfg = O.make_config("ave", C, N, Co, No)
+    p = to_dev(O.random_params(cfg, seed=5))
+    x, other = O.random_inputs(cfg, 10, seed=6)
+    xq, oq = x.bfloat16().cuda(), other.bfloat16().cuda()
+    o1, s1, _ = adapter_forward_raw(cfg_dict(cfg), p, xq, oq)
+    o2, s2, _ = adapter_forward_raw(cfg_dict(cfg), p, xq, oq, force_simt=True)
+    packed = adapter_forward_raw(cfg_dict(cfg), p, xq, oq, pack_only=True)
+    o3, s3, _ = adapter_forward_raw(cfg_dict(cfg), p, xq, oq, packed=packed)
+    torch.cuda.synchronize()
+    assert rel_l2(o1.float().cpu(), o2.float().cpu()) < TOL_BF16
+    assert rel_l2(o1.float().cpu(), o3.float().cpu()) < 2e-3     # pre-packed weights: same kernels
+
+
+@pytest.mark.parametrize("shape,dtype", [("vis_s2", torch.float32), ("aud_s2", torch.bfloat16), ("vis_s3", torch.bfloat16),
+                                         ("aud_s0", torch.bfloat16)])
 def test_train_mode_batch_stats(shape, dtype):
     cfg, out, smap, ro, rs, p, rstats = _run_shape(shape, dtype, 10, True)
     tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
@@ -103,13 +143,18 @@ def test_train_mode_batch_stats(shape, dtype):
         assert rel_l2(p[k].cpu(), v) < tol, k
 
 
-def test_variants_at_real_shape():
-    for variant, kw in [("s4", dict(use_bn=False, use_gate=False)), ("ms3", {}), ("pretrain", dict(K=2)),
-                        ("avqa", dict(K=2, g=4, use_bn=False, use_gate=False))]:
+VARIANT_CASES = [("s4", dict(use_bn=False, use_gate=False)), ("ms3", {}), ("pretrain", dict(K=2)),
+                 ("avqa", dict(K=2, g=4, use_bn=False, use_gate=False)), ("fewshot", dict(K=2, alpha=0.7, beta=0.2, gamma=0.4))]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_variants_at_real_shape(dtype):
+    for variant, kw in VARIANT_CASES:
         shape = "vis_s2"
-        cfg, out, smap, ro, rs, *_ = _run_shape(shape, torch.float32, 10, False, variant=variant, **kw)
-        assert rel_l2(out, ro) < 5e-5, variant
-        assert rel_l2(smap, rs) < 5e-5, variant
+        cfg, out, smap, ro, rs, *_ = _run_shape(shape, dtype, 10, False, variant=variant, **kw)
+        tol = 5e-5 if dtype == torch.float32 else TOL_BF16
+        assert rel_l2(out, ro) < tol, (variant, rel_l2(out, ro))
+        assert rel_l2(smap, rs) < tol, (variant, rel_l2(smap, rs))
 
 
 def test_module_contract_and_strided_inputs():
