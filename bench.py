@@ -282,6 +282,11 @@ def run_engine(args, rank, world, local_rank):
     ms_step = timed(step_resident, args.steps, args.warmup)
     launches = (L.launch_count() - n0) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop() if sampler else None
+    quick = os.environ.get("DGSCT_BENCH_QUICK") == "1"      # profiling runs under ncu: timed region only
+    if quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_step, "clips_per_s": world * args.B / (ms_step * 1e-3)}), flush=True)
+        return
     d2h = step_e2e()
     ms_e2e = timed(step_e2e, max(3, args.steps // 2), 3)
 

@@ -313,8 +313,9 @@ static tc::OperandDesc kmaj(const void* p, int rows, int cols, long long ld, lon
 static tc::OperandDesc mnmaj(const void* p, int k_rows, int mn_cols, long long ld, long long bs) {
   return tc::OperandDesc{p, 1, ld, bs, k_rows, mn_cols};
 }
-static tc::EpiStore tc_store(void* out, int out_bf16, long long ld, long long sb) {
-  tc::EpiStore e{}; e.out = out; e.out_bf16 = out_bf16; e.ld = ld; e.sb = sb; e.alpha = 1.f; e.act = ACT_NONE;
+template <bool OUT_BF16, bool COLSUM = false, bool STATS = false>
+static tc::EpiStore<OUT_BF16, false, COLSUM, STATS> tc_store(void* out, long long ld, long long sb) {
+  tc::EpiStore<OUT_BF16, false, COLSUM, STATS> e{}; e.out = out; e.ld = ld; e.sb = sb;
   return e;
 }
 
@@ -328,21 +329,6 @@ struct SimtTokUpdate {
         const float v = acc[i][j] + tok[(long long)k * C + c];
         o[(long long)b * K * C + (long long)k * C + c] = __float2bfloat16_rn(v);
         o2[(long long)b * K * C + (long long)k * C + c] = v;
-      }
-    }
-  }
-};
-struct TcAffineRelu {   // zr[b,m,n] = relu(acc*scale[n] + shift[n]) (bf16) ; optional fp32 tap of acc
-  bf16* zr; long long ldz, sbz; const float* scale; const float* shift; float* ztap; int Cd;
-  __device__ void begin(int, int, bool) {}
-  __device__ void end(int, int, bool) {}
-  __device__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int Nn) {
-    if (!row_ok) return;
-    for (int j = 0; j < 16; ++j) {
-      const int n = n0 + j;
-      if (n < Nn) {
-        if (ztap) ztap[((long long)b * (sbz / ldz) + m) * Cd + n] = v[j];
-        zr[(long long)b * sbz + (long long)m * ldz + n] = __float2bfloat16_rn(fmaxf(fmaf(v[j], scale[n], shift[n]), 0.f));
       }
     }
   }
@@ -397,7 +383,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
 
   // (R1) U[b] (N,Co) = Wres (N,No) . other[b] (No,Co) + b_res[n]
   {
-    tc::EpiStore te = tc_store(U, 1, Co, (long long)N * Co);
+    auto te = tc_store<true>(U, Co, (long long)N * Co);
     EpiBiasStore se = epi_store(U, 1, Co, (long long)N * Co);
     te.bias_m = se.bias_m = (d.flags & DGSCT_F_NO_CONV_BIAS) ? nullptr : P.resample_b;
     DGSCT_RC(gemm_auto(ST_RESAMPLE_CONV, "resample_conv", true, kmaj(Wres, N, No, pp.ld_res, 0),
@@ -405,7 +391,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   // (R2) V = U . Wfc^T + b_fc ; osum[b,c] = sum_n V
   {
-    tc::EpiStore te = tc_store(V, 1, C, (long long)N * C);
+    auto te = tc_store<true, true>(V, C, (long long)N * C);
     EpiBiasStore se = epi_store(V, 1, C, (long long)N * C);
     te.bias_n = se.bias_n = P.fc_b; te.colsum = se.colsum = osum; te.ncols_total = se.ncols_total = C;
     DGSCT_RC(gemm_auto(ST_RESAMPLE_FC, "resample_fc", true, kmaj(U, N, Co, Co, (long long)N * Co), kmaj(Wfc, C, Co, pp.ld_fc, 0),
@@ -415,7 +401,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   const bool tok_tc = (K == 32);
   // (T1) L[b,n,k] = V[b,n,:] . tok[k,:]  (fp32) ; P = softmax over tokens (bf16)
   {
-    tc::EpiStore te = tc_store(L, 0, K, (long long)N * K);
+    auto te = tc_store<false>(L, K, (long long)N * K);
     EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);
     DGSCT_RC(gemm_auto(ST_TOK_LOGITS, "tok_logits", tok_tc, kmaj(V, N, C, C, (long long)N * C), kmaj(Wtok, K, C, pp.ld_c, 0),
                        N, K, C, BT, te, se, st));
@@ -430,8 +416,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   // (T3) Tp[b,k,c] = tok[k,c] + sum_n P[b,n,k] V[b,n,c]     computed as D(c,k): both operands token-major
   {
-    tc::EpiStore te = tc_store(TpB, 1, C, (long long)K * C);
-    te.transposed = 1; te.add_t = P.tokens; te.add_ld = C; te.out2 = Tp; te.ld2 = C; te.sb2 = (long long)K * C;
+    tc::EpiTokUpdate te{TpB, Tp, P.tokens, C, K};
     // SIMT twin computes the same D(c,k) orientation: rows m = c, columns n = k
     SimtTokUpdate se{TpB, Tp, P.tokens, C, K};
     DGSCT_RC(gemm_auto(ST_TOK_UPDATE, "tok_update", tok_tc, mnmaj(V, N, C, C, (long long)N * C), mnmaj(Pb, N, K, K, (long long)N * K),
@@ -440,12 +425,12 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   if (taps && taps->Tp) DGSCT_RC(tap(Tp, 0, taps->Tp, (size_t)BT * K * C, st));
   // (T4a) Q[b,n,:] = softmax_k(x[b,n,:] . Tp[b,k,:])  (bf16, reuses the P buffer)
   if (tok_tc) {
-    tc::EpiRowSoftmax32 te{}; te.out = Pb; te.out_bf16 = 1; te.ld = K; te.sb = (long long)N * K;
+    tc::EpiRowSoftmax32 te{}; te.out = Pb; te.ld = K; te.sb = (long long)N * K;
     EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);   // unused twin (operands are always TMA-describable here)
     DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", true, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
                        N, K, C, BT, te, se, st));
   } else {
-    tc::EpiStore te = tc_store(L, 0, K, (long long)N * K);
+    auto te = tc_store<false>(L, K, (long long)N * K);
     EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);
     DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", false, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
                        N, K, C, BT, te, se, st));
@@ -458,7 +443,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   // (T4b) X1 = x + gate_av * Q . Tp
   {
-    tc::EpiResidual te{X1, x, 1, C, (long long)N * C, P.gate_av, 0.f};
+    tc::EpiResidual te{X1, (const bf16*)x, C, (long long)N * C, P.gate_av, 0.f};
     EpiResidual se{X1, x, 1, C, (long long)N * C, P.gate_av};
     DGSCT_RC(gemm_auto(ST_X_UPDATE, "x_update", tok_tc, kmaj(Pb, N, K, K, (long long)N * K), mnmaj(TpB, K, C, C, (long long)K * C),
                        N, C, K, BT, te, se, st));
@@ -482,7 +467,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   // (C2) qsum[b,c] = sum_n aq1[b,c] relu(X1[b,n,:] . Wv1[c,:] + b)
   {
-    tc::EpiReluMulColsum te{P.v1_b, aq1, qsum, C};
+    tc::EpiReluMulColsum te{P.v1_b, aq1, qsum, C, C};
     EpiReluMulColsum se{P.v1_b, aq1, qsum, C};
     DGSCT_RC(gemm_auto(ST_CHANNEL_QUERY, "channel_query", true, kmaj(X1, N, C, C, (long long)N * C), kmaj(Wv1, C, C, pp.ld_c, 0),
                        N, C, C, BT, te, se, st));
@@ -536,12 +521,12 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   // (B2) Z = Y . Wdown^T (dense block-diagonal) ; eval: Zr = relu(bn1(Z)) fused into the epilogue
   {
     if (fuse_bn1) {
-      TcAffineRelu te{Zr, ldz, (long long)N * ldz, bn1_scale, bn1_shift, taps ? taps->Z : nullptr, Cd};
+      tc::EpiAffineRelu te{Zr, ldz, N, bn1_scale, bn1_shift, taps ? taps->Z : nullptr, Cd};
       SimtAffineRelu se{Zr, ldz, (long long)N * ldz, bn1_scale, bn1_shift, taps ? taps->Z : nullptr, Cd};
       DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(V, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
                          N, Cd, C, BT, te, se, st));
     } else {
-      tc::EpiStore te = tc_store(Z, 0, Cd, (long long)N * Cd);
+      auto te = tc_store<false, false, true>(Z, Cd, (long long)N * Cd);
       EpiBiasStore se = epi_store(Z, 0, Cd, (long long)N * Cd);
       te.stat_sum = se.stat_sum = bn1_sum; te.stat_sq = se.stat_sq = bn1_sq;
       DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(V, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
@@ -556,11 +541,17 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   // (B3) Uo = Zr . Wup^T (dense block-diagonal) ; bn2 batch statistics in train mode
   {
-    tc::EpiStore te = tc_store(Uo, 0, C, (long long)N * C);
     EpiBiasStore se = epi_store(Uo, 0, C, (long long)N * C);
-    if (train && use_bn) { te.stat_sum = se.stat_sum = bn2_sum; te.stat_sq = se.stat_sq = bn2_sq; }
-    DGSCT_RC(gemm_auto(ST_UP, "up_sampler", true, kmaj(Zr, N, Cd, ldz, (long long)N * ldz), kmaj(Wup, C, Cd, pp.ld_up, 0),
-                       N, C, Cd, BT, te, se, st));
+    if (train && use_bn) {
+      auto te = tc_store<false, false, true>(Uo, C, (long long)N * C);
+      te.stat_sum = se.stat_sum = bn2_sum; te.stat_sq = se.stat_sq = bn2_sq;
+      DGSCT_RC(gemm_auto(ST_UP, "up_sampler", true, kmaj(Zr, N, Cd, ldz, (long long)N * ldz), kmaj(Wup, C, Cd, pp.ld_up, 0),
+                         N, C, Cd, BT, te, se, st));
+    } else {
+      auto te = tc_store<false>(Uo, C, (long long)N * C);
+      DGSCT_RC(gemm_auto(ST_UP, "up_sampler", true, kmaj(Zr, N, Cd, ldz, (long long)N * ldz), kmaj(Wup, C, Cd, pp.ld_up, 0),
+                         N, C, Cd, BT, te, se, st));
+    }
   }
   { StageScope _sc(ST_BN_FINALIZE, st); count_launch();
     bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, use_bn, train, bn2_sum, bn2_sq, count, P.bn2_w, P.bn2_b, P.bn2_rm,

@@ -20,7 +20,6 @@ namespace dgsct {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int THREADS = 128;
 constexpr int MAX_STAGES = 8;
 
 struct Params {
@@ -36,6 +35,7 @@ struct Params {
   int a_boxes, b_boxes, a_box_bytes, b_box_bytes;
   uint32_t tmem_cols;
   int* err_flag;                // device int set to non-zero when a bounded wait expires
+  int debug_mode;               // bring-up only: 1 = epilogue skips the TMEM loads, 2 = skips loads and functor
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -46,6 +46,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -108,6 +111,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&a)[16], float (&b)[16]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(r[16 + i]); }
+}
+
+// functors that must see a whole accumulator row in one thread declare `static constexpr bool kWholeRow = true`
+template <typename T, typename = void>
+struct epi_whole_row { static constexpr bool value = false; };
+template <typename T>
+struct epi_whole_row<T, decltype((void)T::kWholeRow)> { static constexpr bool value = T::kWholeRow; };
+
 // shared-memory matrix descriptor (tcgen05): start address, leading/stride byte offsets (16-B units),
 // descriptor version 1, swizzle mode in bits [61,64)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int sw_bytes) {
@@ -167,12 +192,19 @@ __device__ __forceinline__ int colsum16_owner_col(int lane) {
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
+// Persistent, warp-specialised: grid = #SMs (or fewer tiles); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+//   warp 0 (one lane)  TMA producer: runs ahead over (tile, k-block), bounded by the smem ring
+//   warp 1 (one lane)  MMA issuer: accumulates tile i into TMEM accumulator (i & 1)
+//   warps 2..5         epilogue: drain accumulator (i & 1) through the functor while the MMAs of tile i+1 run
 // EPI interface:
-//   void begin(int b, int m, bool row_ok)                       once per thread (row m of batch b)
+//   void begin(int b, int m, bool row_ok)                       once per thread per tile (row m of batch b)
 //   void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N)   16 consecutive columns, warp-convergent
 //   void end(int b, int m, bool row_ok)
+constexpr int EPI_WARPS = 8;   // two warps per TMEM lane group: a lone warp per scheduler cannot hide its own latencies
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+
 template <typename EPI>
-__global__ void __launch_bounds__(THREADS) gemm_tc_kernel(const __grid_constant__ Params p, EPI epi) {
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p, EPI epi_in) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -180,12 +212,14 @@ __global__ void __launch_bounds__(THREADS) gemm_tc_kernel(const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+  uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;        // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
-  const int n_blk = blockIdx.x, m_blk = blockIdx.y, b = blockIdx.z;
-  const int m0 = m_blk * BM, n0 = n_blk * p.BN;
   const int num_k = (p.K + p.BK - 1) / p.BK;
+  const int n_blocks = (p.N + p.BN - 1) / p.BN, m_blocks = (p.M + BM - 1) / BM;
+  const int tiles_per_batch = n_blocks * m_blocks;
+  const int num_tiles = tiles_per_batch * p.batch;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.mapA);
@@ -194,7 +228,10 @@ __global__ void __launch_bounds__(THREADS) gemm_tc_kernel(const __grid_constant_
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(tmem_full_bar), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
@@ -202,79 +239,125 @@ __global__ void __launch_bounds__(THREADS) gemm_tc_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_stride = p.tmem_cols / 2;   // columns between the two accumulators
 
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer =====
-    const int a_atom = p.a_sw / 2, b_atom = p.b_sw / 2;   // elements per swizzle row
-    bool ok = true;
-    for (int kb = 0; kb < num_k && ok; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (kb / p.stages) & 1;
-      ok = mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, p.err_flag);
-      if (!ok) break;
-      const uint32_t fb = smem_u32(&full_bar[s]);
-      mbar_expect_tx(fb, (uint32_t)(p.a_boxes * p.a_box_bytes + p.b_boxes * p.b_box_bytes));
-      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-      const uint32_t sb = sa + p.a_stage_bytes;
-      const int k0 = kb * p.BK;
-      if (p.a_mn_major) {
-        for (int j = 0; j < p.a_boxes; ++j)
-          tma_load_3d(sa + j * p.a_box_bytes, &p.mapA, m0 + j * a_atom, k0, p.a_batched ? b : 0, fb);
-      } else {
-        tma_load_3d(sa, &p.mapA, k0, m0, p.a_batched ? b : 0, fb);
-      }
-      if (p.b_mn_major) {
-        for (int j = 0; j < p.b_boxes; ++j)
-          tma_load_3d(sb + j * p.b_box_bytes, &p.mapB, n0 + j * b_atom, k0, p.b_batched ? b : 0, fb);
-      } else {
-        tma_load_3d(sb, &p.mapB, k0, n0, p.b_batched ? b : 0, fb);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      const int a_atom = p.a_sw / 2, b_atom = p.b_sw / 2;   // elements per swizzle row
+      const uint32_t tx_bytes = (uint32_t)(p.a_boxes * p.a_box_bytes + p.b_boxes * p.b_box_bytes);
+      int it = 0;   // running k-block counter across tiles (ring position)
+      bool ok = true;
+      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
+        const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+        const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          ok = mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, p.err_flag);
+          if (!ok) break;
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, tx_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + p.a_stage_bytes;
+          const int k0 = kb * p.BK;
+          if (p.a_mn_major) {
+            for (int j = 0; j < p.a_boxes; ++j)
+              tma_load_3d(sa + j * p.a_box_bytes, &p.mapA, m0 + j * a_atom, k0, p.a_batched ? b : 0, fb);
+          } else {
+            tma_load_3d(sa, &p.mapA, k0, m0, p.a_batched ? b : 0, fb);
+          }
+          if (p.b_mn_major) {
+            for (int j = 0; j < p.b_boxes; ++j)
+              tma_load_3d(sb + j * p.b_box_bytes, &p.mapB, n0 + j * b_atom, k0, p.b_batched ? b : 0, fb);
+          } else {
+            tma_load_3d(sb, &p.mapB, k0, n0, p.b_batched ? b : 0, fb);
+          }
+        }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc(p.BN, p.a_mn_major, p.b_mn_major);
-    // per-operand descriptor recipe
-    const uint32_t a_lbo = p.a_mn_major ? (uint32_t)p.a_box_bytes : 16u;
-    const uint32_t a_sbo = 8u * (uint32_t)p.a_sw;
-    const uint32_t a_kstep = p.a_mn_major ? 16u * (uint32_t)p.a_sw : 32u;   // bytes per UMMA_K (16 elements)
-    const uint32_t b_lbo = p.b_mn_major ? (uint32_t)p.b_box_bytes : 16u;
-    const uint32_t b_sbo = 8u * (uint32_t)p.b_sw;
-    const uint32_t b_kstep = p.b_mn_major ? 16u * (uint32_t)p.b_sw : 32u;
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc(p.BN, p.a_mn_major, p.b_mn_major);
+      const uint32_t a_lbo = p.a_mn_major ? (uint32_t)p.a_box_bytes : 16u;
+      const uint32_t a_sbo = 8u * (uint32_t)p.a_sw;
+      const uint32_t a_kstep = p.a_mn_major ? 16u * (uint32_t)p.a_sw : 32u;   // bytes per UMMA_K (16 elements)
+      const uint32_t b_lbo = p.b_mn_major ? (uint32_t)p.b_box_bytes : 16u;
+      const uint32_t b_sbo = 8u * (uint32_t)p.b_sw;
+      const uint32_t b_kstep = p.b_mn_major ? 16u * (uint32_t)p.b_sw : 32u;
+      const int ksteps = p.BK / 16;
+      int it = 0, ti = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        const uint32_t acc_ph = (ti >> 1) & 1;
+        ok = mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_ph ^ 1, p.err_flag);   // epilogue drained this accumulator
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
+        for (int kb = 0; kb < num_k; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          ok = mbar_wait(smem_u32(&full_bar[s]), ph, p.err_flag);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + p.a_stage_bytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, p.a_sw);
+            const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, p.b_sw);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage once these MMAs have read it
+        }
+        if (ok) umma_commit(smem_u32(&tmem_full_bar[acc]));   // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue warps: warp w owns TMEM lanes [32 (w % 4), +32); the two warps of a lane group take
+    // alternating 32-column blocks (functors that need a whole row in one thread set kWholeRow) =====
+    EPI epi = epi_in;
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const bool whole_row = epi_whole_row<EPI>::value;
+    int ti = 0;
     bool ok = true;
-    for (int kb = 0; kb < num_k && ok; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (kb / p.stages) & 1;
-      ok = mbar_wait(smem_u32(&full_bar[s]), ph, p.err_flag);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+      const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
+      const int acc = ti & 1;
+      const uint32_t acc_ph = (ti >> 1) & 1;
+      if (ok) ok = mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_ph, p.err_flag);
+      ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-      const uint32_t sb = sa + p.a_stage_bytes;
-      const int ksteps = p.BK / 16;
-      for (int k = 0; k < ksteps; ++k) {
-        const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, p.a_sw);
-        const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, p.b_sw);
-        umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+      const int m = m0 + lane_grp * 32 + lane;
+      const bool row_ok = m < p.M;
+      const uint32_t lane_base = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(lane_grp * 32) << 16);
+      if (p.debug_mode < 2 && !(whole_row && half == 1)) {
+        epi.begin(b, m, row_ok);
+        const int c_begin = whole_row ? 0 : half * 32, c_step = whole_row ? 32 : 64;
+        for (int c = c_begin; c < p.BN; c += c_step) {
+          float v0[16], v1[16];
+          const bool two = (c + 32 <= p.BN);
+          if (p.debug_mode == 0) {
+            if (two) tmem_ld32(lane_base + (uint32_t)c, v0, v1);
+            else tmem_ld16(lane_base + (uint32_t)c, v0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { v0[j] = (float)(c + j); v1[j] = (float)(c + 16 + j); }
+          }
+          epi.chunk(b, m, n0 + c, v0, row_ok, p.N);
+          if (two) epi.chunk(b, m, n0 + c + 16, v1, row_ok, p.N);
+        }
+        epi.end(b, m, row_ok);
       }
-      umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage once these MMAs have read it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
     }
-    umma_commit(smem_u32(tmem_full_bar));     // accumulator complete
   }
-  __syncwarp();
-
-  // ===== epilogue: all 4 warps, warp w owns TMEM lanes [32w, 32w+32) =====
-  const bool acc_ok = mbar_wait(smem_u32(tmem_full_bar), 0, p.err_flag);
-  __syncwarp();
-  tc_fence_after();
-  const int m = m0 + warp * 32 + lane;
-  const bool row_ok = acc_ok && (m < p.M);
-  epi.begin(b, m, row_ok);
-  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-  for (int c = 0; c < p.BN; c += 16) {
-    float v[16];
-    tmem_ld16(lane_base + (uint32_t)c, v);
-    epi.chunk(b, m, n0 + c, v, row_ok, p.N);
-  }
-  epi.end(b, m, row_ok);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
@@ -300,6 +383,7 @@ int* tc_err_flag_device_ptr();
 int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint = 0,
                 int stages_hint = 0);
 size_t smem_bytes(const Params& p);
+int num_sms();
 bool operands_ok(const OperandDesc& A, const OperandDesc& B, int K);
 
 template <typename EPI>
@@ -311,7 +395,8 @@ inline cudaError_t launch(const Params& p, EPI epi, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid(ceil_div(p.N, p.BN), ceil_div(p.M, BM), p.batch);
+  const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) * p.batch;
+  const int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
   gemm_tc_kernel<EPI><<<grid, THREADS, smem, st>>>(p, epi);
   return cudaGetLastError();
 }

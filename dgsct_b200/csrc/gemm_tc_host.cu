@@ -65,6 +65,18 @@ static int encode(CUtensorMap* map, const OperandDesc& o, int batch, int box0, i
 
 size_t smem_bytes(const Params& p) { return 1024 + (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 256; }
 
+int num_sms() {
+  static thread_local int n = 0, dev = -1;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (n == 0 || cur != dev) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, cur);
+    dev = cur;
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint,
                 int stages_hint) {
   if (!operands_ok(A, B, K)) return DGSCT_ERR_UNSUPPORTED;
@@ -91,16 +103,17 @@ int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, in
   p.b_stage_bytes = round_up(p.b_boxes * p.b_box_bytes, 1024);
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int num_k = (K + p.BK - 1) / p.BK;
-  int stages = stages_hint > 0 ? stages_hint : (96 * 1024) / stage_bytes;
+  int stages = stages_hint > 0 ? stages_hint : (200 * 1024) / stage_bytes;   // one persistent CTA per SM
   if (stages < 2) stages = 2;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > num_k && num_k >= 1) stages = num_k < 2 ? 2 : num_k;
+  (void)num_k;
   p.stages = stages;
   if (smem_bytes(p) > 227 * 1024) return DGSCT_ERR_UNSUPPORTED;
   uint32_t cols = 32;
-  while ((int)cols < BN) cols <<= 1;
+  while ((int)cols < 2 * BN) cols <<= 1;     // two accumulators (double-buffered epilogue)
   p.tmem_cols = cols;
   p.err_flag = tc_err_flag_device_ptr();
+  p.debug_mode = 0;
   int rc;
   if (A.mn_major) rc = encode(&p.mapA, A, batch, a_atom, p.BK, p.a_sw);
   else rc = encode(&p.mapA, A, batch, p.BK, BM, p.a_sw);
