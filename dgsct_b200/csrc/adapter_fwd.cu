@@ -50,6 +50,8 @@ FwdPlan make_fwd_plan(const dgsct_desc& d) {
     p.Zr = take(BT * N * (size_t)pad8((int)Cd) * 2);
     p.Uo32 = take(BT * N * C * 4);                    // up-sampler output stays fp32 until ln_post
     p.packed = take(make_pack_plan(d).total);
+    p.aq = take(BT * (C + H) * 4);
+    p.vec_bf = take(BT * (size_t)pad8((int)C) * 2);
   }
   p.total = off;
   return p;
@@ -174,7 +176,7 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
   // (C2) qsum[b,c] = sum_n aq1[b,c] * relu(X1[b,n,:] . Wv1[c,:] + b)            net_trans.py:594-595
   {
     GemmShape sh{N, C, C, BT, 1};
-    EpiReluMulColsum e{P.v1_b, aq1, qsum, C};
+    EpiReluMulColsum e{P.v1_b, aq1, qsum, C, C};
     DGSCT_GEMM(ST_CHANNEL_QUERY, sh, op(X1, C, 1, (long long)N * C, bf), op(P.v1_w, C, 1, 0, 0), AxIdentity{}, e, "channel_query");
   }
   // (C3) m = sigmoid(Wc relu(Wb q + bb) + bc)                                   net_trans.py:596-597
@@ -276,7 +278,12 @@ int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaSt
   rows(P.tokens, K, C, pp.tok, pp.ld_c);
   rows(P.v1_w, C, C, pp.v1, pp.ld_c);
   rows(P.v2_w, H, C, pp.v2, pp.ld_c);
-  count_launch(2);
+  rows(P.a1_w, C, C, pp.cat1, pp.ld_c);
+  rows(P.a2_w, H, C, pp.cat1 + (size_t)C * pp.ld_c * 2, pp.ld_c);
+  rows(P.bott_w, H, C, pp.bott, pp.ld_c);
+  rows(P.c_w, C, H, pp.catt, pp.ld_h);
+  count_launch(3);
+  concat2_f32_kernel<<<ceil_div(C + H, 256), 256, 0, st>>>(P.a1_b, C, P.a2_b, H, (float*)(packed + pp.cat1_bias));
   pack_grouped_kernel<<<ceil_div(Cd * pp.ld_c, 256), 256, 0, st>>>(P.down_w, Cd, C, d.g, (bf16*)(packed + pp.down), pp.ld_c);
   pack_grouped_kernel<<<ceil_div(C * pp.ld_up, 256), 256, 0, st>>>(P.up_w, C, Cd, d.g, (bf16*)(packed + pp.up), pp.ld_up);
   DGSCT_LAUNCH_CHECK("pack_params");
@@ -286,12 +293,12 @@ int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaSt
 // one product through the tcgen05 kernel, or through the SIMT kernel when TMA cannot describe the operands
 template <typename TE, typename SE>
 static int gemm_auto(int stage, const char* name, bool allow_tc, const tc::OperandDesc& A, const tc::OperandDesc& B, int M, int N,
-                     int K, int batch, TE te, SE se, cudaStream_t st) {
+                     int K, int batch, TE te, SE se, cudaStream_t st, int bn_hint = 0) {
   StageScope _sc(stage, st);
   count_launch();
   if (allow_tc) {
     tc::Params p;
-    const int rc = tc::make_params(p, A, B, M, N, K, batch);
+    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint);
     if (rc == DGSCT_OK) {
       cudaError_t e = tc::launch(p, te, st);
       if (e != cudaSuccess) { set_cuda_error(e, name); return DGSCT_ERR_CUDA; }
@@ -313,9 +320,9 @@ static tc::OperandDesc kmaj(const void* p, int rows, int cols, long long ld, lon
 static tc::OperandDesc mnmaj(const void* p, int k_rows, int mn_cols, long long ld, long long bs) {
   return tc::OperandDesc{p, 1, ld, bs, k_rows, mn_cols};
 }
-template <bool OUT_BF16, bool COLSUM = false, bool STATS = false>
-static tc::EpiStore<OUT_BF16, false, COLSUM, STATS> tc_store(void* out, long long ld, long long sb) {
-  tc::EpiStore<OUT_BF16, false, COLSUM, STATS> e{}; e.out = out; e.ld = ld; e.sb = sb;
+template <bool OUT_BF16, bool COLSUM = false, bool STATS = false, int ACT = ACT_NONE>
+static tc::EpiStore<OUT_BF16, ACT, COLSUM, STATS> tc_store(void* out, long long ld, long long sb) {
+  tc::EpiStore<OUT_BF16, ACT, COLSUM, STATS> e{}; e.out = out; e.ld = ld; e.sb = sb; e.alpha = 1.f;
   return e;
 }
 
@@ -361,7 +368,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   float* osum = (float*)(ws + pl.osum); float* qsum = (float*)(ws + pl.qsum); float* ssum = (float*)(ws + pl.ssum);
   double* bn1_sum = (double*)(ws + pl.bn1_sum); double* bn1_sq = (double*)(ws + pl.bn1_sq);
   double* bn2_sum = (double*)(ws + pl.bn2_sum); double* bn2_sq = (double*)(ws + pl.bn2_sq);
-  float* aq1 = (float*)(ws + pl.aq1); float* aq2 = (float*)(ws + pl.aq2); float* hbuf = (float*)(ws + pl.h);
+  float* hbuf = (float*)(ws + pl.h);
   float* mvec = (float*)(ws + pl.m); float* tau = (float*)(ws + pl.tau); float* sig = (float*)(ws + pl.sig);
   float* bn1_scale = (float*)(ws + pl.bn1_scale); float* bn1_shift = (float*)(ws + pl.bn1_shift);
   float* bn2_scale = (float*)(ws + pl.bn2_scale); float* bn2_shift = (float*)(ws + pl.bn2_shift);
@@ -449,14 +456,20 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
                        N, C, K, BT, te, se, st));
   }
   if (taps) DGSCT_RC(tap(X1, 1, taps->X1, (size_t)BT * N * C, st));
-  // (C1) small per-frame linears (fp32 SIMT): aq1, aq2, tau
+  // (C1) per-frame linears on tensor cores: [aq1 | aq2] = relu(obar [Wa1; Wa2]^T + b) ; tau stays SIMT (N = 1)
+  float* aq = (float*)(ws + pl.aq);
+  bf16* vecb = (bf16*)(ws + pl.vec_bf);
+  const int ldv = pad8(C);
+  const float* aq1 = aq; const float* aq2 = aq + C; const int aq_ld = C + H;
   {
-    GemmShape sh{BT, C, C, 1, 1};
-    EpiBiasStore e = epi_store(aq1, 0, C, 0); e.bias_n = P.a1_b; e.alpha = invN; e.act = ACT_RELU;
-    DGSCT_GEMM(ST_SMALL_LINEAR, sh, op(osum, C, 1, 0, 0), op(P.a1_w, C, 1, 0, 0), AxIdentity{}, e, "aq1");
-    GemmShape sh2{BT, H, C, 1, 1};
-    EpiBiasStore e2 = epi_store(aq2, 0, H, 0); e2.bias_n = P.a2_b; e2.alpha = invN; e2.act = ACT_RELU;
-    DGSCT_GEMM(ST_SMALL_LINEAR, sh2, op(osum, C, 1, 0, 0), op(P.a2_w, C, 1, 0, 0), AxIdentity{}, e2, "aq2");
+    { StageScope _sc(ST_SMALL_LINEAR, st); count_launch();
+      scale_to_bf16_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(osum, invN, vecb, (size_t)BT * C);
+      DGSCT_LAUNCH_CHECK("obar_bf16"); }
+    auto te = tc_store<false, false, false, ACT_RELU>(aq, aq_ld, 0);
+    te.bias_n = (const float*)(pk + pp.cat1_bias);
+    EpiBiasStore se = epi_store(aq, 0, aq_ld, 0); se.bias_n = te.bias_n; se.act = ACT_RELU;
+    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "aq12", true, kmaj(vecb, BT, C, C, 0), kmaj(pk + pp.cat1, C + H, C, pp.ld_c, 0),
+                       BT, C + H, C, 1, te, se, st, 64));
     if (d.flags & DGSCT_F_TEMPORAL) {
       GemmShape sh3{BT, 1, C, 1, 1};
       EpiBiasStore e3 = epi_store(tau, 0, 1, 0); e3.bias_n = P.t_b; e3.alpha = invN; e3.act = ACT_SIGMOID;
@@ -467,19 +480,27 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   // (C2) qsum[b,c] = sum_n aq1[b,c] relu(X1[b,n,:] . Wv1[c,:] + b)
   {
-    tc::EpiReluMulColsum te{P.v1_b, aq1, qsum, C, C};
-    EpiReluMulColsum se{P.v1_b, aq1, qsum, C};
+    tc::EpiReluMulColsum te{P.v1_b, aq1, qsum, C, aq_ld};
+    EpiReluMulColsum se{P.v1_b, aq1, qsum, C, aq_ld};
     DGSCT_RC(gemm_auto(ST_CHANNEL_QUERY, "channel_query", true, kmaj(X1, N, C, C, (long long)N * C), kmaj(Wv1, C, C, pp.ld_c, 0),
                        N, C, C, BT, te, se, st));
   }
-  // (C3) m = sigmoid(Wc relu(Wb q + bb) + bc)
+  // (C3) m = sigmoid(Wc relu(Wb q + bb) + bc)   (two small tensor-core linears, h kept in bf16)
   {
-    GemmShape sh{BT, H, C, 1, 1};
-    EpiBiasStore e = epi_store(hbuf, 0, H, 0); e.bias_n = P.bott_b; e.alpha = invN; e.act = ACT_RELU;
-    DGSCT_GEMM(ST_SMALL_LINEAR, sh, op(qsum, C, 1, 0, 0), op(P.bott_w, C, 1, 0, 0), AxIdentity{}, e, "channel_bottleneck");
-    GemmShape sh2{BT, C, H, 1, 1};
-    EpiBiasStore e2 = epi_store(mvec, 0, C, 0); e2.bias_n = P.c_b; e2.act = ACT_SIGMOID;
-    DGSCT_GEMM(ST_SMALL_LINEAR, sh2, op(hbuf, H, 1, 0, 0), op(P.c_w, H, 1, 0, 0), AxIdentity{}, e2, "channel_gate");
+    bf16* hb = (bf16*)hbuf;                 // (BT, ld_h) bf16 in the fp32-sized h buffer
+    { StageScope _sc(ST_SMALL_LINEAR, st); count_launch();
+      scale_to_bf16_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(qsum, invN, vecb, (size_t)BT * C);
+      DGSCT_LAUNCH_CHECK("q_bf16"); }
+    auto te = tc_store<true, false, false, ACT_RELU>(hb, pp.ld_h, 0);
+    te.bias_n = P.bott_b;
+    EpiBiasStore se = epi_store(hb, 1, pp.ld_h, 0); se.bias_n = P.bott_b; se.act = ACT_RELU;
+    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "channel_bottleneck", true, kmaj(vecb, BT, C, C, 0), kmaj(pk + pp.bott, H, C, pp.ld_c, 0),
+                       BT, H, C, 1, te, se, st, 64));
+    auto te2 = tc_store<false, false, false, ACT_SIGMOID>(mvec, C, 0);
+    te2.bias_n = P.c_b;
+    EpiBiasStore se2 = epi_store(mvec, 0, C, 0); se2.bias_n = P.c_b; se2.act = ACT_SIGMOID;
+    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "channel_gate", true, kmaj(hb, BT, H, pp.ld_h, 0), kmaj(pk + pp.catt, C, H, pp.ld_h, 0),
+                       BT, C, H, 1, te2, se2, st, 64));
   }
   if (taps && taps->m) DGSCT_RC(tap(mvec, 0, taps->m, (size_t)BT * C, st));
   // (S1) Xc = X1 (1+m) (bf16, in the U buffer) ; ssum[b,n] = sum_j ws[j] aq2[b,j] relu(Xc[b,n,:] . Wv2[j,:] + b)
@@ -488,8 +509,8 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
       scale_cols_kernel<<<2048, 256, 0, st>>>(X1, mvec, Xc, rowsBT, N, C);
       DGSCT_LAUNCH_CHECK("scale_cols"); }
-    tc::EpiSpatialRowsum te{P.v2_b, aq2, P.s_w, ssum, H, N, 0.f};
-    EpiSpatialRowsum se{P.v2_b, aq2, P.s_w, ssum, H, N};
+    tc::EpiSpatialRowsum te{P.v2_b, aq2, P.s_w, ssum, aq_ld, N, 0.f};
+    EpiSpatialRowsum se{P.v2_b, aq2, P.s_w, ssum, aq_ld, N};
     DGSCT_RC(gemm_auto(ST_SPATIAL_QUERY, "spatial_query", true, kmaj(Xc, N, C, C, (long long)N * C), kmaj(Wv2, H, C, pp.ld_c, 0),
                        N, H, C, BT, te, se, st));
   }
@@ -507,7 +528,8 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     a.rows = rowsBT; a.y_tap = taps ? taps->Y : nullptr;
     const int wpb = 4;
     StageScope _sc(ST_GATE_LN, st); count_launch();
-    gate_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
+    if (!launch_gate_ln_vec(a, st))
+      gate_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
     DGSCT_LAUNCH_CHECK("gate_ln");
   }
   const double count = (double)BT * (double)N;
@@ -567,7 +589,8 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     a.eps = d.eps_ln; a.C = C; a.rows = rowsBT;
     const int wpb = 4;
     StageScope _sc(ST_OUT_LN, st); count_launch();
-    out_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
+    if (!launch_out_ln_vec(a, st))
+      out_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
     DGSCT_LAUNCH_CHECK("out_ln");
   }
   return DGSCT_OK;

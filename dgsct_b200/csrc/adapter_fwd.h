@@ -9,7 +9,7 @@ struct FwdPlan {
   size_t bufA, bufV, bufX1, bufL, Tp, Z;
   size_t acc_begin, osum, qsum, ssum, bn1_sum, bn1_sq, bn2_sum, bn2_sq, acc_end;
   size_t aq1, aq2, h, m, tau, sig, bn1_scale, bn1_shift, bn2_scale, bn2_shift;
-  size_t Pb, TpB, Zr, Uo32, packed;   // tensor-core path: bf16 P/Q, bf16 latent tokens, bf16 relu(bn1(Z)), packed weights
+  size_t Pb, TpB, Zr, Uo32, packed, aq, vec_bf;   // aq: [aq1 | aq2] fp32 (BT, C+H); vec_bf: bf16 per-frame vectors   // tensor-core path: bf16 P/Q, bf16 latent tokens, bf16 relu(bn1(Z)), packed weights
   size_t total;
 };
 

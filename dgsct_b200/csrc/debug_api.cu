@@ -25,14 +25,14 @@ int dgsct_debug_gemm_bf16(const void* A, const void* B, float* D, int M, int N, 
     p.debug_mode = (bn_hint >> 20) & 3;
     cudaError_t err;
     if (out_bf16) {
-      tc::EpiStore<true, false, false, false> e{};
-      e.out = D; e.ld = N; e.sb = (long long)M * N;
+      tc::EpiStore<true, ACT_NONE, false, false> e{};
+      e.alpha = 1.f; e.out = D; e.ld = N; e.sb = (long long)M * N;
       if ((bn_hint >> 24) & 1) e.out = nullptr;   // timing experiment: no global stores
       if ((bn_hint >> 25) & 1) e.sb = 0;          // timing experiment: every frame writes the same (L2-resident) tile
       err = (use_tc == 2) ? tc::launch_np(p, e, st, stages_hint > 0 ? stages_hint : 96) : tc::launch(p, e, st);
     } else {
-      tc::EpiStore<false, false, false, false> e{};
-      e.out = D; e.ld = N; e.sb = (long long)M * N;
+      tc::EpiStore<false, ACT_NONE, false, false> e{};
+      e.alpha = 1.f; e.out = D; e.ld = N; e.sb = (long long)M * N;
       err = (use_tc == 2) ? tc::launch_np(p, e, st, stages_hint > 0 ? stages_hint : 96) : tc::launch(p, e, st);
     }
     if (err != cudaSuccess) { set_cuda_error(err, "debug_gemm_tc"); return DGSCT_ERR_CUDA; }

@@ -75,7 +75,7 @@ struct EpiResidual {
 
 // colsum[b,n] += sum_m relu(acc + bias[n]) * mul[b,n]     (channel-gate query, net_trans.py:594-595)
 struct EpiReluMulColsum {
-  const float* bias; const float* mul; float* colsum; int ncols;
+  const float* bias; const float* mul; float* colsum; int ncols; int mul_ld;
   __device__ __forceinline__ void operator()(int b, int gi, int m, int n, float (&acc)[4][4], int M, int N) const {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -86,7 +86,7 @@ struct EpiReluMulColsum {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (m + i < M) s += fmaxf(acc[i][j] + bj, 0.f);
-        s *= mul[(long long)b * ncols + gn];
+        s *= mul[(long long)b * mul_ld + gn];
       }
       s = colpair_sum(s);
       if ((threadIdx.x & 16) == 0 && gn < N) atomicAdd(&colsum[(long long)b * ncols + gn], s);
@@ -96,14 +96,14 @@ struct EpiReluMulColsum {
 
 // rowsum[b,m] += sum_n relu(acc + bias[n]) * mul[b,n] * w[n]   (spatial-gate logit, net_trans.py:602-605)
 struct EpiSpatialRowsum {
-  const float* bias; const float* mul; const float* w; float* rowsum; int ncols; int nrows;
+  const float* bias; const float* mul; const float* w; float* rowsum; int mul_ld; int nrows;
   __device__ __forceinline__ void operator()(int b, int gi, int m, int n, float (&acc)[4][4], int M, int N) const {
     float f[4], bj[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gn = n + j;
       const bool ok = gn < N;
-      f[j] = ok ? mul[(long long)b * ncols + gn] * w[gn] : 0.f;
+      f[j] = ok ? mul[(long long)b * mul_ld + gn] * w[gn] : 0.f;
       bj[j] = ok ? bias[gn] : 0.f;
     }
 #pragma unroll

@@ -7,7 +7,8 @@ namespace dgsct {
 // byte offsets of each packed matrix inside the packed-weights buffer; `ld*` are row pitches in elements
 struct PackPlan {
   size_t res, fc, tok, v1, v2, down, up, total;
-  int ld_res, ld_fc, ld_c, ld_up;
+  size_t cat1, bott, catt, cat1_bias;    // [a1_w; a2_w] (C+H, C), bottleneck (H, C), channel gate (C, H), [a1_b; a2_b] fp32
+  int ld_res, ld_fc, ld_c, ld_up, ld_h;
 };
 
 inline int pad8(int x) { return (x + 7) / 8 * 8; }
@@ -15,7 +16,7 @@ inline int pad8(int x) { return (x + 7) / 8 * 8; }
 inline PackPlan make_pack_plan(const dgsct_desc& d) {
   PackPlan p{};
   const size_t N = d.N, C = d.C, K = d.K, Cd = d.C / d.r, H = d.C / 2;
-  p.ld_res = pad8(d.No); p.ld_fc = pad8(d.Co); p.ld_c = pad8(d.C); p.ld_up = pad8((int)Cd);
+  p.ld_res = pad8(d.No); p.ld_fc = pad8(d.Co); p.ld_c = pad8(d.C); p.ld_up = pad8((int)Cd); p.ld_h = pad8((int)H);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   p.res = take(N * p.ld_res * 2);
@@ -25,6 +26,10 @@ inline PackPlan make_pack_plan(const dgsct_desc& d) {
   p.v2 = take(H * p.ld_c * 2);
   p.down = take(Cd * p.ld_c * 2);
   p.up = take(C * p.ld_up * 2);
+  p.cat1 = take((C + H) * p.ld_c * 2);
+  p.bott = take(H * p.ld_c * 2);
+  p.catt = take(C * p.ld_h * 2);
+  p.cat1_bias = take((C + H) * 4);
   p.total = off;
   return p;
 }
@@ -49,6 +54,18 @@ __global__ void pack_grouped_kernel(const float* __restrict__ src, int out_ch, i
     if (c < in_ch && c / ipg == o / opg) v = src[(size_t)o * ipg + (c - (o / opg) * ipg)];
     dst[i] = __float2bfloat16_rn(v);
   }
+}
+
+// dst bf16 = alpha * src fp32 (per-frame vectors feeding the small tensor-core linears)
+__global__ void scale_to_bf16_kernel(const float* __restrict__ src, float alpha, bf16* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(alpha * src[i]);
+}
+
+__global__ void concat2_f32_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < na) dst[i] = a[i];
+  else if (i < na + nb) dst[i] = b[i - na];
 }
 
 // out (rows, C) bf16 = x1 * (1 + m[b, c])          (net_trans.py:598, A operand of the spatial-gate GEMM)

@@ -179,3 +179,185 @@ __global__ void tap_copy_kernel(const void* __restrict__ src, int is_bf16, float
 }
 
 }  // namespace dgsct
+
+// ---- vectorised (16-byte) row kernels for the bf16 path ---------------------------------------------------
+// One warp per token row, each lane owns VPL vectors of 8 consecutive channels kept in registers; statistics by
+// warp shuffles.  Requires C % 8 == 0 and 16-byte aligned rows.
+namespace dgsct {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    f[2 * j] = __bfloat162float(t.x); f[2 * j + 1] = __bfloat162float(t.y);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+  return u;
+}
+__device__ __forceinline__ void ldf8(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) gate_ln_vec_kernel(GateLnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = a.C >> 3;
+  const bf16* x1 = reinterpret_cast<const bf16*>(a.x1);
+  bf16* y = reinterpret_cast<bf16*>(a.y);
+  for (long long row = warp0; row < a.rows; row += nwarps) {
+    const int b = (int)(row / a.N);
+    const float base = a.beta * a.sig[row] + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha;
+    float v[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const uint4 u = *reinterpret_cast<const uint4*>(x1 + row * a.C + vi * 8);
+        float mm[8];
+        unpack8(u, v[i]);
+        ldf8(a.m + (size_t)b * a.C + vi * 8, mm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] *= fmaf(a.alpha, mm[j], base); sum += v[i][j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln_w) {
+      mean = warp_sum(sum) / a.C;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; sq += dlt * dlt; }
+        }
+      rstd = rsqrtf(warp_sum(sq) / a.C + a.eps);
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        if (a.ln_w) {
+          float w[8], bb[8];
+          ldf8(a.ln_w + vi * 8, w);
+          ldf8(a.ln_b + vi * 8, bb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = fmaf((v[i][j] - mean) * rstd, w[j], bb[j]);
+        }
+        *reinterpret_cast<uint4*>(y + row * a.C + vi * 8) = pack8(v[i]);
+        if (a.y_tap) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a.y_tap[row * a.C + vi * 8 + j] = v[i][j];
+        }
+      }
+    }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) out_ln_vec_kernel(OutLnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int nvec = a.C >> 3;
+  const float* u = reinterpret_cast<const float*>(a.u);
+  bf16* out = reinterpret_cast<bf16*>(a.out);
+  const float g = a.gate ? a.gate[0] : 1.f;
+  const float gpre = a.gate_before_ln ? g : 1.f, gpost = a.gate_before_ln ? 1.f : g;
+  for (long long row = warp0; row < a.rows; row += nwarps) {
+    float v[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float sc[8], sh[8];
+        ldf8(u + row * a.C + vi * 8, v[i]);
+        ldf8(a.scale + vi * 8, sc);
+        ldf8(a.shift + vi * 8, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] = fmaf(v[i][j], sc[j], sh[j]) * gpre; sum += v[i][j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (a.ln_w) {
+      mean = warp_sum(sum) / a.C;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; sq += dlt * dlt; }
+        }
+      rstd = rsqrtf(warp_sum(sq) / a.C + a.eps);
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        if (a.ln_w) {
+          float w[8], bb[8];
+          ldf8(a.ln_w + vi * 8, w);
+          ldf8(a.ln_b + vi * 8, bb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = fmaf((v[i][j] - mean) * rstd, w[j], bb[j]) * gpost;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] *= gpost;
+        }
+        *reinterpret_cast<uint4*>(out + row * a.C + vi * 8) = pack8(v[i]);
+      }
+    }
+  }
+}
+
+// launch the vectorised kernel when the row width allows it; return false if the caller must use the scalar one
+inline bool launch_gate_ln_vec(const GateLnArgs& a, cudaStream_t st) {
+  if (a.C % 8 || !a.in_bf16 || !a.out_bf16 || a.C > 2048) return false;
+  const int vpl = (a.C / 8 + 31) / 32;
+  const long long blocks_needed = (a.rows + 7) / 8;
+  const unsigned grid = (unsigned)(blocks_needed < 148LL * 16 ? blocks_needed : 148LL * 16);
+  switch (vpl) {
+    case 1: gate_ln_vec_kernel<1><<<grid, 256, 0, st>>>(a); break;
+    case 2: gate_ln_vec_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: gate_ln_vec_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    case 4: gate_ln_vec_kernel<4><<<grid, 256, 0, st>>>(a); break;
+    case 5: case 6: gate_ln_vec_kernel<6><<<grid, 256, 0, st>>>(a); break;
+    default: gate_ln_vec_kernel<8><<<grid, 256, 0, st>>>(a); break;
+  }
+  return true;
+}
+inline bool launch_out_ln_vec(const OutLnArgs& a, cudaStream_t st) {
+  if (a.C % 8 || a.in_bf16 || !a.out_bf16 || a.C > 2048) return false;
+  const int vpl = (a.C / 8 + 31) / 32;
+  const long long blocks_needed = (a.rows + 7) / 8;
+  const unsigned grid = (unsigned)(blocks_needed < 148LL * 16 ? blocks_needed : 148LL * 16);
+  switch (vpl) {
+    case 1: out_ln_vec_kernel<1><<<grid, 256, 0, st>>>(a); break;
+    case 2: out_ln_vec_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    case 3: out_ln_vec_kernel<3><<<grid, 256, 0, st>>>(a); break;
+    case 4: out_ln_vec_kernel<4><<<grid, 256, 0, st>>>(a); break;
+    case 5: case 6: out_ln_vec_kernel<6><<<grid, 256, 0, st>>>(a); break;
+    default: out_ln_vec_kernel<8><<<grid, 256, 0, st>>>(a); break;
+  }
+  return true;
+}
+
+}  // namespace dgsct

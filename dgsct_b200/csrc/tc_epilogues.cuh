@@ -62,11 +62,12 @@ __device__ __forceinline__ void store_row16(void* out, size_t idx, const float (
 
 __device__ __forceinline__ int nvalid16(int n0, int N) { const int r = N - n0; return r < 0 ? 0 : (r > 16 ? 16 : r); }
 
-// out[b, m, n] = relu?(acc + bias_m[m] + bias_n[n])  (+ per-frame column sums, + global fp64 column moments)
-template <bool OUT_BF16, bool RELU, bool COLSUM, bool STATS>
+// out[b, m, n] = act(alpha*acc + bias_m[m] + bias_n[n])  (+ per-frame column sums, + global fp64 column moments)
+template <bool OUT_BF16, int ACT, bool COLSUM, bool STATS>
 struct EpiStore {
   void* out; long long ld, sb;
   const float* bias_m; const float* bias_n;
+  float alpha;
   float* colsum; int ncols_total;
   double* stat_sum; double* stat_sq;
   __device__ __forceinline__ void begin(int, int, bool) {}
@@ -78,12 +79,16 @@ struct EpiStore {
       float bn[16];
       load16_guard(bias_n + n0, bn, nvalid);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += bn[j];
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(alpha, v[j], bn[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= alpha;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float x = v[j] + bm;
-      if (RELU) x = fmaxf(x, 0.f);
+      if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
+      if (ACT == ACT_SIGMOID) x = __frcp_rn(1.f + __expf(-x));
       v[j] = x;
     }
     if (out && row_ok && nvalid > 0) store_row16<OUT_BF16>(out, (size_t)((long long)b * sb + (long long)m * ld + n0), v, nvalid);
