@@ -28,12 +28,15 @@ struct Params {
   int a_mn_major, b_mn_major;   // 0: K-major, 1: MN-major
   int a_sw, b_sw;               // swizzle span in bytes (128 or 64)
   int a_batched, b_batched;     // tensor-map coordinate 2 is the batch index (else 0)
-  int BN;                       // instruction / tile N (multiple of 16, <= 256)
+  int BN;                       // tile N per frame (multiple of 16, <= 256)
+  int fpack;                    // frames packed side by side along the instruction N (MN-major batched B, shared A)
   int BK;                       // K elements per pipeline stage (64 or 32)
   int stages;
   int a_stage_bytes, b_stage_bytes;
   int a_boxes, b_boxes, a_box_bytes, b_box_bytes;
   uint32_t tmem_cols;
+  int acc_bufs;                 // TMEM accumulators per CTA: 2 = epilogue overlaps the next tile's MMAs, 1 = single
+  int ctas_per_sm;              // 1: one big-smem CTA per SM; 2: two half-smem CTAs per SM (long-K products)
   int* err_flag;                // device int set to non-zero when a bounded wait expires
   int debug_mode;               // bring-up only: 1 = epilogue skips the TMEM loads, 2 = skips loads and functor
 };
@@ -204,7 +207,7 @@ constexpr int EPI_WARPS = 8;   // two warps per TMEM lane group: a lone warp per
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 
 template <typename EPI>
-__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p, EPI epi_in) {
+__global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_constant__ Params p, EPI epi_in) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,7 +222,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   const int num_k = (p.K + p.BK - 1) / p.BK;
   const int n_blocks = (p.N + p.BN - 1) / p.BN, m_blocks = (p.M + BM - 1) / BM;
   const int tiles_per_batch = n_blocks * m_blocks;
-  const int num_tiles = tiles_per_batch * p.batch;
+  const int fpack = p.fpack;                              // frames per tile (1 unless packed)
+  const int num_tiles = tiles_per_batch * ((p.batch + fpack - 1) / fpack);
+  const int BNI = p.BN * fpack;                           // instruction N
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.mapA);
@@ -239,17 +244,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc_stride = p.tmem_cols / 2;   // columns between the two accumulators
+  const uint32_t acc_stride = p.acc_bufs == 2 ? p.tmem_cols / 2 : 0;   // columns between the two accumulators
+  const int acc_bufs = p.acc_bufs;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
       const int a_atom = p.a_sw / 2, b_atom = p.b_sw / 2;   // elements per swizzle row
-      const uint32_t tx_bytes = (uint32_t)(p.a_boxes * p.a_box_bytes + p.b_boxes * p.b_box_bytes);
+      const uint32_t tx_bytes = (uint32_t)(p.a_boxes * p.a_box_bytes + fpack * p.b_boxes * p.b_box_bytes);
       int it = 0;   // running k-block counter across tiles (ring position)
       bool ok = true;
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+        const int b = (t / tiles_per_batch) * fpack, r = t % tiles_per_batch;
         const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
         for (int kb = 0; kb < num_k; ++kb, ++it) {
           const int s = it % p.stages;
@@ -268,8 +274,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             tma_load_3d(sa, &p.mapA, k0, m0, p.a_batched ? b : 0, fb);
           }
           if (p.b_mn_major) {
-            for (int j = 0; j < p.b_boxes; ++j)
-              tma_load_3d(sb + j * p.b_box_bytes, &p.mapB, n0 + j * b_atom, k0, p.b_batched ? b : 0, fb);
+            for (int f = 0; f < fpack; ++f)       // a frame past the batch is out of bounds for TMA: zero fill
+              for (int j = 0; j < p.b_boxes; ++j)
+                tma_load_3d(sb + (f * p.b_boxes + j) * p.b_box_bytes, &p.mapB, n0 + j * b_atom, k0, p.b_batched ? b + f : 0, fb);
           } else {
             tma_load_3d(sb, &p.mapB, k0, n0, p.b_batched ? b : 0, fb);
           }
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = make_idesc(p.BN, p.a_mn_major, p.b_mn_major);
+      const uint32_t idesc = make_idesc(BNI, p.a_mn_major, p.b_mn_major);
       const uint32_t a_lbo = p.a_mn_major ? (uint32_t)p.a_box_bytes : 16u;
       const uint32_t a_sbo = 8u * (uint32_t)p.a_sw;
       const uint32_t a_kstep = p.a_mn_major ? 16u * (uint32_t)p.a_sw : 32u;   // bytes per UMMA_K (16 elements)
@@ -290,8 +297,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       int it = 0, ti = 0;
       bool ok = true;
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x, ++ti) {
-        const int acc = ti & 1;
-        const uint32_t acc_ph = (ti >> 1) & 1;
+        const int acc = acc_bufs == 2 ? (ti & 1) : 0;
+        const uint32_t acc_ph = acc_bufs == 2 ? ((ti >> 1) & 1) : (ti & 1);
         ok = mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_ph ^ 1, p.err_flag);   // epilogue drained this accumulator
         if (!ok) break;
         tc_fence_after();
@@ -324,10 +331,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     int ti = 0;
     bool ok = true;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-      const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+      const int b0 = (t / tiles_per_batch) * fpack, r = t % tiles_per_batch;
       const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
-      const int acc = ti & 1;
-      const uint32_t acc_ph = (ti >> 1) & 1;
+      const int acc = acc_bufs == 2 ? (ti & 1) : 0;
+      const uint32_t acc_ph = acc_bufs == 2 ? ((ti >> 1) & 1) : (ti & 1);
       if (ok) ok = mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_ph, p.err_flag);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
@@ -336,11 +343,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       const bool row_ok = m < p.M;
       const uint32_t lane_base = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(lane_grp * 32) << 16);
       if (p.debug_mode < 2 && !(whole_row && half == 1)) {
-        epi.begin(b, m, row_ok);
+        epi.begin(b0, m, row_ok);
         const int c_begin = whole_row ? 0 : half * 32, c_step = whole_row ? 32 : 64;
-        for (int c = c_begin; c < p.BN; c += c_step) {
+        for (int c = c_begin; c < BNI; c += c_step) {
           float v0[16], v1[16];
-          const bool two = (c + 32 <= p.BN);
+          const bool two = (c + 32 <= BNI);
           if (p.debug_mode == 0) {
             if (two) tmem_ld32(lane_base + (uint32_t)c, v0, v1);
             else tmem_ld16(lane_base + (uint32_t)c, v0);
@@ -348,10 +355,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v0[j] = (float)(c + j); v1[j] = (float)(c + 16 + j); }
           }
-          epi.chunk(b, m, n0 + c, v0, row_ok, p.N);
-          if (two) epi.chunk(b, m, n0 + c + 16, v1, row_ok, p.N);
+          if (fpack == 1) {
+            epi.chunk(b0, m, n0 + c, v0, row_ok, p.N);
+            if (two) epi.chunk(b0, m, n0 + c + 16, v1, row_ok, p.N);
+          } else {                               // packed frames: 16-column chunks never straddle a frame (BN % 16 == 0)
+            const int f0 = c / p.BN, f1 = (c + 16) / p.BN;
+            epi.chunk(b0 + f0, m, c - f0 * p.BN, v0, row_ok && (b0 + f0 < p.batch), p.N);
+            if (two) epi.chunk(b0 + f1, m, c + 16 - f1 * p.BN, v1, row_ok && (b0 + f1 < p.batch), p.N);
+          }
         }
-        epi.end(b, m, row_ok);
+        epi.end(b0, m, row_ok);
       }
       tc_fence_before();
       __syncwarp();
@@ -395,8 +408,9 @@ inline cudaError_t launch(const Params& p, EPI epi, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) * p.batch;
-  const int grid = (int)(tiles < (long long)num_sms() ? tiles : (long long)num_sms());
+  const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) * ceil_div(p.batch, p.fpack);
+  const long long slots = (long long)num_sms() * p.ctas_per_sm;
+  const int grid = (int)(tiles < slots ? tiles : slots);
   gemm_tc_kernel<EPI><<<grid, THREADS, smem, st>>>(p, epi);
   return cudaGetLastError();
 }

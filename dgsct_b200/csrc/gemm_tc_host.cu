@@ -1,6 +1,8 @@
 // Host side of the tcgen05 GEMM: TMA tensor-map construction and tile recipe selection.
 #include "gemm_tc.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace dgsct {
@@ -99,18 +101,36 @@ int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, in
   else { p.a_boxes = 1; p.a_box_bytes = BM * p.BK * 2; }
   if (B.mn_major) { p.b_boxes = (BN + b_atom - 1) / b_atom; p.b_box_bytes = p.BK * p.b_sw; }
   else { p.b_boxes = 1; p.b_box_bytes = BN * p.BK * 2; }
+  // frame packing: when every frame's N fits several times in one instruction (N <= 128) and the A tile is shared,
+  // put f frames side by side (each frame's swizzle atoms are separate TMA boxes, so the layout is uniform)
+  p.fpack = 1;
+  if (B.mn_major && p.b_batched && !p.a_batched && N <= 128 && N == BN && batch > 1 && BN % b_atom == 0 && !getenv("DGSCT_NO_FPACK")) {
+    int f = 256 / BN;
+    if (f > batch) f = batch;
+    if (f > 4) f = 4;
+    p.fpack = f < 1 ? 1 : f;
+  }
   p.a_stage_bytes = round_up(p.a_boxes * p.a_box_bytes, 1024);
-  p.b_stage_bytes = round_up(p.b_boxes * p.b_box_bytes, 1024);
+  p.b_stage_bytes = round_up(p.fpack * p.b_boxes * p.b_box_bytes, 1024);
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int num_k = (K + p.BK - 1) / p.BK;
-  int stages = stages_hint > 0 ? stages_hint : (200 * 1024) / stage_bytes;   // one persistent CTA per SM
+  // Long-K products (main loop dominated, L2-latency sensitive) run two half-smem CTAs per SM: two independent
+  // TMA/MMA streams per SM hide each other's barrier round trips (968 vs 713 TFLOP/s on the stage-0 resampler).
+  // Short-K products keep one big-smem CTA per SM with a double-buffered accumulator.
+  const char* force = getenv("DGSCT_TC_CTAS");
+  p.ctas_per_sm = force ? atoi(force) : ((num_k >= 8 && 2 * stage_bytes <= 104 * 1024) ? 2 : 1);
+  if (p.ctas_per_sm != 2) p.ctas_per_sm = 1;
+  const int budget = p.ctas_per_sm == 2 ? 104 * 1024 : 200 * 1024;
+  int stages = stages_hint > 0 ? stages_hint : budget / stage_bytes;
   if (stages < 2) stages = 2;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  (void)num_k;
   p.stages = stages;
   if (smem_bytes(p) > 227 * 1024) return DGSCT_ERR_UNSUPPORTED;
+  const int BNI = BN * p.fpack;
+  const int max_cols = p.ctas_per_sm == 2 ? 256 : 512;
+  p.acc_bufs = (2 * BNI <= max_cols) ? 2 : 1;
   uint32_t cols = 32;
-  while ((int)cols < 2 * BN) cols <<= 1;     // two accumulators (double-buffered epilogue)
+  while ((int)cols < p.acc_bufs * BNI) cols <<= 1;
   p.tmem_cols = cols;
   p.err_flag = tc_err_flag_device_ptr();
   p.debug_mode = 0;

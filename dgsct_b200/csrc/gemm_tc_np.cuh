@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(128) gemm_tc_np_kernel(const __grid_constant__
 template <typename EPI>
 inline cudaError_t launch_np(Params p, EPI epi, cudaStream_t st, int smem_budget_kb) {
   static bool attr_set = false;
+  if (p.fpack != 1) return cudaErrorInvalidValue;   // the A/B kernel does not implement frame packing
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   int stages = (smem_budget_kb * 1024) / stage_bytes;
   if (stages < 2) stages = 2;

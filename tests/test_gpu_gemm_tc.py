@@ -53,6 +53,9 @@ CASES = [
     (256, 192, 256, 2, 0, 1, True, False),
     (144, 256, 256, 2, 0, 1, True, False),
     (64, 48, 36, 2, 0, 1, True, False),          # stage-3 audio resampler: K = 36 tokens
+    (300, 96, 200, 3, 0, 1, True, False),        # frame packing (2 frames per tile) with an odd batch
+    (130, 48, 70, 7, 0, 1, True, False),         # frame packing, 4 frames per tile, ragged last group
+    (260, 128, 130, 5, 0, 1, True, False),       # frame packing of 128-wide frames
     (192, 32, 300, 2, 1, 1, False, False),       # latent-token update: both operands token-major
     (100, 192, 32, 2, 0, 1, False, False),       # x update: K = 32
     (1536, 32, 36, 2, 1, 1, False, False),
