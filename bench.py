@@ -231,10 +231,22 @@ def run_engine(args, rank, world, local_rank):
         modules.append(m.to(dev).eval())
     BT = args.B * args.T
 
+    # The audio and visual adapters of one position read the same two token tensors and are independent
+    # (net_trans.py:891-892): they are issued on two streams and joined after every pair, as the interleave loop's
+    # data dependencies allow (the frozen backbone blocks sit between consecutive pairs).
+    s_aud, s_vis = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
     def step_resident():
-        for kind, s, p, pk in stack:
-            x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
-            adapter_forward_raw(ADAPTER_CFG, p, x, o, training=False, packed=pk)
+        cur = torch.cuda.current_stream(dev)
+        for i in range(0, len(stack), 2):
+            s_aud.wait_stream(cur)
+            s_vis.wait_stream(cur)
+            for (kind, s, p, pk), strm in ((stack[i], s_aud), (stack[i + 1], s_vis)):
+                x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
+                with torch.cuda.stream(strm):
+                    adapter_forward_raw(ADAPTER_CFG, p, x, o, training=False, packed=pk)
+            cur.wait_stream(s_aud)
+            cur.wait_stream(s_vis)
 
     h2d = sum(t.numel() * t.element_size() for t in vis_h + aud_h)
     last_maps = [None, None]
@@ -291,7 +303,7 @@ def run_engine(args, rank, world, local_rank):
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            step_resident()                      # warm the per-stream workspace outside the capture
+            step_resident()                      # warm the per-stream workspaces outside the capture
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):

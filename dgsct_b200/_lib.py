@@ -30,6 +30,15 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
 
 
+GRAD_FIELDS = ["resample_w", "resample_b", "fc_w", "fc_b", "a1_w", "a1_b", "v1_w", "v1_b", "bott_w", "bott_b", "v2_w", "v2_b",
+               "a2_w", "a2_b", "s_w", "s_b", "c_w", "c_b", "tokens", "gate_av", "gate", "down_w", "up_w", "bn1_w", "bn1_b",
+               "bn2_w", "bn2_b", "lnb_w", "lnb_b", "lnp_w", "lnp_b", "t_w", "t_b"]
+
+
+class Grads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in GRAD_FIELDS]
+
+
 TAP_FIELDS = ["V", "Tp", "X1", "obar", "m", "s", "Y", "Z"]
 
 
@@ -38,7 +47,7 @@ class Taps(C.Structure):
 
 
 EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgsct_workspace_bytes",
-           "dgsct_packed_bytes", "dgsct_pack_params",
+           "dgsct_packed_bytes", "dgsct_pack_params", "dgsct_bwd_workspace_bytes", "dgsct_adapter_bwd",
            "dgsct_adapter_fwd", "dgsct_bicubic_matrix", "dgsct_num_stages", "dgsct_stage_name",
            "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
            "dgsct_tc_error_flag"]
@@ -74,6 +83,11 @@ def lib() -> C.CDLL:
     L.dgsct_adapter_fwd.restype = C.c_int
     L.dgsct_adapter_fwd.argtypes = [C.POINTER(Desc), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.POINTER(Taps), C.c_void_p, C.c_size_t, C.c_void_p]
+    L.dgsct_bwd_workspace_bytes.restype = C.c_size_t
+    L.dgsct_bwd_workspace_bytes.argtypes = [C.POINTER(Desc)]
+    L.dgsct_adapter_bwd.restype = C.c_int
+    L.dgsct_adapter_bwd.argtypes = [C.POINTER(Desc), C.POINTER(Params)] + [C.c_void_p] * 8 + [C.POINTER(Grads), C.c_void_p,
+                                                                                             C.c_size_t, C.c_void_p]
     L.dgsct_packed_bytes.restype = C.c_size_t
     L.dgsct_packed_bytes.argtypes = [C.POINTER(Desc)]
     L.dgsct_pack_params.restype = C.c_int

@@ -77,13 +77,9 @@ def bicubic_matrix(n_in_side: int, n_out_side: int, device) -> torch.Tensor:
     return w
 
 
-def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor,
-                        training: bool = False, want_taps: bool = False, force_simt: bool = False,
-                        packed: Optional[torch.Tensor] = None, pack_only: bool = False):
-    """Token-major entry: x (BT,N,C), other (BT,No,Co) contiguous CUDA tensors (fp32 or bf16); ``params`` maps
-    reference state_dict names to fp32 CUDA tensors.  ``cfg`` keys: K, r, g, T, alpha, beta, gamma, resampler,
-    ln_before, ln_post, gate_before_ln, use_bn, use_gate, temporal, eps_ln, eps_bn, bn_momentum.
-    Returns (out (BT,N,C), smap (BT,N), tmap (BT,) fp32 | None[, taps dict])."""
+def _describe(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor, training: bool,
+              force_simt: bool = False):
+    """Validate the call and build the C-ABI descriptor + parameter table.  Returns (desc, params_struct, keep, x, other)."""
     if not (x.is_cuda and other.is_cuda):
         raise RuntimeError("dgsct_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
     if x.dtype != other.dtype or x.dtype not in (torch.float32, torch.bfloat16):
@@ -143,10 +139,23 @@ def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Ten
     if params["my_tokens"].shape[0] != d.K:
         raise ValueError("my_tokens rows != K")
     d.flags = flags
+    return d, P, keep, x, other
+
+
+def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor,
+                        training: bool = False, want_taps: bool = False, force_simt: bool = False,
+                        packed: Optional[torch.Tensor] = None, pack_only: bool = False):
+    """Token-major entry: x (BT,N,C), other (BT,No,Co) contiguous CUDA tensors (fp32 or bf16); ``params`` maps
+    reference state_dict names to fp32 CUDA tensors.  ``cfg`` keys: K, r, g, T, alpha, beta, gamma, resampler,
+    ln_before, ln_post, gate_before_ln, use_bn, use_gate, temporal, eps_ln, eps_bn, bn_momentum.
+    Returns (out (BT,N,C), smap (BT,N), tmap (BT,) fp32 | None[, taps dict])."""
+    d, P, keep, x, other = _describe(cfg, params, x, other, training, force_simt)
+    BT, N, Cc = x.shape
+    dev = x.device
     lib = L.lib()
     nbytes = lib.dgsct_workspace_bytes(C.byref(d))
     if nbytes == 0:
-        raise ValueError(f"dgsct: invalid adapter description C={Cc} N={N} Co={Co} No={No} K={d.K} r={d.r} g={d.g} T={d.T} BT={BT}")
+        raise ValueError(f"dgsct: invalid adapter description C={Cc} N={N} Co={d.Co} No={d.No} K={d.K} r={d.r} g={d.g} T={d.T} BT={BT}")
     stream = torch.cuda.current_stream(dev).cuda_stream
     if pack_only:
         pb = lib.dgsct_packed_bytes(C.byref(d))
@@ -185,20 +194,87 @@ def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Ten
     return out, smap, tmap
 
 
+# reverse of _PARAM_MAP for the gradient table (running stats have no gradient)
+_GRAD_NAMES = {v: k for k, v in _PARAM_MAP.items() if "running" not in k}
+
+
+def adapter_backward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor,
+                         d_out: torch.Tensor, d_smap: Optional[torch.Tensor] = None, d_tmap: Optional[torch.Tensor] = None,
+                         training: bool = True, packed: Optional[torch.Tensor] = None):
+    """Gradients of the adapter w.r.t. x, other and every parameter (dgsct_adapter_bwd).  The forward keeps no state:
+    the library recomputes it inside this call.  Returns (dx, dother, {state_dict name: fp32 grad})."""
+    d, P, keep, x, other = _describe(cfg, params, x, other, training)
+    dev = x.device
+    lib = L.lib()
+    d_out = d_out.to(x.dtype).contiguous()
+    if d_smap is not None:
+        d_smap = d_smap.to(x.dtype).contiguous()
+    if d_tmap is not None:
+        d_tmap = d_tmap.to(torch.float32).contiguous()
+    G = L.Grads()
+    grads: Dict[str, torch.Tensor] = {}
+    bicubic = cfg.get("resampler", "conv") == "bicubic"
+    for field, name in _GRAD_NAMES.items():
+        t = params.get(name)
+        if t is None or (bicubic and field in ("resample_w", "resample_b")):
+            continue
+        if field in ("t_w", "t_b") and not cfg.get("temporal", False):
+            continue
+        g = torch.zeros_like(t, dtype=torch.float32)
+        grads[name] = g
+        setattr(G, field, g.data_ptr())
+    nbytes = lib.dgsct_bwd_workspace_bytes(C.byref(d))
+    if nbytes == 0:
+        raise ValueError("dgsct: invalid adapter description for backward")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws = _workspace(dev, ("bwd", stream), nbytes + 256)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    dx = torch.empty_like(x)
+    dother = torch.empty_like(other)
+    with torch.cuda.device(dev):
+        rc = lib.dgsct_adapter_bwd(C.byref(d), C.byref(P), C.c_void_p(packed.data_ptr() if packed is not None else 0),
+                                   C.c_void_p(x.data_ptr()), C.c_void_p(other.data_ptr()), C.c_void_p(d_out.data_ptr()),
+                                   C.c_void_p(d_smap.data_ptr() if d_smap is not None else 0),
+                                   C.c_void_p(d_tmap.data_ptr() if d_tmap is not None else 0),
+                                   C.c_void_p(dx.data_ptr()), C.c_void_p(dother.data_ptr()), C.byref(G),
+                                   C.c_void_p(ws_ptr), C.c_size_t(nbytes), C.c_void_p(stream))
+    L.check(rc, "adapter_bwd")
+    return dx, dother, grads
+
+
 class _AdapterFn(torch.autograd.Function):
-    """Forward through the engine.  The backward kernels are not part of this build yet: asking for a gradient
-    raises instead of silently falling back to PyTorch autograd."""
+    """autograd bridge: forward and backward both run in libdgsct.so (no PyTorch autograd fallback).  The forward
+    saves only its inputs; the backward call recomputes the intermediates (activation recomputation)."""
 
     @staticmethod
-    def forward(ctx, module, xt, ot, *flat_params):
-        out, smap, tmap = adapter_forward_raw(module._cfg(), module._param_dict(), xt, ot, training=module.training)
-        ctx.mark_non_differentiable(*( [tmap] if tmap is not None else [] ))
-        return (out, smap, tmap) if tmap is not None else (out, smap)
+    def forward(ctx, module, names, xt, ot, *flat_params):
+        cfg, params = module._cfg(), module._param_dict()
+        packed = module._packed_weights(cfg, params, xt, ot)
+        out, smap, tmap = adapter_forward_raw(cfg, params, xt, ot, training=module.training, packed=packed)
+        ctx.module, ctx.names, ctx.training, ctx.packed = module, names, module.training, packed
+        ctx.save_for_backward(xt, ot)
+        if tmap is not None:
+            return out, smap, tmap
+        return out, smap
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError("dgsct_b200: adapter backward kernels are not implemented in this round; "
-                                  "run under torch.no_grad() / eval for now")
+    def backward(ctx, *gouts):
+        xt, ot = ctx.saved_tensors
+        module = ctx.module
+        cfg, params = module._cfg(), module._param_dict()
+        d_out = gouts[0]
+        if d_out is None:
+            d_out = torch.zeros_like(xt)
+        d_smap = gouts[1] if len(gouts) > 1 else None
+        d_tmap = gouts[2] if len(gouts) > 2 else None
+        dx, dother, grads = adapter_backward_raw(cfg, params, xt, ot, d_out, d_smap, d_tmap, training=ctx.training,
+                                                 packed=ctx.packed)
+        flat = []
+        for n in ctx.names:
+            g = grads.get(n)
+            p = params.get(n)
+            flat.append(g.view_as(p) if (g is not None and p is not None) else None)
+        return (None, None, dx, dother, *flat)
 
 
 class VisualAdapter(nn.Module):
@@ -304,7 +380,8 @@ class VisualAdapter(nn.Module):
         need_grad = torch.is_grad_enabled() and (x.requires_grad or vis_token.requires_grad or
                                                  any(p.requires_grad for p in self.parameters()))
         if need_grad:
-            res = _AdapterFn.apply(self, xt, ot, *[p for p in self.parameters()])
+            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            res = _AdapterFn.apply(self, tuple(n for n, _ in named), xt, ot, *[p for _, p in named])
         else:
             cfg, params = self._cfg(), self._param_dict()
             res = adapter_forward_raw(cfg, params, xt, ot, training=self.training,

@@ -1,0 +1,576 @@
+// Backward of VisualAdapter.forward (gradients w.r.t. x, vis_token and every parameter; reference = autograd of
+// DG-SCT/AVE/nets/net_trans.py:552-674).  The call first RE-RUNS the forward into its own workspace with a
+// non-aliasing plan (activation recomputation: the training forward keeps nothing and costs the same memory as
+// inference), then walks the stages in reverse.  Large products go through gemm_auto (tcgen05 when the operands are
+// bf16 and TMA-describable, SIMT otherwise); everything else is in bwd_kernels.cuh.
+// (textually included at the end of adapter_fwd.cu: one translation unit owns every header-defined kernel)
+#include "bwd_kernels.cuh"
+
+namespace dgsct {
+
+// ---- generic output epilogues for the backward products ------------------------------------------------------------
+enum { OUT_STORE = 0, OUT_ADD = 1, OUT_ATOMIC = 2 };
+
+// SIMT: value = alpha * acc * colscale[b, n] (+ resid[b,m,n]) (+ bcast[b, n]); store / add / atomicAdd; optionally
+// written transposed (out[b, n, m]).
+struct EpiOut {
+  void* out; int out_bf16; long long ld, sb; int mode; int transposed;
+  float alpha; const float* alpha_ptr;                  // alpha_ptr (device scalar) multiplies alpha when non-NULL
+  const float* colscale; int cs_ld;                     // per-frame per-column scale (1+m), or NULL
+  const void* resid; int resid_bf16;                    // same indexing as out
+  const float* bcast; int bc_ld; float bc_scale;        // + bc_scale * bcast[b, n]
+  __device__ __forceinline__ void operator()(int b, int gi, int m, int n, float (&acc)[4][4], int M, int N) const {
+    const float al = alpha * (alpha_ptr ? alpha_ptr[0] : 1.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gm = m + i, gn = n + j;
+        if (gm < M && gn < N) {
+          float v = al * acc[i][j];
+          if (colscale) v *= colscale[(long long)b * cs_ld + gn];
+          if (bcast) v += bc_scale * bcast[(long long)b * bc_ld + gn];
+          const size_t idx = transposed ? (size_t)((long long)b * sb + (long long)gn * ld + gm)
+                                        : (size_t)((long long)b * sb + (long long)gm * ld + gn);
+          if (resid) v += ld_act(resid, idx, resid_bf16);
+          if (mode == OUT_ATOMIC) atomicAdd(reinterpret_cast<float*>(out) + idx, v);
+          else if (mode == OUT_ADD) st_act(out, idx, ld_act(out, idx, out_bf16) + v, out_bf16);
+          else st_act(out, idx, v, out_bf16);
+        }
+      }
+  }
+};
+
+namespace tc {
+// tensor-core twin (row-major output only; transposed outputs use EpiOutT)
+template <bool OUT_BF16, int MODE, bool RESID, bool BCAST, bool CSCALE>
+struct EpiOut {
+  void* out; long long ld, sb; float alpha; const float* alpha_ptr; float al;
+  const float* colscale; int cs_ld; const bf16* resid; const float* bcast; int bc_ld; float bc_scale;
+  __device__ __forceinline__ void begin(int, int, bool) { al = alpha * (alpha_ptr ? alpha_ptr[0] : 1.f); }
+  __device__ __forceinline__ void end(int, int, bool) {}
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    if (!row_ok || nvalid <= 0) return;
+    const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= al;
+    if (CSCALE) {
+      float cs[16];
+      load16_guard(colscale + (long long)b * cs_ld + n0, cs, nvalid);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= cs[j];
+    }
+    if (BCAST) {
+      float bc[16];
+      load16_guard(bcast + (long long)b * bc_ld + n0, bc, nvalid);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(bc_scale, bc[j], v[j]);
+    }
+    if (RESID) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) v[j] += __bfloat162float(resid[idx + j]);
+    }
+    if (MODE == OUT_ATOMIC) {
+      float* o = reinterpret_cast<float*>(out) + idx;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) atomicAdd(o + j, v[j]);
+    } else {
+      if (MODE == OUT_ADD) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) v[j] += OUT_BF16 ? __bfloat162float(reinterpret_cast<const bf16*>(out)[idx + j])
+                                           : reinterpret_cast<const float*>(out)[idx + j];
+      }
+      store_row16<OUT_BF16>(out, idx, v, nvalid);
+    }
+  }
+};
+struct EpiNone {   // placeholder for products that never take the tensor-core kernel
+  __device__ __forceinline__ void begin(int, int, bool) {}
+  __device__ __forceinline__ void end(int, int, bool) {}
+  __device__ __forceinline__ void chunk(int, int, int, float (&)[16], bool, int) {}
+};
+// transposed: accumulator is D(m, n); writes out[b, n, m] (fp32) -- lanes are consecutive m: coalesced
+template <int MODE>
+struct EpiOutT {
+  float* out; long long ld, sb; float alpha; const float* alpha_ptr; float al;
+  __device__ __forceinline__ void begin(int, int, bool) { al = alpha * (alpha_ptr ? alpha_ptr[0] : 1.f); }
+  __device__ __forceinline__ void end(int, int, bool) {}
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    if (!row_ok) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) {
+        float* o = out + (long long)b * sb + (long long)(n0 + j) * ld + m;
+        if (MODE == OUT_ATOMIC) atomicAdd(o, al * v[j]);
+        else if (MODE == OUT_ADD) *o += al * v[j];
+        else *o = al * v[j];
+      }
+  }
+};
+}  // namespace tc
+
+// ---- dispatcher (same policy as the forward's gemm_auto) ------------------------------------------------------------
+struct Gemm {
+  int stage; const char* name; cudaStream_t st; bool allow_tc;
+};
+
+static GemmOperand simt_operand(const tc::OperandDesc& o, int is_bf16) {
+  return GemmOperand{o.ptr, o.mn_major ? 1 : o.ld, o.mn_major ? o.ld : 1, o.batch_stride, 0, is_bf16};
+}
+
+template <typename TE, typename AX>
+static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const tc::OperandDesc& B, int b_bf16, int M, int N, int K,
+                    int batch, TE te, const EpiOut& se, AX ax, bool ax_identity, int bn_hint = 0) {
+  StageScope _sc(g.stage, g.st);
+  count_launch();
+  if (g.allow_tc && a_bf16 && b_bf16 && ax_identity) {
+    tc::Params p;
+    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint);
+    if (rc == DGSCT_OK) {
+      cudaError_t e = tc::launch(p, te, g.st);
+      if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
+      return DGSCT_OK;
+    }
+    if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
+  }
+  GemmShape sh{M, N, K, batch, 1};
+  cudaError_t e = launch_gemm_simt(sh, simt_operand(A, a_bf16), simt_operand(B, b_bf16), ax, se, g.st);
+  if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
+  return DGSCT_OK;
+}
+
+static tc::OperandDesc K_(const void* p, int rows, int cols, long long ld, long long bs) { return tc::OperandDesc{p, 0, ld, bs, rows, cols}; }
+static tc::OperandDesc MN_(const void* p, int k_rows, int mn_cols, long long ld, long long bs) { return tc::OperandDesc{p, 1, ld, bs, k_rows, mn_cols}; }
+
+static EpiOut eo(void* out, int out_bf16, long long ld, long long sb, int mode) {
+  EpiOut e{}; e.out = out; e.out_bf16 = out_bf16; e.ld = ld; e.sb = sb; e.mode = mode; e.alpha = 1.f;
+  return e;
+}
+template <typename T>
+static T to_tc(const EpiOut& e) {   // copy the shared fields into a tensor-core functor
+  T t{}; t.out = e.out; t.ld = e.ld; t.sb = e.sb; t.alpha = e.alpha; t.alpha_ptr = e.alpha_ptr;
+  return t;
+}
+template <typename T>
+static T to_tc_full(const EpiOut& e) {
+  T t = to_tc<T>(e);
+  t.colscale = e.colscale; t.cs_ld = e.cs_ld; t.resid = (const bf16*)e.resid; t.bcast = e.bcast; t.bc_ld = e.bc_ld; t.bc_scale = e.bc_scale;
+  return t;
+}
+template <typename T>
+static T to_tcT(const EpiOut& e) {
+  T t{}; t.out = (float*)e.out; t.ld = e.ld; t.sb = e.sb; t.alpha = e.alpha; t.alpha_ptr = e.alpha_ptr;
+  return t;
+}
+
+#define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+#define KCHECK(name) DGSCT_LAUNCH_CHECK(name)
+
+struct BwdPlan {
+  size_t fwd;                        // keep-mode forward workspace
+  size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
+  size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, dWup_d, dWd_d, zero_end;
+  size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd;
+  size_t total;
+};
+
+static BwdPlan make_bwd_plan(const dgsct_desc& d) {
+  BwdPlan p{};
+  const size_t BT = d.BT, N = d.N, C = d.C, Co = d.Co, K = d.K, Cd = d.C / d.r, H = d.C / 2;
+  const size_t es = d.io_dtype == DGSCT_BF16 ? 2 : 4;
+  const size_t ldz = pad8((int)Cd);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  p.fwd = take(make_fwd_plan(d, true).total);
+  p.gUo = take(BT * N * C * es);
+  p.gZ = take(BT * N * ldz * es);
+  p.gY = take(BT * N * C * es);
+  p.gX1 = take(BT * N * C * es);
+  p.S1 = take(BT * N * C * es);          // z1 -> dz1 ; later dXc
+  p.S2 = take(BT * N * H * es);          // z2 -> dz2
+  p.gV = take(BT * N * C * es);
+  p.gU = take(BT * N * Co * es);
+  p.gQ = take(BT * N * K * es);          // dQraw -> dL2 ; later dL1
+  p.gP = take(BT * N * K * 4);           // dP fp32
+  p.dTp = take(BT * K * C * 4);
+  p.dTpB = take(BT * K * C * 2);
+  p.zero_begin = off;
+  p.dm = take(BT * C * 4); p.dsig = take(BT * N * 4); p.ds = take(BT * N * 4); p.dtau = take(BT * 4);
+  p.daq = take(BT * (C + H) * 4); p.dobar = take(BT * C * 4); p.dr1 = take(BT * C * 4);
+  p.colA = take(C * 4); p.colB = take(C * 4);
+  p.dWup_d = take(C * ldz * 4); p.dWd_d = take(Cd * C * 4);
+  p.zero_end = off;
+  p.vA = take(BT * C * 4); p.vB = take(BT * C * 4); p.vC = take(BT * C * 4); p.vD = take(BT * C * 4);
+  p.coefA = take(C * 4); p.coefB = take(C * 4); p.coefC = take(C * 4);
+  p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
+  p.opm = take(BT * C * 4);
+  p.out_fwd = take(BT * N * C * es); p.smap_fwd = take(BT * N * es); p.tmap_fwd = take(BT * 4);
+  p.total = off;
+  return p;
+}
+
+size_t bwd_workspace_bytes(const dgsct_desc& d) { return make_bwd_plan(d).total; }
+
+int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packed_in, const void* x, const void* other,
+                const void* dout, const void* dsmap, const float* dtmap, void* dx, void* dother, const dgsct_grads& G,
+                char* ws, cudaStream_t st) {
+  dgsct_desc d = d_in;
+  d.flags |= DGSCT_F_NO_STAT_UPDATE;                        // the recompute pass must not touch the running buffers
+  const BwdPlan bp = make_bwd_plan(d);
+  const FwdPlan fp = make_fwd_plan(d, true);
+  const PackPlan pp = make_pack_plan(d);
+  const int BT = d.BT, N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2, ldz = pad8(Cd);
+  const int bf = d.io_dtype == DGSCT_BF16;
+  const bool tcp = bf && !(d.flags & DGSCT_F_FORCE_SIMT);   // forward ran the tensor-core pipeline
+  if (bf && !tcp) return DGSCT_ERR_UNSUPPORTED;
+  const bool train = d.flags & DGSCT_F_TRAIN, use_bn = d.flags & DGSCT_F_USE_BN;
+  const long long R = (long long)BT * N;
+  const float invN = 1.f / (float)N;
+  char* fw = ws + bp.fwd;
+
+  // ---- 0. recompute the forward, keeping every intermediate ---------------------------------------------------
+  const char* pk = (const char*)packed_in;
+  if (tcp) {
+    if (!pk) { RC(pack_params(d, P, fw + fp.packed, st)); pk = fw + fp.packed; }
+    RC(adapter_fwd_tc(d, P, pk, x, other, ws + bp.out_fwd, ws + bp.smap_fwd, (float*)(ws + bp.tmap_fwd), nullptr, fw, st, true));
+  } else {
+    RC(adapter_fwd_simt(d, P, x, other, ws + bp.out_fwd, ws + bp.smap_fwd, (float*)(ws + bp.tmap_fwd), nullptr, fw, st, true));
+  }
+  // saved tensors (activation dtype unless noted)
+  const void* U = fw + fp.bufA; const void* V = fw + fp.bufV; const void* X1 = fw + fp.bufX1; const void* Y = fw + fp.Ybuf;
+  const void* Pm = tcp ? (const void*)(fw + fp.Pb) : (const void*)(fw + fp.bufL);
+  const void* Qm = tcp ? (const void*)(fw + fp.Qb) : (const void*)(fw + fp.Qf);
+  const float* Tp = (const float*)(fw + fp.Tp); const void* TpOp = tcp ? (const void*)(fw + fp.TpB) : (const void*)Tp;
+  const float* Z = (const float*)(fw + fp.Z); const float* Uo = (const float*)(fw + fp.Uo32);
+  const float* osum = (const float*)(fw + fp.osum); const float* r1sum = (const float*)(fw + fp.r1sum);
+  const float* aq1 = tcp ? (const float*)(fw + fp.aq) : (const float*)(fw + fp.aq1);
+  const float* aq2 = tcp ? aq1 + C : (const float*)(fw + fp.aq2);
+  const int aq_ld = tcp ? C + H : C, aq2_ld = tcp ? C + H : H;
+  const float* qvec = (const float*)(fw + fp.qvec); const float* mvec = (const float*)(fw + fp.m);
+  const float* ssum = (const float*)(fw + fp.ssum); const float* sig = (const float*)(fw + fp.sig); const float* tau = (const float*)(fw + fp.tau);
+  const float* sc1 = (const float*)(fw + fp.bn1_scale); const float* sh1 = (const float*)(fw + fp.bn1_shift);
+  const float* sc2 = (const float*)(fw + fp.bn2_scale); const float* sh2 = (const float*)(fw + fp.bn2_shift);
+  // h: fp32 (BT,H) in the SIMT path, bf16 (BT, ld_h) in the tensor-core path -> fp32 copy for the small products
+  float* hf = (float*)(ws + bp.vD);
+  if (tcp) {
+    StageScope _sc(ST_MISC, st); count_launch();
+    tap_copy_kernel<<<64, 256, 0, st>>>(fw + fp.h, 1, hf, (size_t)BT * pp.ld_h);   // (BT, ld_h) bf16 -> fp32, same pitch
+    KCHECK("h_f32");
+  }
+  const float* hsrc = tcp ? hf : (const float*)(fw + fp.h);
+  const int h_ld = tcp ? pp.ld_h : H;
+
+  void* gUo = ws + bp.gUo; void* gZ = ws + bp.gZ; void* gY = ws + bp.gY; void* gX1 = ws + bp.gX1;
+  void* S1 = ws + bp.S1; void* S2 = ws + bp.S2; void* gV = ws + bp.gV; void* gU = ws + bp.gU; void* gQ = ws + bp.gQ;
+  float* gP = (float*)(ws + bp.gP); float* dTp = (float*)(ws + bp.dTp); bf16* dTpB = (bf16*)(ws + bp.dTpB);
+  float* dm = (float*)(ws + bp.dm); float* dsig = (float*)(ws + bp.dsig); float* ds = (float*)(ws + bp.ds);
+  float* dtau = (float*)(ws + bp.dtau); float* daq = (float*)(ws + bp.daq); float* dobar = (float*)(ws + bp.dobar);
+  float* dr1 = (float*)(ws + bp.dr1); float* colA = (float*)(ws + bp.colA); float* colB = (float*)(ws + bp.colB);
+  float* dWup_d = (float*)(ws + bp.dWup_d); float* dWd_d = (float*)(ws + bp.dWd_d);
+  float* vA = (float*)(ws + bp.vA); float* vB = (float*)(ws + bp.vB); float* vC = (float*)(ws + bp.vC);
+  float* coefA = (float*)(ws + bp.coefA); float* coefB = (float*)(ws + bp.coefB); float* coefC = (float*)(ws + bp.coefC);
+  float* Wd_f = (float*)(ws + bp.Wd_f32); float* Wup_f = (float*)(ws + bp.Wup_f32); float* opm = (float*)(ws + bp.opm);
+  float* daq1 = daq; float* daq2 = daq + C; const int daq_ld = C + H;
+
+  { StageScope _sc(ST_MISC, st);
+    DGSCT_CUDA_CHECK(cudaMemsetAsync(ws + bp.zero_begin, 0, bp.zero_end - bp.zero_begin, st)); }
+  // weight operands: bf16 packed copies (tensor-core path) or fp32 masters / densified fp32 (SIMT path)
+  const void* Wup_op; const void* Wd_op; const void* Wv2_op; const void* Wv1_op; const void* Wfc_op; const void* Wres_op; const void* Tok_op;
+  int ld_up, ld_dn, ld_v, ld_fc, ld_res, ld_tok;
+  if (tcp) {
+    Wup_op = pk + pp.up; Wd_op = pk + pp.down; Wv2_op = pk + pp.v2; Wv1_op = pk + pp.v1; Wfc_op = pk + pp.fc; Wres_op = pk + pp.res;
+    Tok_op = pk + pp.tok; ld_up = pp.ld_up; ld_dn = pp.ld_c; ld_v = pp.ld_c; ld_fc = pp.ld_fc; ld_res = pp.ld_res; ld_tok = pp.ld_c;
+  } else {
+    StageScope _sc(ST_MISC, st); count_launch(2);
+    densify_grouped_kernel<<<ceil_div(Cd * C, 256), 256, 0, st>>>(P.down_w, Cd, C, d.g, Wd_f, C);
+    densify_grouped_kernel<<<ceil_div(C * ldz, 256), 256, 0, st>>>(P.up_w, C, Cd, d.g, Wup_f, ldz);
+    KCHECK("densify");
+    Wup_op = Wup_f; Wd_op = Wd_f; Wv2_op = P.v2_w; Wv1_op = P.v1_w; Wfc_op = P.fc_w; Wres_op = P.resample_w; Tok_op = P.tokens;
+    ld_up = ldz; ld_dn = C; ld_v = C; ld_fc = Co; ld_res = No; ld_tok = C;
+  }
+  const int wbf = tcp ? 1 : 0;
+  const Gemm GB{ST_MISC, "bwd_gemm", st, tcp};
+  const int rgrid = (int)((R + 7) / 8 < 148 * 4 ? (R + 7) / 8 : 148 * 4);
+  const int ew_grid = 148 * 8;
+
+  // ---- 1. output stage: gate, ln_post, bn2 ----------------------------------------------------------------------
+  {
+    BwdOutArgs a{};
+    a.dout = dout; a.dout_bf16 = bf; a.uo = Uo; a.scale = sc2; a.shift = sh2;
+    const bool lnp = d.flags & DGSCT_F_LN_POST;
+    a.ln_w = lnp ? P.lnp_w : nullptr; a.ln_b = lnp ? P.lnp_b : nullptr;
+    a.gate = (d.flags & DGSCT_F_USE_GATE) ? P.gate : nullptr;
+    a.gate_before_ln = (d.flags & DGSCT_F_GATE_BEFORE_LN) ? 1 : 0;
+    a.eps = d.eps_ln; a.C = C; a.rows = R; a.db2 = gUo; a.db2_bf16 = bf;
+    a.d_lnw = lnp ? G.lnp_w : nullptr; a.d_lnb = lnp ? G.lnp_b : nullptr; a.d_gate = a.gate ? G.gate : nullptr;
+    const int wpb = C <= 768 ? 8 : 4;
+    static bool attr1 = false;
+    if (!attr1) { DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr1 = true; }
+    StageScope _sc(ST_OUT_LN, st); count_launch();
+    { cudaError_t pre = cudaGetLastError(); if (pre != cudaSuccess) { set_cuda_error(pre, "before bwd_out"); return DGSCT_ERR_CUDA; } }
+    bwd_out_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
+    { cudaError_t e_ = cudaGetLastError();
+      if (e_ != cudaSuccess) {
+        fprintf(stderr, "bwd_out launch failed: grid %d block %d smem %zu C %d rows %lld\n", rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, C, (long long)R);
+        set_cuda_error(e_, "bwd_out"); return DGSCT_ERR_CUDA; } }
+  }
+  // bn2 backward: dUo = A*dB2 + B*Uo + Cc
+  if (use_bn) {
+    StageScope _sc(ST_BN_FINALIZE, st); count_launch(3);
+    col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, st>>>(gUo, bf, C, Uo, 0, C, R, C, colA, colB);
+    bn_bwd_coeffs_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, 1, train, colA, colB, (const float*)(fw + fp.bn2_mean),
+                                                           (const float*)(fw + fp.bn2_rstd), P.bn2_w, (double)R, coefA, coefB, coefC,
+                                                           G.bn2_w, G.bn2_b);
+    affine_combine_kernel<<<ew_grid, 256, 0, st>>>(gUo, bf, C, Uo, C, coefA, coefB, coefC, R, C);
+    KCHECK("bn2_bwd");
+  }
+  // ---- 2. up projection: dZr = dUo . Wup ; dWup += dUo^T . Zr ---------------------------------------------------
+  {
+    // Zr = relu(Z*sc1+sh1) as a GEMM operand: the tensor-core forward kept it (bf16, pitch ldz); the fp32 path
+    // rebuilds it into S2 (free until step 5)
+    const void* Zr = fw + fp.Zr;
+    if (!tcp) {
+      StageScope _sc(ST_MISC, st); count_launch();
+      bn_relu_f32_kernel<<<ew_grid, 256, 0, st>>>(Z, sc1, sh1, (float*)S2, R, Cd, ldz);
+      KCHECK("zr_f32");
+      Zr = S2;
+    }
+    EpiOut e1 = eo(gZ, bf, ldz, (long long)N * ldz, OUT_STORE);
+    RC(run_gemm(GB, K_(gUo, N, C, C, (long long)N * C), bf, MN_(Wup_op, C, Cd, ld_up, 0), wbf, N, Cd, C, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    EpiOut e2 = eo(dWup_d, 0, ldz, 0, OUT_ATOMIC);
+    RC(run_gemm(GB, MN_(gUo, N, C, C, (long long)N * C), bf, MN_(Zr, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true));
+    { StageScope _sc(ST_MISC, st); count_launch();
+      ungroup_grad_kernel<<<ceil_div(C * (Cd / d.g), 256), 256, 0, st>>>(dWup_d, C, Cd, d.g, ldz, G.up_w);
+      KCHECK("ungroup_up"); }
+  }
+  // relu + bn1 backward on dZr -> dZ (in place in gZ)
+  {
+    StageScope _sc(ST_BN_FINALIZE, st); count_launch(4);
+    relu_mask_kernel<<<ew_grid, 256, 0, st>>>(gZ, bf, ldz, Z, Cd, sc1, sh1, R, Cd);
+    if (use_bn) {
+      DGSCT_CUDA_CHECK(cudaMemsetAsync(colA, 0, (size_t)C * 4, st));
+      DGSCT_CUDA_CHECK(cudaMemsetAsync(colB, 0, (size_t)C * 4, st));
+      col_reduce_kernel<<<dim3(ceil_div(Cd, 32), 64), 256, 0, st>>>(gZ, bf, ldz, Z, 0, Cd, R, Cd, colA, colB);
+      bn_bwd_coeffs_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, 1, train, colA, colB, (const float*)(fw + fp.bn1_mean),
+                                                              (const float*)(fw + fp.bn1_rstd), P.bn1_w, (double)R, coefA, coefB, coefC,
+                                                              G.bn1_w, G.bn1_b);
+      affine_combine_kernel<<<ew_grid, 256, 0, st>>>(gZ, bf, ldz, Z, Cd, coefA, coefB, coefC, R, Cd);
+    }
+    KCHECK("bn1_bwd");
+  }
+  // ---- 3. down projection: dY = dZ . Wd ; dWd += dZ^T . Y --------------------------------------------------------
+  {
+    EpiOut e1 = eo(gY, bf, C, (long long)N * C, OUT_STORE);
+    RC(run_gemm(GB, K_(gZ, N, Cd, ldz, (long long)N * ldz), bf, MN_(Wd_op, Cd, C, ld_dn, 0), wbf, N, C, Cd, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    EpiOut e2 = eo(dWd_d, 0, C, 0, OUT_ATOMIC); e2.transposed = 1;      // D(c, cd) -> dWd_d[cd, c]
+    RC(run_gemm(GB, MN_(Y, N, C, C, (long long)N * C), bf, MN_(gZ, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
+                to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e2), e2, AxIdentity{}, true));
+    { StageScope _sc(ST_MISC, st); count_launch();
+      ungroup_grad_kernel<<<ceil_div(Cd * (C / d.g), 256), 256, 0, st>>>(dWd_d, Cd, C, d.g, C, G.down_w);
+      KCHECK("ungroup_down"); }
+  }
+  // ---- 4. ln_before + gate combine ------------------------------------------------------------------------------
+  const bool use_tau = (d.flags & DGSCT_F_TEMPORAL) && d.gamma != 0.f;
+  {
+    BwdGateLnArgs a{};
+    a.dy = gY; a.dy_bf16 = bf; a.x1 = X1; a.x1_bf16 = bf; a.m = mvec; a.sig = sig; a.tau = use_tau ? tau : nullptr;
+    const bool lnb = d.flags & DGSCT_F_LN_BEFORE;
+    a.ln_w = lnb ? P.lnb_w : nullptr;
+    a.alpha = d.alpha; a.beta = d.beta; a.gamma = d.gamma; a.eps = d.eps_ln; a.N = N; a.C = C; a.rows = R;
+    a.dx1 = gX1; a.dx1_bf16 = bf; a.dm_acc = dm; a.dsig = dsig; a.dtau = use_tau ? dtau : nullptr;
+    a.d_lnw = lnb ? G.lnb_w : nullptr; a.d_lnb = lnb ? G.lnb_b : nullptr;
+    const int wpb = C <= 768 ? 8 : 4;
+    static bool attr2 = false;
+    if (!attr2) { DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_gate_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr2 = true; }
+    StageScope _sc(ST_GATE_LN, st); count_launch();
+    bwd_gate_ln_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
+    KCHECK("bwd_gate_ln");
+  }
+  // ---- 5. spatial gate --------------------------------------------------------------------------------------------
+  {
+    { StageScope _sc(ST_SPATIAL_MAP, st); count_launch();
+      bwd_spatial_map_kernel<<<BT, 256, 0, st>>>(ssum, P.s_b, N, dsmap, bf, dsig, ds, G.s_b);
+      KCHECK("bwd_spatial_map"); }
+    // z2 = Xc . Wv2^T (pre-bias) -> S2
+    EpiOut e1 = eo(S2, bf, H, (long long)N * H, OUT_STORE);
+    if (tcp) {
+      RC(run_gemm(GB, K_(fw + fp.XcBuf, N, C, C, (long long)N * C), 1, K_(Wv2_op, H, C, ld_v, 0), 1, N, H, C, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    } else {
+      RC(run_gemm(GB, K_(X1, N, C, C, (long long)N * C), 0, K_(Wv2_op, H, C, ld_v, 0), 0, N, H, C, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, (AxOnePlusCol{mvec, C}), false));
+    }
+    { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
+      bwd_spatial_mask_kernel<<<dim3(ceil_div(H, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S2, bf, H, N, P.v2_b, ds, P.s_w, aq2, aq2_ld,
+                                                                                        G.s_w, daq2, daq_ld, G.v2_b);
+      KCHECK("bwd_spatial_mask"); }
+    // dXc = dz2 . Wv2 -> S1 ; dX1 += dXc (1+m) ; dm += sum_n dXc X1
+    EpiOut e2 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
+    RC(run_gemm(GB, K_(S2, N, H, H, (long long)N * H), bf, MN_(Wv2_op, H, C, ld_v, 0), wbf, N, C, H, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e2), e2, AxIdentity{}, true));
+    { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
+      bwd_xc_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, gX1, X1, bf, C, N, mvec, dm);
+      KCHECK("bwd_xc"); }
+    // opm = 1 + m
+    { StageScope _sc(ST_MISC, st); count_launch();
+      one_plus_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(mvec, opm, BT * C);
+      KCHECK("opm"); }
+    // dWv2[j,c] += sum_b (1+m[b,c]) sum_n dz2[b,n,j] X1[b,n,c]
+    EpiOut e3 = eo(G.v2_w, 0, C, 0, OUT_ATOMIC); e3.colscale = opm; e3.cs_ld = C;
+    RC(run_gemm(GB, MN_(S2, N, H, H, (long long)N * H), bf, MN_(X1, N, C, C, (long long)N * C), bf, H, C, N, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, true>>(e3), e3, AxIdentity{}, true));
+  }
+  // ---- 6. channel gate ---------------------------------------------------------------------------------------------
+  {
+    // dpm = dm * m (1-m) -> vA (BT,C)
+    const Gemm GS{ST_SMALL_LINEAR, "bwd_small", st, false};
+    StageScope _sc0(ST_SMALL_LINEAR, st);
+    count_launch();
+    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_SIGMOID_BWD, dm, C, mvec, C, 0.f, vA, C, BT, C);
+    KCHECK("dpm");
+    // d_cb += colsum dpm ; dWc (C,H) += dpm^T h ; dh = dpm . Wc -> vB (BT,H)
+    col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, st>>>(vA, 0, C, nullptr, 0, 0, BT, C, G.c_b, nullptr);
+    EpiOut e1 = eo(G.c_w, 0, H, 0, OUT_ADD);
+    RC(run_gemm(GS, MN_(vA, BT, C, C, 0), 0, MN_(hsrc, BT, H, h_ld, 0), 0, C, H, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
+    EpiOut e2 = eo(vB, 0, H, 0, OUT_STORE);
+    RC(run_gemm(GS, K_(vA, BT, C, C, 0), 0, MN_(P.c_w, C, H, H, 0), 0, BT, H, C, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
+    // dph = dh * 1[h>0] -> vB in place ; d_bb += colsum ; dWb (H,C) += dph^T q ; dq = dph . Wb -> vC (BT,C)
+    count_launch(2);
+    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, vB, H, hsrc, h_ld, 0.f, vB, H, BT, H);
+    col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, st>>>(vB, 0, H, nullptr, 0, 0, BT, H, G.bott_b, nullptr);
+    KCHECK("dph");
+    EpiOut e3 = eo(G.bott_w, 0, C, 0, OUT_ADD);
+    RC(run_gemm(GS, MN_(vB, BT, H, H, 0), 0, MN_(qvec, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
+    EpiOut e4 = eo(vC, 0, C, 0, OUT_STORE);
+    RC(run_gemm(GS, K_(vB, BT, H, H, 0), 0, MN_(P.bott_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e4, AxIdentity{}, true));
+    // q = aq1 * r1sum / N : daq1 = dq * r1sum / N ; dr1 = dq * aq1 / N
+    count_launch(2);
+    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_MUL_SCALE, vC, C, r1sum, C, invN, daq1, daq_ld, BT, C);
+    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_MUL_SCALE, vC, C, aq1, aq_ld, invN, dr1, C, BT, C);
+    KCHECK("dq_split");
+  }
+  {
+    // z1 = X1 . Wv1^T (pre-bias) -> S1 ; dz1 = dr1 * 1[z1+b>0] ; dX1 += dz1 . Wv1 ; dWv1 += dz1^T X1
+    EpiOut e1 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
+    RC(run_gemm(GB, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    { StageScope _sc(ST_CHANNEL_QUERY, st); count_launch();
+      bwd_channel_mask_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, bf, C, N, P.v1_b, dr1, G.v1_b);
+      KCHECK("bwd_channel_mask"); }
+    EpiOut e2 = eo(gX1, bf, C, (long long)N * C, OUT_ADD);
+    RC(run_gemm(GB, K_(S1, N, C, C, (long long)N * C), bf, MN_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
+                to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e2), e2, AxIdentity{}, true));
+    EpiOut e3 = eo(G.v1_w, 0, C, 0, OUT_ATOMIC);
+    RC(run_gemm(GB, MN_(S1, N, C, C, (long long)N * C), bf, MN_(X1, N, C, C, (long long)N * C), bf, C, C, N, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true));
+  }
+  {
+    // aq1 = relu(Wa1 obar + b), aq2 = relu(Wa2 obar + b), tau = sigmoid(wt obar + bt)   [obar = osum / N]
+    const Gemm GS{ST_SMALL_LINEAR, "bwd_small", st, false};
+    StageScope _sc0(ST_SMALL_LINEAR, st);
+    count_launch(3);
+    cast_scale_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(osum, invN, vA, 0, (size_t)BT * C);                     // obar -> vA
+    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_RELU_BWD, daq1, daq_ld, aq1, aq_ld, 0.f, vB, C, BT, C);  // dpa1 -> vB
+    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, daq2, daq_ld, aq2, aq2_ld, 0.f, vC, H, BT, H); // dpa2 -> vC
+    KCHECK("dpa");
+    count_launch(2);
+    col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, st>>>(vB, 0, C, nullptr, 0, 0, BT, C, G.a1_b, nullptr);
+    col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, st>>>(vC, 0, H, nullptr, 0, 0, BT, H, G.a2_b, nullptr);
+    EpiOut e1 = eo(G.a1_w, 0, C, 0, OUT_ADD);
+    RC(run_gemm(GS, MN_(vB, BT, C, C, 0), 0, MN_(vA, BT, C, C, 0), 0, C, C, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
+    EpiOut e2 = eo(G.a2_w, 0, C, 0, OUT_ADD);
+    RC(run_gemm(GS, MN_(vC, BT, H, H, 0), 0, MN_(vA, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
+    EpiOut e3 = eo(dobar, 0, C, 0, OUT_ADD);
+    RC(run_gemm(GS, K_(vB, BT, C, C, 0), 0, MN_(P.a1_w, C, C, C, 0), 0, BT, C, C, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
+    RC(run_gemm(GS, K_(vC, BT, H, H, 0), 0, MN_(P.a2_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
+    if (d.flags & DGSCT_F_TEMPORAL) {
+      count_launch();
+      temporal_bwd_kernel<<<BT, 128, 0, st>>>(use_tau ? dtau : nullptr, dtmap, tau, vA, P.t_w, C, dobar, G.t_w, G.t_b);
+      KCHECK("temporal_bwd");
+    }
+  }
+  // ---- 7. latent-token attention -----------------------------------------------------------------------------------
+  {
+    // dQraw = G . Tp^T -> gQ ; dL2 (in place) ; d_gate_av
+    EpiOut e1 = eo(gQ, bf, K, (long long)N * K, OUT_STORE);
+    RC(run_gemm(GB, K_(gX1, N, C, C, (long long)N * C), bf, K_(TpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    { StageScope _sc(ST_ROW_SOFTMAX, st); count_launch();
+      row_softmax_bwd_kernel<<<rgrid, 256, 0, st>>>(gQ, Qm, bf, R, K, P.gate_av, G.gate_av);
+      KCHECK("row_softmax_bwd"); }
+    // dTp[b,k,c] = g sum_n Q G + sum_n dL2 x     (computed as D(c,k), written transposed)
+    EpiOut e2 = eo(dTp, 0, C, (long long)K * C, OUT_STORE); e2.transposed = 1; e2.alpha_ptr = P.gate_av;
+    RC(run_gemm(GB, MN_(gX1, N, C, C, (long long)N * C), bf, MN_(Qm, N, K, K, (long long)N * K), bf, C, K, N, BT,
+                to_tcT<tc::EpiOutT<OUT_STORE>>(e2), e2, AxIdentity{}, true));
+    EpiOut e3 = eo(dTp, 0, C, (long long)K * C, OUT_ADD); e3.transposed = 1;
+    RC(run_gemm(GB, MN_(x, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
+                to_tcT<tc::EpiOutT<OUT_ADD>>(e3), e3, AxIdentity{}, true));
+    // dx = G + dL2 . Tp
+    EpiOut e4 = eo(dx, bf, C, (long long)N * C, OUT_STORE); e4.resid = gX1; e4.resid_bf16 = bf;
+    RC(run_gemm(GB, K_(gQ, N, K, K, (long long)N * K), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
+    // d tokens += sum_b dTp[b]
+    const void* dTpOp = dTp;
+    { StageScope _sc(ST_MISC, st); count_launch(2);
+      sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, st>>>(dTp, BT, (size_t)K * C, G.tokens);
+      if (tcp) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
+      KCHECK("dtok_sum"); }
+    // dP = V . dTp^T (fp32) ; dL1 = P (dP - sum_n dP P) -> gQ
+    EpiOut e5 = eo(gP, 0, K, (long long)N * K, OUT_STORE);
+    RC(run_gemm(GB, K_(V, N, C, C, (long long)N * C), bf, K_(dTpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
+                to_tc_full<tc::EpiOut<false, OUT_STORE, false, false, false>>(e5), e5, AxIdentity{}, true));
+    { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
+      if (K > 256) return DGSCT_ERR_UNSUPPORTED;
+      col_softmax_bwd_kernel<<<BT, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, gQ, bf, N, K);
+      KCHECK("col_softmax_bwd"); }
+    // dV = P . dTp + dL1 . T + dobar / N
+    EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
+    RC(run_gemm(GB, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
+    EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
+    RC(run_gemm(GB, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
+                to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
+    // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
+    EpiOut e8 = eo(G.tokens, 0, C, 0, OUT_ATOMIC); e8.transposed = 1;
+    RC(run_gemm(GB, MN_(V, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
+                to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true));
+  }
+  // ---- 8. token resampler ---------------------------------------------------------------------------------------------
+  {
+    { StageScope _sc(ST_MISC, st); count_launch();
+      col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, st>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
+      KCHECK("dfc_b"); }
+    // dU = dV . Wfc ; dWfc += dV^T . U
+    EpiOut e1 = eo(gU, bf, Co, (long long)N * Co, OUT_STORE);
+    RC(run_gemm(GB, K_(gV, N, C, C, (long long)N * C), bf, MN_(Wfc_op, C, Co, ld_fc, 0), wbf, N, Co, C, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    EpiOut e2 = eo(G.fc_w, 0, Co, 0, OUT_ATOMIC);
+    RC(run_gemm(GB, MN_(gV, N, C, C, (long long)N * C), bf, MN_(U, N, Co, Co, (long long)N * Co), bf, C, Co, N, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true));
+    // dWres += sum_b dU_b . other_b^T ; d_bres ; dother_b = Wres^T . dU_b
+    if (G.resample_w) {
+      EpiOut e3 = eo(G.resample_w, 0, No, 0, OUT_ATOMIC);
+      RC(run_gemm(GB, K_(gU, N, Co, Co, (long long)N * Co), bf, K_(other, No, Co, Co, (long long)No * Co), bf, N, No, Co, BT,
+                  to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true));
+    }
+    if (G.resample_b && !(d.flags & DGSCT_F_NO_CONV_BIAS)) {
+      StageScope _sc(ST_MISC, st); count_launch();
+      rowsum_frames_kernel<<<N, 256, 0, st>>>(gU, bf, BT, N, Co, G.resample_b);
+      KCHECK("dres_b");
+    }
+    EpiOut e4 = eo(dother, bf, Co, (long long)No * Co, OUT_STORE);
+    RC(run_gemm(GB, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gU, N, Co, Co, (long long)N * Co), bf, No, Co, N, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e4), e4, AxIdentity{}, true));
+  }
+  return DGSCT_OK;
+}
+
+}  // namespace dgsct

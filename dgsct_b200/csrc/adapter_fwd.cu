@@ -21,7 +21,7 @@ int validate_desc(const dgsct_desc* d) {
   return DGSCT_OK;
 }
 
-FwdPlan make_fwd_plan(const dgsct_desc& d) {
+FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
   FwdPlan p{};
   const size_t BT = d.BT, N = d.N, C = d.C, Co = d.Co, K = d.K, Cd = d.C / d.r, H = d.C / 2;
   const size_t es = d.io_dtype == DGSCT_BF16 ? 2 : 4;
@@ -36,6 +36,7 @@ FwdPlan make_fwd_plan(const dgsct_desc& d) {
   p.acc_begin = off;                                // ---- zero-initialised accumulators
   p.osum = take(BT * C * 4);
   p.qsum = take(BT * C * 4);
+  p.r1sum = p.qsum;                                 // same accumulator: sum_n relu(z1), unscaled
   p.ssum = take(BT * N * 4);
   p.bn1_sum = take(Cd * 8); p.bn1_sq = take(Cd * 8);
   p.bn2_sum = take(C * 8); p.bn2_sq = take(C * 8);
@@ -44,6 +45,14 @@ FwdPlan make_fwd_plan(const dgsct_desc& d) {
   p.tau = take(BT * 4); p.sig = take(BT * N * 4);
   p.bn1_scale = take(Cd * 4); p.bn1_shift = take(Cd * 4);
   p.bn2_scale = take(C * 4); p.bn2_shift = take(C * 4);
+  p.bn1_mean = take(Cd * 4); p.bn1_rstd = take(Cd * 4); p.bn2_mean = take(C * 4); p.bn2_rstd = take(C * 4);
+  p.qvec = take(BT * C * 4);
+  p.Ybuf = p.bufV; p.Qf = p.bufL; p.XcBuf = p.bufA;
+  if (keep) {
+    p.Ybuf = take(BT * N * C * es);
+    p.Qf = take(BT * N * K * 4);
+    if (d.io_dtype != DGSCT_BF16) p.Uo32 = take(BT * N * C * 4);
+  }
   if (d.io_dtype == DGSCT_BF16) {
     p.Pb = take(BT * N * K * 2);
     p.TpB = take(BT * K * C * 2);
@@ -52,6 +61,8 @@ FwdPlan make_fwd_plan(const dgsct_desc& d) {
     p.packed = take(make_pack_plan(d).total);
     p.aq = take(BT * (C + H) * 4);
     p.vec_bf = take(BT * (size_t)pad8((int)C) * 2);
+    p.Qb = p.Pb;
+    if (keep) { p.Qb = take(BT * N * K * 2); p.XcBuf = take(BT * N * C * 2); }
   }
   p.total = off;
   return p;
@@ -83,12 +94,16 @@ static int tap(const void* src, int is_bf16, float* dst, size_t n, cudaStream_t 
 }
 
 int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, const void* other, void* out,
-                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st) {
-  const FwdPlan pl = make_fwd_plan(d);
+                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep) {
+  const FwdPlan pl = make_fwd_plan(d, keep);
+  const int upd = (d.flags & DGSCT_F_NO_STAT_UPDATE) ? 0 : 1;
   const int BT = d.BT, N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2, G = d.g;
   const int bf = d.io_dtype == DGSCT_BF16;
   const bool train = d.flags & DGSCT_F_TRAIN, use_bn = d.flags & DGSCT_F_USE_BN;
   void* U = ws + pl.bufA; void* V = ws + pl.bufV; void* X1 = ws + pl.bufX1;
+  void* Yb = ws + pl.Ybuf; float* Lq = (float*)(ws + pl.Qf);
+  void* UoBuf = keep ? (void*)(ws + pl.Uo32) : U; const int uo_bf = keep ? 0 : bf;
+  float* qvec = (float*)(ws + pl.qvec);
   float* L = (float*)(ws + pl.bufL); float* Tp = (float*)(ws + pl.Tp); float* Z = (float*)(ws + pl.Z);
   float* osum = (float*)(ws + pl.osum); float* qsum = (float*)(ws + pl.qsum); float* ssum = (float*)(ws + pl.ssum);
   double* bn1_sum = (double*)(ws + pl.bn1_sum); double* bn1_sq = (double*)(ws + pl.bn1_sq);
@@ -137,20 +152,20 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
   // (T4a) L[b,n,k] = x[b,n,:] . Tp[b,k,:] ; softmax over k                      net_trans.py:583-585
   {
     GemmShape sh{N, K, C, BT, 1};
-    EpiBiasStore e = epi_store(L, 0, K, (long long)N * K);
+    EpiBiasStore e = epi_store(Lq, 0, K, (long long)N * K);
     DGSCT_GEMM(ST_X_LOGITS, sh, op(x, C, 1, (long long)N * C, bf), op(Tp, C, 1, (long long)K * C, 0), AxIdentity{}, e, "x_logits");
   }
   {
     const long long rows = (long long)BT * N;
     { StageScope _sc(ST_ROW_SOFTMAX, st); count_launch();
-  row_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(L, rows, K);
+  row_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(Lq, rows, K);
     DGSCT_LAUNCH_CHECK("row_softmax"); }
   }
   // (T4b) X1 = x + gate_av * Q . Tp                                             net_trans.py:586-589
   {
     GemmShape sh{N, C, K, BT, 1};
     EpiResidual e{X1, x, bf, C, (long long)N * C, P.gate_av};
-    DGSCT_GEMM(ST_X_UPDATE, sh, op(L, K, 1, (long long)N * K, 0), op(Tp, 1, C, (long long)K * C, 0), AxIdentity{}, e, "x_update");
+    DGSCT_GEMM(ST_X_UPDATE, sh, op(Lq, K, 1, (long long)N * K, 0), op(Tp, 1, C, (long long)K * C, 0), AxIdentity{}, e, "x_update");
   }
   if (taps) { int r = tap(X1, bf, taps->X1, (size_t)BT * N * C, st); if (r) return r; }
   // (C1) aq1 = relu(Wa1 obar + b), aq2 = relu(Wa2 obar + b), tau = sigmoid(wt obar + bt)   net_trans.py:593,603
@@ -176,14 +191,17 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
   // (C2) qsum[b,c] = sum_n aq1[b,c] * relu(X1[b,n,:] . Wv1[c,:] + b)            net_trans.py:594-595
   {
     GemmShape sh{N, C, C, BT, 1};
-    EpiReluMulColsum e{P.v1_b, aq1, qsum, C, C};
+    EpiReluMulColsum e{P.v1_b, nullptr, qsum, C, C};      // r1sum[b,c] = sum_n relu(z1), unscaled
     DGSCT_GEMM(ST_CHANNEL_QUERY, sh, op(X1, C, 1, (long long)N * C, bf), op(P.v1_w, C, 1, 0, 0), AxIdentity{}, e, "channel_query");
   }
   // (C3) m = sigmoid(Wc relu(Wb q + bb) + bc)                                   net_trans.py:596-597
   {
+    { StageScope _sc(ST_SMALL_LINEAR, st); count_launch();
+      channel_q_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(aq1, C, qsum, invN, qvec, nullptr, BT, C);
+      DGSCT_LAUNCH_CHECK("channel_q"); }
     GemmShape sh{BT, H, C, 1, 1};
-    EpiBiasStore e = epi_store(hbuf, 0, H, 0); e.bias_n = P.bott_b; e.alpha = invN; e.act = ACT_RELU;
-    DGSCT_GEMM(ST_SMALL_LINEAR, sh, op(qsum, C, 1, 0, 0), op(P.bott_w, C, 1, 0, 0), AxIdentity{}, e, "channel_bottleneck");
+    EpiBiasStore e = epi_store(hbuf, 0, H, 0); e.bias_n = P.bott_b; e.act = ACT_RELU;
+    DGSCT_GEMM(ST_SMALL_LINEAR, sh, op(qvec, C, 1, 0, 0), op(P.bott_w, C, 1, 0, 0), AxIdentity{}, e, "channel_bottleneck");
     GemmShape sh2{BT, C, H, 1, 1};
     EpiBiasStore e2 = epi_store(mvec, 0, C, 0); e2.bias_n = P.c_b; e2.act = ACT_SIGMOID;
     DGSCT_GEMM(ST_SMALL_LINEAR, sh2, op(hbuf, H, 1, 0, 0), op(P.c_w, H, 1, 0, 0), AxIdentity{}, e2, "channel_gate");
@@ -201,7 +219,7 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
   // (B1) Y = LN_before(X1 * (alpha m + beta sig + gamma tau + 1 - alpha))       net_trans.py:611-613, 626-627
   {
     GateLnArgs a{};
-    a.x1 = X1; a.in_bf16 = bf; a.y = V; a.out_bf16 = bf; a.m = mvec; a.sig = sig;
+    a.x1 = X1; a.in_bf16 = bf; a.y = Yb; a.out_bf16 = bf; a.m = mvec; a.sig = sig;
     a.tau = ((d.flags & DGSCT_F_TEMPORAL) && d.gamma != 0.f) ? tau : nullptr;
     const bool lnb = d.flags & DGSCT_F_LN_BEFORE;
     a.ln_w = lnb ? P.lnb_w : nullptr; a.ln_b = lnb ? P.lnb_b : nullptr;
@@ -217,31 +235,33 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
     GemmShape sh{N, Cd / G, C / G, BT, G};
     EpiBiasStore e = epi_store(Z, 0, Cd, (long long)N * Cd);
     if (train && use_bn) { e.stat_sum = bn1_sum; e.stat_sq = bn1_sq; }
-    DGSCT_GEMM(ST_DOWN, sh, op(V, C, 1, (long long)N * C, bf, C / G), op(P.down_w, C / G, 1, 0, 0, (long long)(Cd / G) * (C / G)),
+    DGSCT_GEMM(ST_DOWN, sh, op(Yb, C, 1, (long long)N * C, bf, C / G), op(P.down_w, C / G, 1, 0, 0, (long long)(Cd / G) * (C / G)),
                AxIdentity{}, e, "down_sampler");
   }
   if (taps && taps->Z) { int r = tap(Z, 0, taps->Z, (size_t)BT * N * Cd, st); if (r) return r; }
   const double count = (double)BT * (double)N;
   { StageScope _sc(ST_BN_FINALIZE, st); count_launch();
   bn_finalize_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, use_bn, train, bn1_sum, bn1_sq, count, P.bn1_w, P.bn1_b,
-                                                         P.bn1_rm, P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift);
+                                                         P.bn1_rm, P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift,
+                                                         (float*)(ws + pl.bn1_mean), (float*)(ws + pl.bn1_rstd), upd);
   DGSCT_LAUNCH_CHECK("bn1_finalize"); }
   // (B3) Uo = up_sampler(relu(bn1(Z))) ; bn2 batch statistics                   net_trans.py:638-643
   {
     GemmShape sh{N, C / G, Cd / G, BT, G};
-    EpiBiasStore e = epi_store(U, bf, C, (long long)N * C);
+    EpiBiasStore e = epi_store(UoBuf, uo_bf, C, (long long)N * C);
     if (train && use_bn) { e.stat_sum = bn2_sum; e.stat_sq = bn2_sq; }
     DGSCT_GEMM(ST_UP, sh, op(Z, Cd, 1, (long long)N * Cd, 0, Cd / G), op(P.up_w, Cd / G, 1, 0, 0, (long long)(C / G) * (Cd / G)),
                (AxAffineRelu{bn1_scale, bn1_shift, Cd / G}), e, "up_sampler");
   }
   { StageScope _sc(ST_BN_FINALIZE, st); count_launch();
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, use_bn, train, bn2_sum, bn2_sq, count, P.bn2_w, P.bn2_b,
-                                                        P.bn2_rm, P.bn2_rv, d.eps_bn, d.bn_momentum, bn2_scale, bn2_shift);
+                                                        P.bn2_rm, P.bn2_rv, d.eps_bn, d.bn_momentum, bn2_scale, bn2_shift,
+                                                        (float*)(ws + pl.bn2_mean), (float*)(ws + pl.bn2_rstd), upd);
   DGSCT_LAUNCH_CHECK("bn2_finalize"); }
   // (B4) out = gate * LN_post(bn2(Uo))  (or AVS order)                          net_trans.py:667-672
   {
     OutLnArgs a{};
-    a.u = U; a.in_bf16 = bf; a.out = out; a.out_bf16 = bf; a.scale = bn2_scale; a.shift = bn2_shift;
+    a.u = UoBuf; a.in_bf16 = uo_bf; a.out = out; a.out_bf16 = bf; a.scale = bn2_scale; a.shift = bn2_shift;
     const bool lnp = d.flags & DGSCT_F_LN_POST;
     a.ln_w = lnp ? P.lnp_w : nullptr; a.ln_b = lnp ? P.lnp_b : nullptr;
     a.gate = (d.flags & DGSCT_F_USE_GATE) ? P.gate : nullptr;
@@ -355,8 +375,9 @@ struct SimtAffineRelu {
 #define DGSCT_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packed_in, const void* x, const void* other,
-                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st) {
-  const FwdPlan pl = make_fwd_plan(d);
+                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep) {
+  const FwdPlan pl = make_fwd_plan(d, keep);
+  const int upd = (d.flags & DGSCT_F_NO_STAT_UPDATE) ? 0 : 1;
   const PackPlan pp = make_pack_plan(d);
   const int BT = d.BT, N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2;
   const int ldz = pad8(Cd);
@@ -364,6 +385,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   bf16* U = (bf16*)(ws + pl.bufA); bf16* V = (bf16*)(ws + pl.bufV); bf16* X1 = (bf16*)(ws + pl.bufX1);
   float* L = (float*)(ws + pl.bufL); float* Tp = (float*)(ws + pl.Tp); float* Z = (float*)(ws + pl.Z);
   bf16* Pb = (bf16*)(ws + pl.Pb); bf16* TpB = (bf16*)(ws + pl.TpB); bf16* Zr = (bf16*)(ws + pl.Zr);
+  bf16* Qb = (bf16*)(ws + pl.Qb); bf16* Yb = (bf16*)(ws + pl.Ybuf); float* qvec = (float*)(ws + pl.qvec);
   float* Uo = (float*)(ws + pl.Uo32);
   float* osum = (float*)(ws + pl.osum); float* qsum = (float*)(ws + pl.qsum); float* ssum = (float*)(ws + pl.ssum);
   double* bn1_sum = (double*)(ws + pl.bn1_sum); double* bn1_sq = (double*)(ws + pl.bn1_sq);
@@ -432,7 +454,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   if (taps && taps->Tp) DGSCT_RC(tap(Tp, 0, taps->Tp, (size_t)BT * K * C, st));
   // (T4a) Q[b,n,:] = softmax_k(x[b,n,:] . Tp[b,k,:])  (bf16, reuses the P buffer)
   if (tok_tc) {
-    tc::EpiRowSoftmax32 te{}; te.out = Pb; te.ld = K; te.sb = (long long)N * K;
+    tc::EpiRowSoftmax32 te{}; te.out = Qb; te.ld = K; te.sb = (long long)N * K;
     EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);   // unused twin (operands are always TMA-describable here)
     DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", true, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
                        N, K, C, BT, te, se, st));
@@ -445,14 +467,14 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     row_softmax_kernel<<<(unsigned)((rowsBT + 7) / 8), 256, 0, st>>>(L, rowsBT, K);
     // Q as bf16 for the next product
     pack_rows_kernel<<<(unsigned)(((size_t)rowsBT * K + 255) / 256 > 4096 ? 4096 : ((size_t)rowsBT * K + 255) / 256), 256, 0, st>>>(
-        L, (int)rowsBT, K, Pb, K);
+        L, (int)rowsBT, K, Qb, K);
     DGSCT_LAUNCH_CHECK("row_softmax");
   }
   // (T4b) X1 = x + gate_av * Q . Tp
   {
     tc::EpiResidual te{X1, (const bf16*)x, C, (long long)N * C, P.gate_av, 0.f};
     EpiResidual se{X1, x, 1, C, (long long)N * C, P.gate_av};
-    DGSCT_RC(gemm_auto(ST_X_UPDATE, "x_update", tok_tc, kmaj(Pb, N, K, K, (long long)N * K), mnmaj(TpB, K, C, C, (long long)K * C),
+    DGSCT_RC(gemm_auto(ST_X_UPDATE, "x_update", tok_tc, kmaj(Qb, N, K, K, (long long)N * K), mnmaj(TpB, K, C, C, (long long)K * C),
                        N, C, K, BT, te, se, st));
   }
   if (taps) DGSCT_RC(tap(X1, 1, taps->X1, (size_t)BT * N * C, st));
@@ -480,8 +502,8 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   // (C2) qsum[b,c] = sum_n aq1[b,c] relu(X1[b,n,:] . Wv1[c,:] + b)
   {
-    tc::EpiReluMulColsum te{P.v1_b, aq1, qsum, C, aq_ld};
-    EpiReluMulColsum se{P.v1_b, aq1, qsum, C, aq_ld};
+    tc::EpiReluMulColsum te{P.v1_b, nullptr, qsum, C, aq_ld};     // r1sum[b,c] = sum_n relu(z1), unscaled
+    EpiReluMulColsum se{P.v1_b, nullptr, qsum, C, aq_ld};
     DGSCT_RC(gemm_auto(ST_CHANNEL_QUERY, "channel_query", true, kmaj(X1, N, C, C, (long long)N * C), kmaj(Wv1, C, C, pp.ld_c, 0),
                        N, C, C, BT, te, se, st));
   }
@@ -489,8 +511,8 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   {
     bf16* hb = (bf16*)hbuf;                 // (BT, ld_h) bf16 in the fp32-sized h buffer
     { StageScope _sc(ST_SMALL_LINEAR, st); count_launch();
-      scale_to_bf16_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(qsum, invN, vecb, (size_t)BT * C);
-      DGSCT_LAUNCH_CHECK("q_bf16"); }
+      channel_q_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(aq1, aq_ld, qsum, invN, qvec, vecb, BT, C);
+      DGSCT_LAUNCH_CHECK("channel_q"); }
     auto te = tc_store<true, false, false, ACT_RELU>(hb, pp.ld_h, 0);
     te.bias_n = P.bott_b;
     EpiBiasStore se = epi_store(hb, 1, pp.ld_h, 0); se.bias_n = P.bott_b; se.act = ACT_RELU;
@@ -505,7 +527,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   if (taps && taps->m) DGSCT_RC(tap(mvec, 0, taps->m, (size_t)BT * C, st));
   // (S1) Xc = X1 (1+m) (bf16, in the U buffer) ; ssum[b,n] = sum_j ws[j] aq2[b,j] relu(Xc[b,n,:] . Wv2[j,:] + b)
   {
-    bf16* Xc = U;
+    bf16* Xc = (bf16*)(ws + pl.XcBuf);
     { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
       scale_cols_kernel<<<2048, 256, 0, st>>>(X1, mvec, Xc, rowsBT, N, C);
       DGSCT_LAUNCH_CHECK("scale_cols"); }
@@ -520,7 +542,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   // (B1) Y = LN_before(X1 * (alpha m + beta sig + gamma tau + 1 - alpha))  -> V buffer
   {
     GateLnArgs a{};
-    a.x1 = X1; a.in_bf16 = 1; a.y = V; a.out_bf16 = 1; a.m = mvec; a.sig = sig;
+    a.x1 = X1; a.in_bf16 = 1; a.y = Yb; a.out_bf16 = 1; a.m = mvec; a.sig = sig;
     a.tau = ((d.flags & DGSCT_F_TEMPORAL) && d.gamma != 0.f) ? tau : nullptr;
     const bool lnb = d.flags & DGSCT_F_LN_BEFORE;
     a.ln_w = lnb ? P.lnb_w : nullptr; a.ln_b = lnb ? P.lnb_b : nullptr;
@@ -533,11 +555,12 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     DGSCT_LAUNCH_CHECK("gate_ln");
   }
   const double count = (double)BT * (double)N;
-  const bool fuse_bn1 = !(train && use_bn);     // bn1 affine known before the down projection
+  const bool fuse_bn1 = !(train && use_bn) && !keep;     // bn1 affine known before the down projection
   if (fuse_bn1) {
     StageScope _sc(ST_BN_FINALIZE, st); count_launch();
     bn_finalize_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, use_bn, 0, bn1_sum, bn1_sq, count, P.bn1_w, P.bn1_b, P.bn1_rm,
-                                                           P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift);
+                                                           P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift,
+                                                           (float*)(ws + pl.bn1_mean), (float*)(ws + pl.bn1_rstd), upd);
     DGSCT_LAUNCH_CHECK("bn1_finalize");
   }
   // (B2) Z = Y . Wdown^T (dense block-diagonal) ; eval: Zr = relu(bn1(Z)) fused into the epilogue
@@ -545,18 +568,19 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     if (fuse_bn1) {
       tc::EpiAffineRelu te{Zr, ldz, N, bn1_scale, bn1_shift, taps ? taps->Z : nullptr, Cd};
       SimtAffineRelu se{Zr, ldz, (long long)N * ldz, bn1_scale, bn1_shift, taps ? taps->Z : nullptr, Cd};
-      DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(V, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
+      DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(Yb, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
                          N, Cd, C, BT, te, se, st));
     } else {
       auto te = tc_store<false, false, true>(Z, Cd, (long long)N * Cd);
       EpiBiasStore se = epi_store(Z, 0, Cd, (long long)N * Cd);
-      te.stat_sum = se.stat_sum = bn1_sum; te.stat_sq = se.stat_sq = bn1_sq;
-      DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(V, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
+      te.stat_sum = se.stat_sum = bn1_sum; te.stat_sq = se.stat_sq = bn1_sq;   // (harmless extra moments when BN is frozen)
+      DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(Yb, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
                          N, Cd, C, BT, te, se, st));
       if (taps && taps->Z) DGSCT_RC(tap(Z, 0, taps->Z, (size_t)BT * N * Cd, st));
       StageScope _sc(ST_BN_FINALIZE, st); count_launch(2);
-      bn_finalize_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, use_bn, 1, bn1_sum, bn1_sq, count, P.bn1_w, P.bn1_b, P.bn1_rm,
-                                                             P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift);
+      bn_finalize_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, use_bn, (train && use_bn) ? 1 : 0, bn1_sum, bn1_sq, count, P.bn1_w, P.bn1_b, P.bn1_rm,
+                                                             P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift,
+                                                             (float*)(ws + pl.bn1_mean), (float*)(ws + pl.bn1_rstd), upd);
       bn_relu_kernel<<<2048, 256, 0, st>>>(Z, bn1_scale, bn1_shift, Zr, rowsBT, Cd, ldz);
       DGSCT_LAUNCH_CHECK("bn1_finalize");
     }
@@ -577,7 +601,8 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   }
   { StageScope _sc(ST_BN_FINALIZE, st); count_launch();
     bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, use_bn, train, bn2_sum, bn2_sq, count, P.bn2_w, P.bn2_b, P.bn2_rm,
-                                                          P.bn2_rv, d.eps_bn, d.bn_momentum, bn2_scale, bn2_shift);
+                                                          P.bn2_rv, d.eps_bn, d.bn_momentum, bn2_scale, bn2_shift,
+                                                          (float*)(ws + pl.bn2_mean), (float*)(ws + pl.bn2_rstd), upd);
     DGSCT_LAUNCH_CHECK("bn2_finalize"); }
   {
     OutLnArgs a{};
@@ -597,3 +622,5 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
 }
 
 }  // namespace dgsct
+
+#include "adapter_bwd.inl"

@@ -9,20 +9,31 @@ struct FwdPlan {
   size_t bufA, bufV, bufX1, bufL, Tp, Z;
   size_t acc_begin, osum, qsum, ssum, bn1_sum, bn1_sq, bn2_sum, bn2_sq, acc_end;
   size_t aq1, aq2, h, m, tau, sig, bn1_scale, bn1_shift, bn2_scale, bn2_shift;
-  size_t Pb, TpB, Zr, Uo32, packed, aq, vec_bf;   // aq: [aq1 | aq2] fp32 (BT, C+H); vec_bf: bf16 per-frame vectors   // tensor-core path: bf16 P/Q, bf16 latent tokens, bf16 relu(bn1(Z)), packed weights
+  size_t Pb, TpB, Zr, Uo32, packed, aq, vec_bf;   // tensor-core path: bf16 P, bf16 latent tokens, bf16 relu(bn1(Z)), fp32 up-sampler
+                                                  // output, packed weights, [aq1 | aq2] fp32 (BT, C+H), bf16 per-frame vectors
+  // Regions that alias others unless the plan is built with keep = true (training forward: everything the
+  // backward needs survives the call): Y (else the V buffer), Q fp32 / bf16 (else the P buffers), Xc (else U).
+  size_t Ybuf, Qf, Qb, XcBuf;
+  size_t r1sum, qvec;                             // sum_n relu(z1) (BT,C) ; q = aq1 * r1sum / N (BT,C) fp32
+  size_t bn1_mean, bn1_rstd, bn2_mean, bn2_rstd;  // statistics used by the two BatchNorms (batch or running)
   size_t total;
 };
 
 int validate_desc(const dgsct_desc* d);
-FwdPlan make_fwd_plan(const dgsct_desc& d);
+FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep = false);
 
 // bf16 tensor-core pipeline (tcgen05 GEMMs); `packed` = pre-packed bf16 weights or NULL (packed per call)
 int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packed, const void* x, const void* other,
-                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st);
+                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep = false);
 int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaStream_t st);
 size_t packed_bytes(const dgsct_desc& d);
 
 int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, const void* other, void* out,
-                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st);
+                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep = false);
+
+size_t bwd_workspace_bytes(const dgsct_desc& d);
+int adapter_bwd(const dgsct_desc& d, const dgsct_params& P, const void* packed, const void* x, const void* other,
+                const void* dout, const void* dsmap, const float* dtmap, void* dx, void* dother, const dgsct_grads& G,
+                char* ws, cudaStream_t st);
 
 }  // namespace dgsct

@@ -79,6 +79,33 @@ int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const 
   return adapter_fwd_simt(d, P, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream);
 }
 
+size_t dgsct_bwd_workspace_bytes(const dgsct_desc* desc) {
+  if (validate_desc(desc) != DGSCT_OK) return 0;
+  return bwd_workspace_bytes(*desc);
+}
+
+int dgsct_adapter_bwd(const dgsct_desc* desc, const dgsct_params* params, const void* packed, const void* x, const void* other,
+                      const void* d_out, const void* d_spatial_map, const float* d_temporal_map, void* dx, void* dother,
+                      const dgsct_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate_desc(desc);
+  if (rc != DGSCT_OK) return rc;
+  if (!params || !x || !other || !d_out || !dx || !dother || !grads || !workspace) return DGSCT_ERR_NULL;
+  const dgsct_desc& d = *desc;
+  const dgsct_grads& G = *grads;
+  if (!G.fc_w || !G.fc_b || !G.a1_w || !G.a1_b || !G.v1_w || !G.v1_b || !G.bott_w || !G.bott_b || !G.v2_w || !G.v2_b ||
+      !G.a2_w || !G.a2_b || !G.s_w || !G.s_b || !G.c_w || !G.c_b || !G.tokens || !G.gate_av || !G.down_w || !G.up_w)
+    return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_USE_GATE) && !G.gate) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_USE_BN) && (!G.bn1_w || !G.bn1_b || !G.bn2_w || !G.bn2_b)) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_LN_BEFORE) && (!G.lnb_w || !G.lnb_b)) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_LN_POST) && (!G.lnp_w || !G.lnp_b)) return DGSCT_ERR_NULL;
+  if ((d.flags & DGSCT_F_TEMPORAL) && (!G.t_w || !G.t_b)) return DGSCT_ERR_NULL;
+  if (workspace_bytes < bwd_workspace_bytes(d) || ((uintptr_t)workspace & 255)) return DGSCT_ERR_WORKSPACE;
+  if (packed && ((uintptr_t)packed & 255)) return DGSCT_ERR_WORKSPACE;
+  return adapter_bwd(d, *params, packed, x, other, d_out, d_spatial_map, d_temporal_map, dx, dother, G, (char*)workspace,
+                     (cudaStream_t)stream);
+}
+
 // Cubic convolution coefficients (A = -0.75), the kernel torch uses for mode='bicubic'.
 static void cubic_coeffs(double t, double w[4]) {
   const double A = -0.75;

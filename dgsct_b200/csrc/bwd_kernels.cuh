@@ -1,0 +1,471 @@
+// Element-wise / reduction kernels of the adapter backward (reference: autograd of net_trans.py:552-674).
+// Activation-sized gradients use the activation dtype (fp32 or bf16); every statistic and every parameter
+// gradient is accumulated in fp32.  Column reductions are staged in shared memory per block and flushed with
+// one global atomicAdd per column per block.
+#pragma once
+#include "common.cuh"
+
+namespace dgsct {
+
+// ---- (1) output stage: out = gate * LN_post(B2)  [AVE]   or   out = LN_post(gate * B2)  [AVS],  B2 = Uo*sc2+sh2 ----
+struct BwdOutArgs {
+  const void* dout; int dout_bf16;          // (R, C)
+  const float* uo;                           // (R, C) fp32 pre-BN2 up-sampler output
+  const float* scale; const float* shift;    // folded bn2 affine used by the forward
+  const float* ln_w; const float* ln_b;      // NULL => no ln_post
+  const float* gate;                         // NULL => no gate
+  int gate_before_ln; float eps; int C; long long rows;
+  void* db2; int db2_bf16;                   // (R, C) gradient w.r.t. B2
+  float* d_lnw; float* d_lnb; float* d_gate; // accumulated (may be NULL)
+};
+
+__global__ void bwd_out_kernel(BwdOutArgs a) {
+  extern __shared__ float sm[];               // [2][C] column partials + [warps][C] row staging (x-hat) + [warps][C] (dy)
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* col_w = sm; float* col_b = sm + a.C;
+  float* xh = sm + 2 * a.C + (size_t)warp * 2 * a.C; float* dy = xh + a.C;
+  for (int c = threadIdx.x; c < 2 * a.C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const float g = a.gate ? a.gate[0] : 1.f;
+  float gate_acc = 0.f;
+  for (long long row = (long long)blockIdx.x * warps + warp; row < a.rows; row += (long long)gridDim.x * warps) {
+    const float gpre = a.gate_before_ln ? g : 1.f, gpost = a.gate_before_ln ? 1.f : g;
+    float sum = 0.f;
+    for (int c = lane; c < a.C; c += 32) {
+      const float b2 = fmaf(a.uo[row * a.C + c], a.scale[c], a.shift[c]);
+      const float v = b2 * gpre;            // LN input
+      xh[c] = v; sum += v;
+      dy[c] = ld_act(a.dout, (size_t)(row * a.C + c), a.dout_bf16);
+    }
+    if (a.ln_w) {
+      const float mean = warp_sum(sum) / a.C;
+      float sq = 0.f;
+      for (int c = lane; c < a.C; c += 32) { const float dlt = xh[c] - mean; sq += dlt * dlt; }
+      const float rstd = rsqrtf(warp_sum(sq) / a.C + a.eps);
+      // LN output L = xhat*w + b ; out = gpost * L
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = lane; c < a.C; c += 32) {
+        const float xhat = (xh[c] - mean) * rstd;
+        const float dL = dy[c] * gpost;
+        if (!a.gate_before_ln && a.gate) gate_acc += dy[c] * fmaf(xhat, a.ln_w[c], a.ln_b[c]);   // AVE order: d_gate = sum dOut * L
+        atomicAdd(&col_w[c], dL * xhat);
+        atomicAdd(&col_b[c], dL);
+        const float dxh = dL * a.ln_w[c];
+        xh[c] = xhat; dy[c] = dxh;
+        s1 += dxh; s2 += dxh * xhat;
+      }
+      s1 = warp_sum(s1) / a.C; s2 = warp_sum(s2) / a.C;
+      for (int c = lane; c < a.C; c += 32) {
+        const float dv = rstd * (dy[c] - s1 - xh[c] * s2);      // d(LN input)
+        // AVS order: LN input = g * B2  ->  dB2 = g * dv ; d_gate += dv * B2
+        if (a.gate_before_ln && a.gate) {
+          const float b2 = fmaf(a.uo[row * a.C + c], a.scale[c], a.shift[c]);
+          gate_acc += dv * b2;
+        }
+        st_act(a.db2, (size_t)(row * a.C + c), dv * gpre, a.db2_bf16);
+      }
+    } else {
+      // no ln_post: out = g * B2 in both orders
+      for (int c = lane; c < a.C; c += 32) {
+        const float b2 = fmaf(a.uo[row * a.C + c], a.scale[c], a.shift[c]);
+        if (a.gate) gate_acc += dy[c] * b2;
+        st_act(a.db2, (size_t)(row * a.C + c), dy[c] * g, a.db2_bf16);
+      }
+    }
+  }
+  __syncthreads();
+  if (a.ln_w) {
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      if (a.d_lnw) atomicAdd(&a.d_lnw[c], col_w[c]);
+      if (a.d_lnb) atomicAdd(&a.d_lnb[c], col_b[c]);
+    }
+  }
+  if (a.gate && a.d_gate) {
+    gate_acc = warp_sum(gate_acc);
+    if (lane == 0 && gate_acc != 0.f) atomicAdd(a.d_gate, gate_acc);
+  }
+}
+
+// ---- column reductions over rows: s1[c] += sum_r a[r,c] ; s2[c] += sum_r a[r,c]*b[r,c] (b optional) ----------
+__global__ void col_reduce_kernel(const void* __restrict__ a, int a_bf16, long long a_ld, const void* __restrict__ b, int b_bf16,
+                                  long long b_ld, long long rows, int C, float* __restrict__ s1, float* __restrict__ s2) {
+  __shared__ float r1[8][33], r2[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float p1 = 0.f, p2 = 0.f;
+  if (c < C)
+    for (long long r = (long long)blockIdx.y * 8 + ry; r < rows; r += (long long)gridDim.y * 8) {
+      const float va = ld_act(a, (size_t)(r * a_ld + c), a_bf16);
+      p1 += va;
+      if (b) p2 += va * ld_act(b, (size_t)(r * b_ld + c), b_bf16);
+    }
+  r1[ry][cx] = p1; r2[ry][cx] = p2;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) { p1 += r1[j][cx]; p2 += r2[j][cx]; }
+    if (s1) atomicAdd(&s1[c], p1);
+    if (s2 && b) atomicAdd(&s2[c], p2);
+  }
+}
+
+// ---- BatchNorm backward coefficients: dx = A*dy + B*x + Cc ; also dW, dB -------------------------------------
+// train: xhat = (x-mean)*rstd, dw = sum dy*xhat, db = sum dy, dx = w*rstd*(dy - db/R - xhat*dw/R)
+// eval (running stats): dx = w*rstd*dy.  No BN: A = 1.
+__global__ void bn_bwd_coeffs_kernel(int C, int use_bn, int train, const float* __restrict__ sum_dy, const float* __restrict__ sum_dyx,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ w,
+                                     double count, float* __restrict__ A, float* __restrict__ B, float* __restrict__ Cc,
+                                     float* __restrict__ dW, float* __restrict__ dB) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (!use_bn) { A[c] = 1.f; B[c] = 0.f; Cc[c] = 0.f; return; }
+  const float mu = mean[c], rs = rstd[c];
+  const float db = sum_dy[c];
+  const float dw = (sum_dyx[c] - mu * db) * rs;       // sum dy*(x-mu)*rstd
+  if (dW) atomicAdd(&dW[c], dw);
+  if (dB) atomicAdd(&dB[c], db);
+  const float wr = w[c] * rs;
+  if (train) {
+    const float inv = (float)(1.0 / count);
+    A[c] = wr;
+    B[c] = -wr * rs * dw * inv;
+    Cc[c] = -wr * db * inv + wr * rs * mu * dw * inv;
+  } else {
+    A[c] = wr; B[c] = 0.f; Cc[c] = 0.f;
+  }
+}
+
+// g[r,c] = A[c]*g[r,c] + B[c]*x[r,c] + Cc[c]   (in place on g), optional ReLU mask from z = x*sc+sh > 0 applied FIRST:
+// used as (a) bn2 backward on dB2, (b) relu+bn1 backward on dZr.
+__global__ void affine_combine_kernel(void* __restrict__ g, int g_bf16, long long g_ld, const float* __restrict__ x, long long x_ld,
+                                      const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ Cc,
+                                      long long rows, int C) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C; const int c = (int)(i % C);
+    const float v = ld_act(g, (size_t)(r * g_ld + c), g_bf16);
+    st_act(g, (size_t)(r * g_ld + c), fmaf(A[c], v, fmaf(B[c], x[r * x_ld + c], Cc[c])), g_bf16);
+  }
+}
+// g[r,c] *= 1[z[r,c]*sc[c]+sh[c] > 0]      (ReLU backward with the pre-activation recomputed from Z)
+__global__ void relu_mask_kernel(void* __restrict__ g, int g_bf16, long long g_ld, const float* __restrict__ z, long long z_ld,
+                                 const float* __restrict__ sc, const float* __restrict__ sh, long long rows, int C) {
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C; const int c = (int)(i % C);
+    if (fmaf(z[r * z_ld + c], sc[c], sh[c]) <= 0.f) st_act(g, (size_t)(r * g_ld + c), 0.f, g_bf16);
+  }
+}
+
+// ---- (4) LN_before + gate combine backward --------------------------------------------------------------------
+struct BwdGateLnArgs {
+  const void* dy; int dy_bf16;               // (R, C) gradient w.r.t. Y (LN_before output)
+  const void* x1; int x1_bf16;               // (R, C)
+  const float* m; const float* sig; const float* tau;   // (BT,C), (R), (BT)|NULL
+  const float* ln_w;                         // NULL => no ln_before
+  float alpha, beta, gamma, eps; int N, C; long long rows;
+  void* dx1; int dx1_bf16;                   // (R, C)  written:  dYg * gmul
+  float* dm_acc;                             // (BT, C) += alpha * sum_n dYg*X1
+  float* dsig;                               // (R)     =  beta * sum_c dYg*X1
+  float* dtau;                               // (BT)    += gamma * sum_{n,c} dYg*X1   (NULL if unused)
+  float* d_lnw; float* d_lnb;
+};
+
+__global__ void bwd_gate_ln_kernel(BwdGateLnArgs a) {
+  extern __shared__ float sm[];               // [2][C] column partials + per warp [2][C]
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* col_w = sm; float* col_b = sm + a.C;
+  float* yg = sm + 2 * a.C + (size_t)warp * 2 * a.C; float* dv = yg + a.C;
+  for (int c = threadIdx.x; c < 2 * a.C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  for (long long row = (long long)blockIdx.x * warps + warp; row < a.rows; row += (long long)gridDim.x * warps) {
+    const int b = (int)(row / a.N);
+    const float base = a.beta * a.sig[row] + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha;
+    const float* mrow = a.m + (size_t)b * a.C;
+    float sum = 0.f;
+    for (int c = lane; c < a.C; c += 32) {
+      const float v = ld_act(a.x1, (size_t)(row * a.C + c), a.x1_bf16) * fmaf(a.alpha, mrow[c], base);
+      yg[c] = v; sum += v;
+      dv[c] = ld_act(a.dy, (size_t)(row * a.C + c), a.dy_bf16);
+    }
+    if (a.ln_w) {
+      const float mean = warp_sum(sum) / a.C;
+      float sq = 0.f;
+      for (int c = lane; c < a.C; c += 32) { const float dlt = yg[c] - mean; sq += dlt * dlt; }
+      const float rstd = rsqrtf(warp_sum(sq) / a.C + a.eps);
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = lane; c < a.C; c += 32) {
+        const float xhat = (yg[c] - mean) * rstd;
+        atomicAdd(&col_w[c], dv[c] * xhat);
+        atomicAdd(&col_b[c], dv[c]);
+        const float dxh = dv[c] * a.ln_w[c];
+        yg[c] = xhat; dv[c] = dxh;
+        s1 += dxh; s2 += dxh * xhat;
+      }
+      s1 = warp_sum(s1) / a.C; s2 = warp_sum(s2) / a.C;
+      for (int c = lane; c < a.C; c += 32) dv[c] = rstd * (dv[c] - s1 - yg[c] * s2);   // dYg
+    }
+    float rowdot = 0.f;
+    for (int c = lane; c < a.C; c += 32) {
+      const float x1 = ld_act(a.x1, (size_t)(row * a.C + c), a.x1_bf16);
+      const float dgm = dv[c] * x1;
+      rowdot += dgm;
+      atomicAdd(&a.dm_acc[(size_t)b * a.C + c], a.alpha * dgm);
+      st_act(a.dx1, (size_t)(row * a.C + c), dv[c] * fmaf(a.alpha, mrow[c], base), a.dx1_bf16);
+    }
+    rowdot = warp_sum(rowdot);
+    if (lane == 0) {
+      a.dsig[row] = a.beta * rowdot;
+      if (a.dtau) atomicAdd(&a.dtau[b], a.gamma * rowdot);
+    }
+  }
+  __syncthreads();
+  if (a.ln_w)
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      if (a.d_lnw) atomicAdd(&a.d_lnw[c], col_w[c]);
+      if (a.d_lnb) atomicAdd(&a.d_lnb[c], col_b[c]);
+    }
+}
+
+// ---- (5) spatial map backward: ds[b,n] from dSmap (softmax(tanh s)) and dsig (sigmoid s) ; d_bs += sum ds -------
+__global__ void bwd_spatial_map_kernel(const float* __restrict__ ssum, const float* __restrict__ s_bias, int N,
+                                       const void* __restrict__ dsmap, int dsmap_bf16, const float* __restrict__ dsig,
+                                       float* __restrict__ ds, float* __restrict__ d_sbias) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float bias = s_bias[0];
+  const float* sp = ssum + (size_t)b * N;
+  float z = 0.f, dot = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float e = expf(tanhf(sp[n] + bias));
+    z += e;
+    if (dsmap) dot += e * ld_act(dsmap, (size_t)b * N + n, dsmap_bf16);
+  }
+  z = block_sum(z, red);
+  dot = block_sum(dot, red) / z;            // sum_n y*dy
+  float acc = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float s = sp[n] + bias, t = tanhf(s), sg = 1.f / (1.f + expf(-s));
+    float g = dsig[(size_t)b * N + n] * sg * (1.f - sg);
+    if (dsmap) {
+      const float y = expf(t) / z;
+      g += y * (ld_act(dsmap, (size_t)b * N + n, dsmap_bf16) - dot) * (1.f - t * t);
+    }
+    ds[(size_t)b * N + n] = g;
+    acc += g;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && d_sbias) atomicAdd(d_sbias, acc);
+}
+
+// z2 (R,H) holds the pre-bias spatial query; in place -> dz2 = ds*ws*aq2*1[z2+b>0]; reductions:
+//   d_ws[j] += sum ds*aq2*relu ; d_aq2[b,j] += ws[j]*sum_n ds*relu ; d_b2[j] += sum dz2
+__global__ void bwd_spatial_mask_kernel(void* __restrict__ z2, int bf, int H, int N, const float* __restrict__ bias2,
+                                        const float* __restrict__ ds, const float* __restrict__ ws, const float* __restrict__ aq2,
+                                        int aq_ld, float* __restrict__ d_ws, float* __restrict__ d_aq2, int daq_ld,
+                                        float* __restrict__ d_b2) {
+  // grid (ceil(H/32), BT, row_splits) ; block (32, 8)
+  __shared__ float r_ws[8][33], r_aq[8][33], r_b[8][33];
+  const int jx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jx, b = blockIdx.y;
+  float p_ws = 0.f, p_aq = 0.f, p_b = 0.f;
+  if (j < H) {
+    const float w = ws[j], a2 = aq2[(size_t)b * aq_ld + j], bj = bias2[j];
+    for (int n = blockIdx.z * 8 + ry; n < N; n += gridDim.z * 8) {
+      const size_t idx = ((size_t)b * N + n) * H + j;
+      const float z = ld_act(z2, idx, bf) + bj;
+      const float r = fmaxf(z, 0.f), d = ds[(size_t)b * N + n];
+      const float dz = z > 0.f ? d * w * a2 : 0.f;
+      st_act(z2, idx, dz, bf);
+      p_ws += d * a2 * r; p_aq += d * r; p_b += dz;
+    }
+    p_aq *= w;
+  }
+  r_ws[ry][jx] = p_ws; r_aq[ry][jx] = p_aq; r_b[ry][jx] = p_b;
+  __syncthreads();
+  if (ry == 0 && j < H) {
+    for (int t = 1; t < 8; ++t) { p_ws += r_ws[t][jx]; p_aq += r_aq[t][jx]; p_b += r_b[t][jx]; }
+    atomicAdd(&d_ws[j], p_ws);
+    atomicAdd(&d_aq2[(size_t)b * daq_ld + j], p_aq);
+    atomicAdd(&d_b2[j], p_b);
+  }
+}
+
+// dXc (R,C) given: dX1 += dXc*(1+m) ; dm_acc[b,c] += sum_n dXc*X1
+__global__ void bwd_xc_kernel(const void* __restrict__ dxc, void* __restrict__ dx1, const void* __restrict__ x1, int bf, int C, int N,
+                              const float* __restrict__ m, float* __restrict__ dm_acc) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx, b = blockIdx.y;
+  float p = 0.f;
+  if (c < C) {
+    const float opm = 1.f + m[(size_t)b * C + c];
+    for (int n = blockIdx.z * 8 + ry; n < N; n += gridDim.z * 8) {
+      const size_t idx = ((size_t)b * N + n) * C + c;
+      const float d = ld_act(dxc, idx, bf);
+      st_act(dx1, idx, ld_act(dx1, idx, bf) + d * opm, bf);
+      p += d * ld_act(x1, idx, bf);
+    }
+  }
+  red[ry][cx] = p;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int t = 1; t < 8; ++t) p += red[t][cx];
+    atomicAdd(&dm_acc[(size_t)b * C + c], p);
+  }
+}
+
+// z1 (R,C) pre-bias channel query, in place -> dz1 = dr1[b,c]*1[z1+b>0] ; d_b1[c] += sum dz1
+__global__ void bwd_channel_mask_kernel(void* __restrict__ z1, int bf, int C, int N, const float* __restrict__ bias1,
+                                        const float* __restrict__ dr1, float* __restrict__ d_b1) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx, b = blockIdx.y;
+  float p = 0.f;
+  if (c < C) {
+    const float bj = bias1[c], d = dr1[(size_t)b * C + c];
+    for (int n = blockIdx.z * 8 + ry; n < N; n += gridDim.z * 8) {
+      const size_t idx = ((size_t)b * N + n) * C + c;
+      const float dz = (ld_act(z1, idx, bf) + bj) > 0.f ? d : 0.f;
+      st_act(z1, idx, dz, bf);
+      p += dz;
+    }
+  }
+  red[ry][cx] = p;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int t = 1; t < 8; ++t) p += red[t][cx];
+    atomicAdd(&d_b1[c], p);
+  }
+}
+
+// ---- small per-frame vector ops (BT x width) ---------------------------------------------------------------------
+enum { VOP_SIGMOID_BWD = 0, VOP_RELU_BWD = 1, VOP_MUL_SCALE = 2 };
+// out[i] = op(g[i], y[i]) : sigmoid bwd g*y*(1-y) ; relu bwd g*1[y>0] ; mul-scale g*y*alpha
+__global__ void vec_op_kernel(int op, const float* g, int g_ld, const float* __restrict__ y, int y_ld, float alpha,
+                              float* out, int out_ld, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i % cols;
+  const float gv = g[(size_t)r * g_ld + c], yv = y[(size_t)r * y_ld + c];
+  float v;
+  if (op == VOP_SIGMOID_BWD) v = gv * yv * (1.f - yv);
+  else if (op == VOP_RELU_BWD) v = yv > 0.f ? gv : 0.f;
+  else v = gv * yv * alpha;
+  out[(size_t)r * out_ld + c] = v;
+}
+
+// ---- token attention backward helpers ----------------------------------------------------------------------------
+// rows of (R,K): dL2 = Q*(g*dQraw - sum_k g*dQraw*Q) in place on dq ; d_gate_av += sum Q*dQraw
+__global__ void row_softmax_bwd_kernel(void* __restrict__ dq, const void* __restrict__ q, int bf, long long rows, int K,
+                                       const float* __restrict__ gate_av, float* __restrict__ d_gate_av) {
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float g = gate_av[0];
+  float gacc = 0.f;
+  for (long long row = (long long)blockIdx.x * warps + warp; row < rows; row += (long long)gridDim.x * warps) {
+    float dot = 0.f;
+    for (int k = lane; k < K; k += 32) dot += ld_act(dq, (size_t)(row * K + k), bf) * ld_act(q, (size_t)(row * K + k), bf);
+    dot = warp_sum(dot);
+    gacc += (lane == 0) ? dot : 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float qq = ld_act(q, (size_t)(row * K + k), bf);
+      st_act(dq, (size_t)(row * K + k), g * qq * (ld_act(dq, (size_t)(row * K + k), bf) - dot), bf);
+    }
+  }
+  if (lane == 0 && d_gate_av && gacc != 0.f) atomicAdd(d_gate_av, gacc);
+}
+
+// per frame, columns of (N,K): dL1 = P*(dP - sum_n dP*P)   (dP fp32 in, dL1 act dtype out)
+__global__ void col_softmax_bwd_kernel(const float* __restrict__ dP, const void* __restrict__ P, int p_bf, void* __restrict__ dL1,
+                                       int out_bf, int N, int K) {
+  extern __shared__ float sm[];             // [groups][K]
+  const int b = blockIdx.x;
+  const int groups = blockDim.x / K;
+  const int k = threadIdx.x % K, g = threadIdx.x / K;
+  const bool active = g < groups;
+  const size_t base = (size_t)b * N * K;
+  float s = 0.f;
+  if (active)
+    for (int n = g; n < N; n += groups) s += dP[base + (size_t)n * K + k] * ld_act(P, base + (size_t)n * K + k, p_bf);
+  if (active) sm[g * K + k] = s;
+  __syncthreads();
+  if (active) { s = 0.f; for (int j = 0; j < groups; ++j) s += sm[j * K + k]; }
+  if (active)
+    for (int n = g; n < N; n += groups) {
+      const size_t i = base + (size_t)n * K + k;
+      st_act(dL1, i, ld_act(P, i, p_bf) * (dP[i] - s), out_bf);
+    }
+}
+
+// out[k,c] += sum_b in[b,k,c]     (gradient of the shared latent tokens through T' = T + ...)
+__global__ void sum_frames_kernel(const float* __restrict__ in, int BT, size_t per_frame, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_frame) return;
+  float s = 0.f;
+  for (int b = 0; b < BT; ++b) s += in[(size_t)b * per_frame + i];
+  out[i] += s;
+}
+
+// fp32 -> act dtype copy with scale (operand copies for the tensor-core products)
+__global__ void cast_scale_kernel(const float* __restrict__ src, float alpha, void* __restrict__ dst, int dst_bf16, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st_act(dst, i, alpha * src[i], dst_bf16);
+}
+
+// d_bres[n] += sum_{b,c'} dU[b,n,c']
+__global__ void rowsum_frames_kernel(const void* __restrict__ du, int bf, int BT, int N, int Co, float* __restrict__ out) {
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int b = warp; b < BT; b += warps)
+    for (int c = lane; c < Co; c += 32) s += ld_act(du, ((size_t)b * N + n) * Co + c, bf);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(&out[n], s);
+}
+
+// zr (rows, ldz) fp32 = relu(z*scale+shift)
+__global__ void bn_relu_f32_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                   float* __restrict__ zr, long long rows, int Cd, int ldz) {
+  const long long total = rows * Cd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / Cd; const int c = (int)(i % Cd);
+    zr[row * ldz + c] = fmaxf(fmaf(z[i], scale[c], shift[c]), 0.f);
+  }
+}
+__global__ void one_plus_kernel(const float* __restrict__ m, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = 1.f + m[i];
+}
+// tau[b] = sigmoid(wt . obar[b] + bt): d_pre = (dtau_gate[b] + dtmap[b]) * tau (1-tau)
+__global__ void temporal_bwd_kernel(const float* __restrict__ dtau, const float* __restrict__ dtmap, const float* __restrict__ tau,
+                                    const float* __restrict__ obar, const float* __restrict__ tw, int C, float* __restrict__ dobar,
+                                    float* __restrict__ d_tw, float* __restrict__ d_tb) {
+  const int b = blockIdx.x;
+  const float t = tau[b];
+  const float g = ((dtau ? dtau[b] : 0.f) + (dtmap ? dtmap[b] : 0.f)) * t * (1.f - t);
+  if (g == 0.f) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&d_tw[c], g * obar[(size_t)b * C + c]);
+    dobar[(size_t)b * C + c] += g * tw[c];
+  }
+  if (threadIdx.x == 0) atomicAdd(d_tb, g);
+}
+
+// dense block-diagonal (out, in) fp32 gradient -> grouped conv layout (out, in/g): grad[o, j] += dense[o, (o/opg)*ipg + j]
+__global__ void ungroup_grad_kernel(const float* __restrict__ dense, int out_ch, int in_ch, int groups, int ld_dense,
+                                    float* __restrict__ grad) {
+  const int ipg = in_ch / groups, opg = out_ch / groups;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_ch * ipg) return;
+  const int o = i / ipg, j = i % ipg;
+  grad[i] += dense[(size_t)o * ld_dense + (o / opg) * ipg + j];
+}
+// grouped conv weight (out, in/g) fp32 -> dense block-diagonal fp32 (out, ld)
+__global__ void densify_grouped_kernel(const float* __restrict__ src, int out_ch, int in_ch, int groups, float* __restrict__ dst, int ld) {
+  const int ipg = in_ch / groups, opg = out_ch / groups;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_ch * ld) return;
+  const int o = i / ld, c = i % ld;
+  dst[i] = (c < in_ch && c / ipg == o / opg) ? src[(size_t)o * ipg + (c - (o / opg) * ipg)] : 0.f;
+}
+
+}  // namespace dgsct

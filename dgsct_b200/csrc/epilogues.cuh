@@ -86,7 +86,7 @@ struct EpiReluMulColsum {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (m + i < M) s += fmaxf(acc[i][j] + bj, 0.f);
-        s *= mul[(long long)b * mul_ld + gn];
+        if (mul) s *= mul[(long long)b * mul_ld + gn];
       }
       s = colpair_sum(s);
       if ((threadIdx.x & 16) == 0 && gn < N) atomicAdd(&colsum[(long long)b * ncols + gn], s);

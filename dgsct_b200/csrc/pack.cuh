@@ -62,6 +62,17 @@ __global__ void scale_to_bf16_kernel(const float* __restrict__ src, float alpha,
     dst[i] = __float2bfloat16_rn(alpha * src[i]);
 }
 
+// q[b,c] = aq1[b,c] * r1sum[b,c] * inv_n  (fp32 and/or bf16 copies)      (net_trans.py:595)
+__global__ void channel_q_kernel(const float* __restrict__ aq1, int aq_ld, const float* __restrict__ r1sum, float inv_n,
+                                 float* __restrict__ q32, bf16* __restrict__ q16, int BT, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BT * C) return;
+  const int b = i / C, c = i % C;
+  const float v = aq1[(size_t)b * aq_ld + c] * r1sum[i] * inv_n;
+  if (q32) q32[i] = v;
+  if (q16) q16[i] = __float2bfloat16_rn(v);
+}
+
 __global__ void concat2_f32_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < na) dst[i] = a[i];

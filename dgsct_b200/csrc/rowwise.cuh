@@ -113,23 +113,29 @@ __global__ void gate_ln_kernel(GateLnArgs a) {
 __global__ void bn_finalize_kernel(int C, int use_bn, int train, const double* __restrict__ sum,
                                    const double* __restrict__ sq, double count, const float* __restrict__ w,
                                    const float* __restrict__ bias, float* __restrict__ rm, float* __restrict__ rv,
-                                   float eps, float momentum, float* __restrict__ scale, float* __restrict__ shift) {
+                                   float eps, float momentum, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int update_running) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (!use_bn) { scale[c] = 1.f; shift[c] = 0.f; return; }
+  if (!use_bn) { scale[c] = 1.f; shift[c] = 0.f; mean_out[c] = 0.f; rstd_out[c] = 1.f; return; }
   double mean, var;
   if (train) {
     mean = sum[c] / count;
     var = sq[c] / count - mean * mean;
     if (var < 0.0) var = 0.0;
     const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-    rm[c] = (float)((1.0 - momentum) * rm[c] + momentum * mean);
-    rv[c] = (float)((1.0 - momentum) * rv[c] + momentum * unb);
+    if (update_running) {
+      rm[c] = (float)((1.0 - momentum) * rm[c] + momentum * mean);
+      rv[c] = (float)((1.0 - momentum) * rv[c] + momentum * unb);
+    }
   } else {
     mean = rm[c];
     var = rv[c];
   }
-  const double sc = (double)w[c] / sqrt(var + (double)eps);
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double sc = (double)w[c] * rstd;
+  mean_out[c] = (float)mean;
+  rstd_out[c] = (float)rstd;
   scale[c] = (float)sc;
   shift[c] = (float)((double)bias[c] - mean * sc);
 }

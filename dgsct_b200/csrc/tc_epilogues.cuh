@@ -176,7 +176,7 @@ struct EpiReluMulColsum {
     const float s = warp_colsum16(v);
     const int lane = threadIdx.x & 31;
     const int col = n0 + colsum16_owner_col(lane);
-    if (((lane & 1) == 0) && col < N) atomicAdd(&colsum[(long long)b * ncols + col], s * mul[(long long)b * mul_ld + col]);
+    if (((lane & 1) == 0) && col < N) atomicAdd(&colsum[(long long)b * ncols + col], mul ? s * mul[(long long)b * mul_ld + col] : s);
   }
 };
 

@@ -48,6 +48,7 @@ typedef enum dgsct_dtype { DGSCT_F32 = 0, DGSCT_BF16 = 1 } dgsct_dtype;
 #define DGSCT_F_TEMPORAL       (1u << 6)  /* compute temporal_att_maps (few-shot/nets/net_trans.py:534) */
 #define DGSCT_F_NO_CONV_BIAS   (1u << 7)  /* resampling matrix has no bias (bicubic variant)            */
 #define DGSCT_F_FORCE_SIMT     (1u << 8)  /* debugging: never take the tcgen05 kernels                  */
+#define DGSCT_F_NO_STAT_UPDATE (1u << 9)  /* TRAIN statistics without touching the running buffers       */
 
 typedef struct dgsct_desc {
   int32_t BT;       /* frames in the batch (clips x T)                        */
@@ -85,6 +86,15 @@ typedef struct dgsct_params {
   const float *t_w, *t_b;                      /* (1,C), (1)  temporal_gated.0 or NULL           */
 } dgsct_params;
 
+/* fp32 gradient buffers, one per entry of dgsct_params (same shapes).  dgsct_adapter_bwd ADDS into them, so the
+ * caller zero-fills (or accumulates across micro-batches, main_trans.py:135-136).  Entries whose parameter is absent
+ * for this descriptor (no gate / BN / LN / temporal gate; the bicubic resampler has no trainable matrix) may be NULL. */
+typedef struct dgsct_grads {
+  float *resample_w, *resample_b, *fc_w, *fc_b, *a1_w, *a1_b, *v1_w, *v1_b, *bott_w, *bott_b, *v2_w, *v2_b, *a2_w, *a2_b,
+      *s_w, *s_b, *c_w, *c_b, *tokens, *gate_av, *gate, *down_w, *up_w, *bn1_w, *bn1_b, *bn2_w, *bn2_b, *lnb_w, *lnb_b,
+      *lnp_w, *lnp_b, *t_w, *t_b;
+} dgsct_grads;
+
 /* Optional taps of intermediate tensors (fp32, token-major) for stage-by-stage parity tests.
  * Any pointer may be NULL. */
 typedef struct dgsct_taps {
@@ -118,6 +128,16 @@ int dgsct_pack_params(const dgsct_desc *desc, const dgsct_params *params, void *
 int dgsct_adapter_fwd(const dgsct_desc *desc, const dgsct_params *params, const void *packed, const void *x,
                       const void *other, void *out, void *spatial_map, float *temporal_map, const dgsct_taps *taps,
                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of VisualAdapter.forward.  The forward keeps no state: this call recomputes the forward into its own
+ * workspace (activation recomputation; BatchNorm batch statistics are recomputed, running buffers are NOT updated
+ * again) and then back-propagates.  d_out / d_spatial_map / dx / dother are `io_dtype`; d_spatial_map and
+ * d_temporal_map (fp32, (BT)) may be NULL.  `desc` must equal the forward's (same TRAIN flag). */
+size_t dgsct_bwd_workspace_bytes(const dgsct_desc *desc);
+int dgsct_adapter_bwd(const dgsct_desc *desc, const dgsct_params *params, const void *packed, const void *x,
+                      const void *other, const void *d_out, const void *d_spatial_map, const float *d_temporal_map,
+                      void *dx, void *dother, const dgsct_grads *grads, void *workspace, size_t workspace_bytes,
+                      void *stream);
 
 /* Stage profiler (used by bench.py for the per-kernel roofline).  When enabled every pipeline stage is
  * bracketed by CUDA events on the launching stream; collect() synchronises on them, writes accumulated

@@ -1,0 +1,146 @@
+"""Gradient parity of dgsct_adapter_bwd (through the C ABI / the autograd bridge) against the reference gradients
+stored in the golden fixtures (fp32) and against oracle autograd at real shapes (fp32 and bf16)."""
+import dataclasses
+import types
+
+import pytest
+import torch
+
+import dgsct_b200
+from dgsct_b200.adapter import adapter_backward_raw, adapter_forward_raw
+from oracle import dgsct_oracle as O
+from tests.golden_util import case_names, load_case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(params):
+    return {k: v.float().cuda().contiguous() for k, v in params.items()}
+
+
+@pytest.mark.parametrize("name", case_names())
+@pytest.mark.parametrize("training", [False, True])
+def test_fp32_gradients_match_reference_golden(name, training):
+    cfg, meta, params, t = load_case(name)
+    tag = "train" if training else "eval"
+    p = _dev(params)
+    x, other = t["x"].float().cuda(), t["other"].float().cuda()
+    d_out = t["R_out"].float().cuda()
+    d_smap = t["R_smap"].float().reshape(x.shape[0], -1).cuda()
+    d_tmap = t["R_tmap"].float().reshape(-1).cuda() if (cfg.temporal and cfg.gamma != 0.0) else None
+    rm_before = {k: v.clone() for k, v in p.items() if "running" in k}
+    dx, dother, grads = adapter_backward_raw(dataclasses.asdict(cfg), p, x, other, d_out, d_smap, d_tmap, training=training)
+    torch.cuda.synchronize()
+    for k, v in rm_before.items():                      # the recompute pass must not touch the running buffers
+        assert torch.equal(p[k], v), k
+    errs = {"x": rel_l2(dx.cpu(), t[f"{tag}/grad_x"]), "other": rel_l2(dother.cpu(), t[f"{tag}/grad_other"])}
+    for k, v in t.items():
+        if k.startswith(f"{tag}/grad/"):
+            pn = k[len(f"{tag}/grad/"):]
+            if pn not in grads:
+                continue
+            ref = v.reshape(grads[pn].shape)
+            if float(ref.abs().max()) < 1e-12:
+                assert float(grads[pn].abs().max()) < 1e-4, pn      # exactly 0 in exact arithmetic (e.g. a bias in front of a batch-stat BN)
+                continue
+            errs[pn] = rel_l2(grads[pn].cpu(), ref)
+    _drop_ill_conditioned(errs, cfg, training)
+    bad = {k: f"{v:.2e}" for k, v in errs.items() if v > 2e-4}
+    assert not bad, bad
+    assert len(errs) >= 19
+
+
+def _drop_ill_conditioned(errs, cfg, training):
+    """Gradients that are zero in exact arithmetic are sums of cancelling fp32 terms; a relative error is meaningless:
+    * a bias in front of a batch-statistics BatchNorm (ln_before.bias when training with BN);
+    * the gate in the AVS order, LN_post(gate * v): LayerNorm is scale invariant up to eps."""
+    if training and cfg.use_bn:
+        errs.pop("ln_before.bias", None)
+    if cfg.gate_before_ln and cfg.ln_post:
+        errs.pop("gate", None)
+
+
+SHAPES = {"vis_s1": (384, 576, 192, 1024), "vis_s2": (768, 144, 384, 256), "aud_s3": (768, 64, 1536, 36), "aud_s1": (192, 1024, 384, 576)}
+
+
+def _oracle_grads(cfg, params, x, other, R_out, R_smap, training, autocast_bf16=False):
+    p = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in params.items()}
+    xs, os_ = x.clone().requires_grad_(True), other.clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast_bf16):
+        out, smap, tmap, _ = O.adapter_forward(cfg, p, xs, os_, training=training)
+    ((out.float() * R_out).sum() + (smap.float().reshape(R_smap.shape) * R_smap).sum()).backward()
+    return xs.grad, os_.grad, {k: v.grad for k, v in p.items() if v.grad is not None}
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gradients_at_real_shapes(shape, dtype):
+    C, N, Co, No = SHAPES[shape]
+    cfg = O.make_config("ave", C, N, Co, No)
+    params = O.random_params(cfg, seed=21)
+    x, other = O.random_inputs(cfg, 10, seed=22)
+    g = torch.Generator().manual_seed(23)
+    R_out = torch.randn(10, N, C, generator=g)
+    R_smap = torch.randn(10, N, generator=g)
+    xq, oq = x.to(dtype), other.to(dtype)
+    p = _dev(params)
+    dx, dother, grads = adapter_backward_raw(dataclasses.asdict(cfg), p, xq.cuda(), oq.cuda(), R_out.to(dtype).cuda(),
+                                             R_smap.to(dtype).cuda(), None, training=True)
+    torch.cuda.synchronize()
+    from dgsct_b200 import _lib as L
+    assert L.lib().dgsct_tc_error_flag(1) == 0
+    gx, go, gp = _oracle_grads(cfg, params, xq.float(), oq.float(), R_out.to(dtype).float(), R_smap.to(dtype).float(), True)
+    # fp32: exact-fp32 kernels (1e-6..1e-4 typical; small bias sums up to ~1e-3).  bf16: every activation and activation
+    # gradient is rounded to bf16 between kernels, as in bf16 autocast training: 4-6e-2 rel-L2 on the longest chains.
+    errs = {"x": rel_l2(dx.float().cpu(), gx), "other": rel_l2(dother.float().cpu(), go)}
+    for k, v in gp.items():
+        if k in grads and float(v.abs().max()) > 1e-6:
+            errs[k] = rel_l2(grads[k].cpu(), v.reshape(grads[k].shape))
+    _drop_ill_conditioned(errs, cfg, True)
+    print(shape, dtype, {k: f"{v:.1e}" for k, v in errs.items()})
+    if dtype == torch.float32:
+        # exact-fp32 kernels: 1e-6..1e-4 typical, small cancelling bias sums up to ~1e-3
+        bad = {k: f"{v:.2e}" for k, v in errs.items() if v > 3e-3}
+    else:
+        # bf16: activations and their gradients are rounded to bf16 between kernels exactly as in bf16 autocast training.
+        # The yardstick is PyTorch's own bf16 autocast of the same math (the oracle under torch.autocast): the sharp
+        # token softmax makes several gradients ill-conditioned (fc.bias 0.6-0.8, resampler weights ~0.1 rel-L2 there).
+        ax, ao, ap = _oracle_grads(cfg, params, xq.float(), oq.float(), R_out.to(dtype).float(), R_smap.to(dtype).float(), True,
+                                   autocast_bf16=True)
+        ref_err = {"x": rel_l2(ax, gx), "other": rel_l2(ao, go)}
+        for k in errs:
+            if k in ap:
+                ref_err[k] = rel_l2(ap[k], gp[k])
+        print("   torch bf16 autocast:", {k: f"{ref_err[k]:.1e}" for k in errs})
+        bad = {k: f"{v:.2e} (autocast {ref_err[k]:.2e})" for k, v in errs.items() if v > max(4.0 * ref_err[k], 5e-2)}
+    assert not bad, bad
+
+
+def test_autograd_bridge_trains_a_module():
+    opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=2, is_before_layernorm=1, is_post_layernorm=1)
+    C, N, Co, No = 768, 36, 384, 64
+    ad = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, num_tk=32, conv_dim_in=No, conv_dim_out=N,
+                                  linear_in=Co, linear_out=C).cuda().train()
+    cfg = O.make_config("ave", C, N, Co, No)
+    params = O.random_params(cfg, seed=4)
+    ad.load_state_dict(params, strict=False)
+    f_v = torch.randn(10, N, C, device="cuda", requires_grad=True)
+    f_a = torch.randn(10, No, Co, device="cuda", requires_grad=True)
+    out, smap = ad(f_v.permute(0, 2, 1).unsqueeze(-1), f_a.permute(0, 2, 1).unsqueeze(-1))
+    loss = (out.squeeze(-1).permute(0, 2, 1) * f_v.detach()).sum() + smap.sum() * 0.5 + (smap[:, 0, :3]).sum()
+    loss.backward()
+    gx, go, gp = None, None, None
+    p = {k: v.clone().requires_grad_("running" not in k) for k, v in params.items()}
+    xs, os_ = f_v.detach().cpu().clone().requires_grad_(True), f_a.detach().cpu().clone().requires_grad_(True)
+    o2, s2, _, _ = O.adapter_forward(cfg, p, xs, os_, training=True)
+    ((o2 * xs.detach()).sum() + s2.sum() * 0.5 + s2[:, 0, :3].sum()).backward()
+    assert rel_l2(f_v.grad.cpu(), xs.grad) < 1e-3 and rel_l2(f_a.grad.cpu(), os_.grad) < 1e-3
+    sd = dict(ad.named_parameters())
+    for k in ("conv_adapter.weight", "fc.weight", "my_tokens", "gate", "gate_av", "down_sampler.weight", "bn2.weight", "ln_post.bias"):
+        assert rel_l2(sd[k].grad.cpu(), p[k].grad.reshape(sd[k].shape)) < 1e-3, k
+    assert sd["gate_tk"].grad is None
+    # one SGD step moves the loss
+    with torch.no_grad():
+        for q in ad.parameters():
+            if q.grad is not None:
+                q -= 1e-3 * q.grad
