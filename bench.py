@@ -31,6 +31,10 @@ ADAPTER_CFG = dict(K=32, r=8, g=2, T=10, alpha=0.3, beta=0.05, gamma=0.0, resamp
                    ln_post=True, gate_before_ln=False, use_bn=True, use_gate=True, temporal=False)
 
 
+METRIC = {"train": "AVE clips/sec (B=8,T=10): adapter-stack train step (fwd+bwd+all-reduce+Adam over the 48 DG-SCT adapters)",
+          "fwd": "AVE clips/sec (B=8,T=10): adapter-stack forward (48 VisualAdapter.forward calls)"}
+
+
 def layer_list():
     out = []
     for li, s in enumerate(PAIRS):
@@ -144,27 +148,54 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def make_cpu_step(args):
+    """One CPU step of the same workload on ONE clip (B=1): the oracle restatement of the reference path; in train mode
+    forward + backward (torch autograd of the oracle) + Adam, with train-mode BatchNorm."""
+    from oracle import dgsct_oracle as O
+    gen = torch.Generator().manual_seed(43)
+    vis, aud = make_tokens(1, args.T, gen, torch.float32)
+    stack = []
+    for kind, li, pos, s in layer_list():
+        C, N, Co, No = dims(kind, s)
+        stack.append((kind, s, O.make_config("ave", C, N, Co, No), make_params(C, N, Co, No, gen)))
+    if args.mode != "train":
+        def step():
+            with torch.no_grad():
+                for kind, s, cfg, p in stack:
+                    x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
+                    O.adapter_forward(cfg, p, x, o, training=False)
+        return step
+    leaves = []
+    for kind, s, cfg, p in stack:
+        for k, v in p.items():
+            if "running" not in k:
+                v.requires_grad_(True)
+                leaves.append(v)
+    opt = torch.optim.Adam(leaves, lr=1e-5)
+    d_vis = [torch.randn(t.shape, generator=gen) * 1e-2 for t in vis]
+    d_aud = [torch.randn(t.shape, generator=gen) * 1e-2 for t in aud]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        for kind, s, cfg, p in stack:
+            x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
+            out, smap, _, stats = O.adapter_forward(cfg, p, x, o, training=True)
+            ((out * (d_vis[s] if kind == "vis" else d_aud[s])).sum() + smap.sum()).backward()
+            for k, v in stats.items():
+                p[k] = v
+        opt.step()
+    return step
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (the oracle restatement pinned to the reference's
     classes by tests/golden), all host threads, one clip (B=1, T=10 -> BT=10) per step."""
     if rank != 0:
         return
-    from oracle import dgsct_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    gen = torch.Generator().manual_seed(43)
     Bs = 1
-    vis, aud = make_tokens(Bs, args.T, gen, torch.float32)
-    stack = []
-    for kind, li, pos, s in layer_list():
-        C, N, Co, No = dims(kind, s)
-        stack.append((kind, s, O.make_config("ave", C, N, Co, No), make_params(C, N, Co, No, gen)))
-
-    def step():
-        with torch.no_grad():
-            for kind, s, cfg, p in stack:
-                x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
-                O.adapter_forward(cfg, p, x, o, training=False)
+    step = make_cpu_step(args)
 
     for _ in range(args.warmup):
         step()
@@ -173,20 +204,22 @@ def run_reference(args, rank, world):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = Bs / dt
-    line = {"metric": "AVE adapter-stack clips/sec (48 VisualAdapter.forward, B=8 T=10 workload)", "value": v, "unit": "clips/s",
+    line = {"metric": METRIC[args.mode], "value": v, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
             "config": workload_config(args, "cpu"),
             "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                             "sample": f"B={Bs} clip (BT={Bs * args.T}) per step, 48 adapters, fp32 eval, torch CPU ({cores} threads)"},
+                             "sample": f"B={Bs} clip (BT={Bs * args.T}) per step, 48 adapters, fp32, {args.mode}, torch CPU ({cores} threads)"},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, where):
-    return {"workload": f"AVE adapter stack fwd: 48 VisualAdapter.forward calls, Swin-V2-L/192 + HTS-AT/256 token shapes, "
-                        f"B={args.B} clips x T={args.T} frames per GPU, K=32 r=8 g=2, eval-mode BN",
+    what = ("train step (forward + backward + grad all-reduce + fused Adam), train-mode BatchNorm" if args.mode == "train"
+            else "forward, eval-mode BN")
+    return {"workload": f"AVE adapter stack {what}: 48 VisualAdapter calls, Swin-V2-L/192 + HTS-AT/256 token shapes, "
+                        f"B={args.B} clips x T={args.T} frames per GPU, K=32 r=8 g=2",
             "B_per_gpu": args.B, "T": args.T, "adapters": 48, "adapter_params": 188.5e6, "mode": args.mode,
             "l2": "per-step working set (377 MB packed bf16 weights + 250 MB tokens + intermediates) exceeds the 126 MB L2; no explicit flush",
             "launch": "eager" if getattr(args, "no_graph", False) else "cuda-graph replay of the 48-call step",
@@ -309,6 +342,58 @@ def run_engine(args, rank, world, local_rank):
         with torch.cuda.graph(graph):
             step_resident()
         run_step = graph.replay
+    fwd_ms = None
+    if args.mode == "train":
+        from dgsct_b200.ddp import GradBucketer
+        fwd_ms = timed(run_step, max(3, args.steps // 2), 3)            # forward-only reference point (same stack)
+        for m in modules:
+            m.train()
+            if hasattr(m, "gate_tk"):
+                m.gate_tk.requires_grad_(False)                        # declared, never used (net_trans.py:487)
+        groups = [[p for p in m.parameters() if p.requires_grad] for m in reversed(modules)]   # backward completion order
+        bucketer = GradBucketer(groups, bucket_bytes=32 << 20)
+        opt_adam = torch.optim.Adam([p for m in modules for p in m.parameters() if p.requires_grad], lr=1e-5, fused=True)
+        vis_g = [t.clone().requires_grad_(True) for t in vis]
+        aud_g = [t.clone().requires_grad_(True) for t in aud]
+        ggen = torch.Generator(device=dev).manual_seed(7)
+        d_vis = [torch.randn(t.shape, generator=ggen, device=dev, dtype=torch.float32).mul_(1e-2).to(dtype) for t in vis]
+        d_aud = [torch.randn(t.shape, generator=ggen, device=dev, dtype=torch.float32).mul_(1e-2).to(dtype) for t in aud]
+        dm_vis = [torch.randn(t.shape[0], 1, t.shape[1], generator=ggen, device=dev, dtype=torch.float32).to(dtype) for t in vis]
+        dm_aud = [torch.randn(t.shape[0], 1, t.shape[1], generator=ggen, device=dev, dtype=torch.float32).to(dtype) for t in aud]
+        nmod = len(modules)
+
+        def step_train(tok_v=None, tok_a=None):
+            tv, ta = (tok_v or vis_g), (tok_a or aud_g)
+            bucketer.zero_grad()
+            for t in tv + ta:
+                t.grad = None
+            outs = []
+            for (kind, s, p, pk), m in zip(stack, modules):           # forward through all 48 adapters
+                x, o = (tv[s], ta[s]) if kind == "vis" else (ta[s], tv[s])
+                out, smap = m(x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
+                outs.append((kind, s, out, smap))
+            for j, (kind, s, out, smap) in enumerate(reversed(outs)):  # backward in reverse order, all-reduce per bucket
+                dgo = (d_vis[s] if kind == "vis" else d_aud[s]).permute(0, 2, 1).unsqueeze(-1)
+                dgm = dm_vis[s] if kind == "vis" else dm_aud[s]
+                torch.autograd.backward([out, smap], [dgo, dgm])
+                bucketer.group_done(j)
+            bucketer.finish()
+            opt_adam.step()
+
+        run_step = step_train
+        n0 = L.launch_count()
+        step_train()
+        torch.cuda.synchronize(dev)
+        launches_per_step = L.launch_count() - n0
+
+        def step_e2e():      # noqa: F811  (train-mode end-to-end: host tokens in, fwd+bwd+all-reduce+Adam, scalar out)
+            v = [t.to(dev, non_blocking=True).requires_grad_(True) for t in vis_h]
+            a = [t.to(dev, non_blocking=True).requires_grad_(True) for t in aud_h]
+            step_train(v, a)
+            res = torch.stack([v[0].grad.float().abs().sum(), a[0].grad.float().abs().sum()])
+            d2h_buf[:2].copy_(res, non_blocking=True)
+            return 8
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step = timed(run_step, args.steps, args.warmup)
     launches = launches_per_step * args.steps
@@ -326,10 +411,17 @@ def run_engine(args, rank, world, local_rank):
     cpu_base = None
     stage_ms = None
     if rank == 0:
+        def step_sequential():                # one stream, so per-stage event times do not overlap
+            for kind, s_, p_, pk_ in stack:
+                x_, o_ = (vis[s_], aud[s_]) if kind == "vis" else (aud[s_], vis[s_])
+                adapter_forward_raw(ADAPTER_CFG, p_, x_, o_, training=False, packed=pk_)
+
+        step_sequential()
+        torch.cuda.synchronize(dev)
         L.profile_enable(True)
         psteps = 3
         for _ in range(psteps):
-            step_resident()
+            step_sequential()
         torch.cuda.synchronize(dev)
         prof = L.profile_collect()
         L.profile_enable(False)
@@ -351,15 +443,16 @@ def run_engine(args, rank, world, local_rank):
                 "share_of_step": (t_conv * 1e3) / max(sum(v[0] for v in prof.values()) / psteps, 1e-9)}
         tot_bytes = sum(alg_bytes(*dims(k, s), BT) for k, _, _, s in layer_list())
         tot_flops = sum(alg_flops(*dims(k, s), BT) for k, _, _, s in layer_list())
-        roof["stack"] = {"algorithmic_GB": tot_bytes / 1e9, "algorithmic_TFLOP": tot_flops / 1e12,
-                         "hbm_GBps": tot_bytes / (ms_step * 1e-3) / 1e9, "hbm_frac": tot_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
-                         "tensor_TFLOPs": tot_flops / (ms_step * 1e-3) / 1e12,
-                         "tensor_frac": tot_flops / (ms_step * 1e-3) / 1e12 / tf_peak}
+        t_fwd = (fwd_ms if fwd_ms is not None else ms_step) * 1e-3      # adapter-forward time (the metric's second half)
+        roof["stack"] = {"what": "whole adapter-forward stack (48 calls), algorithmic bytes / flops of SURVEY.md 8(d)",
+                         "algorithmic_GB": tot_bytes / 1e9, "algorithmic_TFLOP": tot_flops / 1e12, "fwd_ms": t_fwd * 1e3,
+                         "hbm_GBps": tot_bytes / t_fwd / 1e9, "hbm_frac": tot_bytes / t_fwd / 1e9 / hbm_peak,
+                         "tensor_TFLOPs": tot_flops / t_fwd / 1e12, "tensor_frac": tot_flops / t_fwd / 1e12 / tf_peak}
         cpu_base = cpu_baseline(args)
 
     if rank == 0:
         value = world * args.B / (ms_step * 1e-3)
-        line = {"metric": "AVE adapter-stack clips/sec (48 VisualAdapter.forward, B=8 T=10 workload)", "value": value,
+        line = {"metric": METRIC[args.mode], "value": value,
                 "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "impl": "engine", "config": workload_config(args, torch.cuda.get_device_name(dev)),
@@ -367,34 +460,29 @@ def run_engine(args, rank, world, local_rank):
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
                 "stage_ms_per_step": stage_ms}
+        if fwd_ms is not None:
+            line["forward_only"] = {"ms_per_step": fwd_ms, "clips_per_s": world * args.B / (fwd_ms * 1e-3)}
+            line["collective"] = {"op": "all-reduce (mean) of adapter gradients, fp32, bucketed 32 MB, NCCL" if world > 1 else "none (1 GPU)",
+                                  "bytes_per_step": bucketer.total_bytes() if world > 1 else 0}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def cpu_baseline(args):
-    """Oracle on the host cores, bounded sample: one clip (BT=T) through the 48 adapters, best of 3."""
-    from oracle import dgsct_oracle as O
+    """Oracle on the host cores, bounded sample: one clip (BT=T) through the 48 adapters (same mode), best of 3."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    gen = torch.Generator().manual_seed(43)
-    vis, aud = make_tokens(1, args.T, gen, torch.float32)
-    stack = []
-    for kind, li, pos, s in layer_list():
-        C, N, Co, No = dims(kind, s)
-        stack.append((kind, s, O.make_config("ave", C, N, Co, No), make_params(C, N, Co, No, gen)))
+    step = make_cpu_step(args)
     best = 1e30
-    with torch.no_grad():
-        for it in range(4):
-            t0 = time.perf_counter()
-            for kind, s, cfg, p in stack:
-                x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
-                O.adapter_forward(cfg, p, x, o, training=False)
-            dt = time.perf_counter() - t0
-            if it:
-                best = min(best, dt)
+    for it in range(4 if args.mode != "train" else 3):
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if it:
+            best = min(best, dt)
     return {"value": 1.0 / best, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"1 clip (BT={args.T}) through the 48 adapters, fp32 eval, torch CPU {cores} threads, best of 3"}
+            "sample": f"1 clip (BT={args.T}) through the 48 adapters, fp32, {args.mode}, torch CPU {cores} threads, best of {3 if args.mode != 'train' else 2}"}
 
 
 def main():
@@ -406,7 +494,8 @@ def main():
     ap.add_argument("--B", type=int, default=8)
     ap.add_argument("--T", type=int, default=10)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
-    ap.add_argument("--mode", default="fwd", choices=["fwd"])
+    ap.add_argument("--mode", default="train", choices=["fwd", "train"],
+                    help="train: fwd + bwd + gradient all-reduce + Adam over the 48 adapters (BASELINE config 2/3); fwd: forward only")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python loop instead of CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup

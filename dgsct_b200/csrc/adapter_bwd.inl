@@ -123,14 +123,17 @@ static GemmOperand simt_operand(const tc::OperandDesc& o, int is_bf16) {
   return GemmOperand{o.ptr, o.mn_major ? 1 : o.ld, o.mn_major ? o.ld : 1, o.batch_stride, 0, is_bf16};
 }
 
+// sum_b: the product is a weight gradient sum_b A_b . B_b^T -- the tensor-core kernel accumulates groups of frames inside
+// the tile (its functor is called with the frame-group index and must add atomically); the SIMT twin runs one frame per
+// batch entry and adds atomically.
 template <typename TE, typename AX>
 static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const tc::OperandDesc& B, int b_bf16, int M, int N, int K,
-                    int batch, TE te, const EpiOut& se, AX ax, bool ax_identity, int bn_hint = 0) {
+                    int batch, TE te, const EpiOut& se, AX ax, bool ax_identity, int bn_hint = 0, bool sum_b = false) {
   StageScope _sc(g.stage, g.st);
   count_launch();
   if (g.allow_tc && a_bf16 && b_bf16 && ax_identity) {
     tc::Params p;
-    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint);
+    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint, 0, sum_b);
     if (rc == DGSCT_OK) {
       cudaError_t e = tc::launch(p, te, g.st);
       if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
@@ -220,7 +223,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
                 const void* dout, const void* dsmap, const float* dtmap, void* dx, void* dother, const dgsct_grads& G,
                 char* ws, cudaStream_t st) {
   dgsct_desc d = d_in;
-  d.flags |= DGSCT_F_NO_STAT_UPDATE;                        // the recompute pass must not touch the running buffers
+  d.flags |= DGSCT_F_NO_STAT_UPDATE | DGSCT_F_NO_OUTPUT;   // the recompute pass must not touch the running buffers
   const BwdPlan bp = make_bwd_plan(d);
   const FwdPlan fp = make_fwd_plan(d, true);
   const PackPlan pp = make_pack_plan(d);
@@ -295,6 +298,10 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   }
   const int wbf = tcp ? 1 : 0;
   const Gemm GB{ST_MISC, "bwd_gemm", st, tcp};
+  const Gemm G_UD{ST_BWD_UPDOWN, "bwd_updown", st, tcp}, G_SP{ST_BWD_SPATIAL, "bwd_spatial", st, tcp}, G_CH{ST_BWD_CHANNEL, "bwd_channel", st, tcp},
+      G_TK{ST_BWD_TOKEN, "bwd_token", st, tcp}, G_FC{ST_BWD_FC, "bwd_fc", st, tcp}, G_DW{ST_BWD_DWRES, "bwd_dwres", st, tcp},
+      G_DO{ST_BWD_DOTHER, "bwd_dother", st, tcp};
+  (void)GB;
   const int rgrid = (int)((R + 7) / 8 < 148 * 4 ? (R + 7) / 8 : 148 * 4);
   const int ew_grid = 148 * 8;
 
@@ -341,11 +348,11 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       Zr = S2;
     }
     EpiOut e1 = eo(gZ, bf, ldz, (long long)N * ldz, OUT_STORE);
-    RC(run_gemm(GB, K_(gUo, N, C, C, (long long)N * C), bf, MN_(Wup_op, C, Cd, ld_up, 0), wbf, N, Cd, C, BT,
+    RC(run_gemm(G_UD, K_(gUo, N, C, C, (long long)N * C), bf, MN_(Wup_op, C, Cd, ld_up, 0), wbf, N, Cd, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     EpiOut e2 = eo(dWup_d, 0, ldz, 0, OUT_ATOMIC);
-    RC(run_gemm(GB, MN_(gUo, N, C, C, (long long)N * C), bf, MN_(Zr, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
-                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true));
+    RC(run_gemm(G_UD, MN_(gUo, N, C, C, (long long)N * C), bf, MN_(Zr, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true, 0, true));
     { StageScope _sc(ST_MISC, st); count_launch();
       ungroup_grad_kernel<<<ceil_div(C * (Cd / d.g), 256), 256, 0, st>>>(dWup_d, C, Cd, d.g, ldz, G.up_w);
       KCHECK("ungroup_up"); }
@@ -368,11 +375,11 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   // ---- 3. down projection: dY = dZ . Wd ; dWd += dZ^T . Y --------------------------------------------------------
   {
     EpiOut e1 = eo(gY, bf, C, (long long)N * C, OUT_STORE);
-    RC(run_gemm(GB, K_(gZ, N, Cd, ldz, (long long)N * ldz), bf, MN_(Wd_op, Cd, C, ld_dn, 0), wbf, N, C, Cd, BT,
+    RC(run_gemm(G_UD, K_(gZ, N, Cd, ldz, (long long)N * ldz), bf, MN_(Wd_op, Cd, C, ld_dn, 0), wbf, N, C, Cd, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     EpiOut e2 = eo(dWd_d, 0, C, 0, OUT_ATOMIC); e2.transposed = 1;      // D(c, cd) -> dWd_d[cd, c]
-    RC(run_gemm(GB, MN_(Y, N, C, C, (long long)N * C), bf, MN_(gZ, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
-                to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e2), e2, AxIdentity{}, true));
+    RC(run_gemm(G_UD, MN_(Y, N, C, C, (long long)N * C), bf, MN_(gZ, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
+                to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e2), e2, AxIdentity{}, true, 0, true));
     { StageScope _sc(ST_MISC, st); count_launch();
       ungroup_grad_kernel<<<ceil_div(Cd * (C / d.g), 256), 256, 0, st>>>(dWd_d, Cd, C, d.g, C, G.down_w);
       KCHECK("ungroup_down"); }
@@ -390,7 +397,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     const int wpb = C <= 768 ? 8 : 4;
     static bool attr2 = false;
     if (!attr2) { DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_gate_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr2 = true; }
-    StageScope _sc(ST_GATE_LN, st); count_launch();
+    StageScope _sc(ST_BWD_GATE_LN, st); count_launch();
     bwd_gate_ln_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
     KCHECK("bwd_gate_ln");
   }
@@ -402,10 +409,10 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     // z2 = Xc . Wv2^T (pre-bias) -> S2
     EpiOut e1 = eo(S2, bf, H, (long long)N * H, OUT_STORE);
     if (tcp) {
-      RC(run_gemm(GB, K_(fw + fp.XcBuf, N, C, C, (long long)N * C), 1, K_(Wv2_op, H, C, ld_v, 0), 1, N, H, C, BT,
+      RC(run_gemm(G_SP, K_(fw + fp.XcBuf, N, C, C, (long long)N * C), 1, K_(Wv2_op, H, C, ld_v, 0), 1, N, H, C, BT,
                   to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     } else {
-      RC(run_gemm(GB, K_(X1, N, C, C, (long long)N * C), 0, K_(Wv2_op, H, C, ld_v, 0), 0, N, H, C, BT,
+      RC(run_gemm(G_SP, K_(X1, N, C, C, (long long)N * C), 0, K_(Wv2_op, H, C, ld_v, 0), 0, N, H, C, BT,
                   to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, (AxOnePlusCol{mvec, C}), false));
     }
     { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
@@ -414,7 +421,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("bwd_spatial_mask"); }
     // dXc = dz2 . Wv2 -> S1 ; dX1 += dXc (1+m) ; dm += sum_n dXc X1
     EpiOut e2 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
-    RC(run_gemm(GB, K_(S2, N, H, H, (long long)N * H), bf, MN_(Wv2_op, H, C, ld_v, 0), wbf, N, C, H, BT,
+    RC(run_gemm(G_SP, K_(S2, N, H, H, (long long)N * H), bf, MN_(Wv2_op, H, C, ld_v, 0), wbf, N, C, H, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e2), e2, AxIdentity{}, true));
     { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
       bwd_xc_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, gX1, X1, bf, C, N, mvec, dm);
@@ -424,15 +431,20 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       one_plus_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(mvec, opm, BT * C);
       KCHECK("opm"); }
     // dWv2[j,c] += sum_b (1+m[b,c]) sum_n dz2[b,n,j] X1[b,n,c]
-    EpiOut e3 = eo(G.v2_w, 0, C, 0, OUT_ATOMIC); e3.colscale = opm; e3.cs_ld = C;
-    RC(run_gemm(GB, MN_(S2, N, H, H, (long long)N * H), bf, MN_(X1, N, C, C, (long long)N * C), bf, H, C, N, BT,
-                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, true>>(e3), e3, AxIdentity{}, true));
+    if (tcp) {      // Xc = X1 (1+m) was kept by the forward: plain sum over frames
+      EpiOut e3 = eo(G.v2_w, 0, C, 0, OUT_ATOMIC);
+      RC(run_gemm(G_SP, MN_(S2, N, H, H, (long long)N * H), 1, MN_(fw + fp.XcBuf, N, C, C, (long long)N * C), 1, H, C, N, BT,
+                  to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
+    } else {
+      EpiOut e3 = eo(G.v2_w, 0, C, 0, OUT_ATOMIC); e3.colscale = opm; e3.cs_ld = C;
+      RC(run_gemm(G_SP, MN_(S2, N, H, H, (long long)N * H), bf, MN_(X1, N, C, C, (long long)N * C), bf, H, C, N, BT,
+                  to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, true>>(e3), e3, AxIdentity{}, true));
+    }
   }
   // ---- 6. channel gate ---------------------------------------------------------------------------------------------
   {
     // dpm = dm * m (1-m) -> vA (BT,C)
-    const Gemm GS{ST_SMALL_LINEAR, "bwd_small", st, false};
-    StageScope _sc0(ST_SMALL_LINEAR, st);
+    const Gemm GS{ST_BWD_SMALL, "bwd_small", st, false};
     count_launch();
     vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_SIGMOID_BWD, dm, C, mvec, C, 0.f, vA, C, BT, C);
     KCHECK("dpm");
@@ -460,22 +472,21 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   {
     // z1 = X1 . Wv1^T (pre-bias) -> S1 ; dz1 = dr1 * 1[z1+b>0] ; dX1 += dz1 . Wv1 ; dWv1 += dz1^T X1
     EpiOut e1 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
-    RC(run_gemm(GB, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
+    RC(run_gemm(G_CH, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     { StageScope _sc(ST_CHANNEL_QUERY, st); count_launch();
       bwd_channel_mask_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, bf, C, N, P.v1_b, dr1, G.v1_b);
       KCHECK("bwd_channel_mask"); }
     EpiOut e2 = eo(gX1, bf, C, (long long)N * C, OUT_ADD);
-    RC(run_gemm(GB, K_(S1, N, C, C, (long long)N * C), bf, MN_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
+    RC(run_gemm(G_CH, K_(S1, N, C, C, (long long)N * C), bf, MN_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e2), e2, AxIdentity{}, true));
     EpiOut e3 = eo(G.v1_w, 0, C, 0, OUT_ATOMIC);
-    RC(run_gemm(GB, MN_(S1, N, C, C, (long long)N * C), bf, MN_(X1, N, C, C, (long long)N * C), bf, C, C, N, BT,
-                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true));
+    RC(run_gemm(G_CH, MN_(S1, N, C, C, (long long)N * C), bf, MN_(X1, N, C, C, (long long)N * C), bf, C, C, N, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
   }
   {
     // aq1 = relu(Wa1 obar + b), aq2 = relu(Wa2 obar + b), tau = sigmoid(wt obar + bt)   [obar = osum / N]
-    const Gemm GS{ST_SMALL_LINEAR, "bwd_small", st, false};
-    StageScope _sc0(ST_SMALL_LINEAR, st);
+    const Gemm GS{ST_BWD_SMALL, "bwd_small", st, false};
     count_launch(3);
     cast_scale_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(osum, invN, vA, 0, (size_t)BT * C);                     // obar -> vA
     vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_RELU_BWD, daq1, daq_ld, aq1, aq_ld, 0.f, vB, C, BT, C);  // dpa1 -> vB
@@ -501,21 +512,21 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   {
     // dQraw = G . Tp^T -> gQ ; dL2 (in place) ; d_gate_av
     EpiOut e1 = eo(gQ, bf, K, (long long)N * K, OUT_STORE);
-    RC(run_gemm(GB, K_(gX1, N, C, C, (long long)N * C), bf, K_(TpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
+    RC(run_gemm(G_TK, K_(gX1, N, C, C, (long long)N * C), bf, K_(TpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     { StageScope _sc(ST_ROW_SOFTMAX, st); count_launch();
       row_softmax_bwd_kernel<<<rgrid, 256, 0, st>>>(gQ, Qm, bf, R, K, P.gate_av, G.gate_av);
       KCHECK("row_softmax_bwd"); }
     // dTp[b,k,c] = g sum_n Q G + sum_n dL2 x     (computed as D(c,k), written transposed)
     EpiOut e2 = eo(dTp, 0, C, (long long)K * C, OUT_STORE); e2.transposed = 1; e2.alpha_ptr = P.gate_av;
-    RC(run_gemm(GB, MN_(gX1, N, C, C, (long long)N * C), bf, MN_(Qm, N, K, K, (long long)N * K), bf, C, K, N, BT,
+    RC(run_gemm(G_TK, MN_(gX1, N, C, C, (long long)N * C), bf, MN_(Qm, N, K, K, (long long)N * K), bf, C, K, N, BT,
                 to_tcT<tc::EpiOutT<OUT_STORE>>(e2), e2, AxIdentity{}, true));
     EpiOut e3 = eo(dTp, 0, C, (long long)K * C, OUT_ADD); e3.transposed = 1;
-    RC(run_gemm(GB, MN_(x, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
+    RC(run_gemm(G_TK, MN_(x, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
                 to_tcT<tc::EpiOutT<OUT_ADD>>(e3), e3, AxIdentity{}, true));
     // dx = G + dL2 . Tp
     EpiOut e4 = eo(dx, bf, C, (long long)N * C, OUT_STORE); e4.resid = gX1; e4.resid_bf16 = bf;
-    RC(run_gemm(GB, K_(gQ, N, K, K, (long long)N * K), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+    RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
     // d tokens += sum_b dTp[b]
     const void* dTpOp = dTp;
@@ -525,7 +536,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("dtok_sum"); }
     // dP = V . dTp^T (fp32) ; dL1 = P (dP - sum_n dP P) -> gQ
     EpiOut e5 = eo(gP, 0, K, (long long)N * K, OUT_STORE);
-    RC(run_gemm(GB, K_(V, N, C, C, (long long)N * C), bf, K_(dTpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
+    RC(run_gemm(G_TK, K_(V, N, C, C, (long long)N * C), bf, K_(dTpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
                 to_tc_full<tc::EpiOut<false, OUT_STORE, false, false, false>>(e5), e5, AxIdentity{}, true));
     { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
       if (K > 256) return DGSCT_ERR_UNSUPPORTED;
@@ -533,15 +544,15 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("col_softmax_bwd"); }
     // dV = P . dTp + dL1 . T + dobar / N
     EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
-    RC(run_gemm(GB, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+    RC(run_gemm(G_TK, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
     EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
-    RC(run_gemm(GB, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
+    RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
     // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
     EpiOut e8 = eo(G.tokens, 0, C, 0, OUT_ATOMIC); e8.transposed = 1;
-    RC(run_gemm(GB, MN_(V, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
-                to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true));
+    RC(run_gemm(G_TK, MN_(V, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
+                to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true, 0, true));
   }
   // ---- 8. token resampler ---------------------------------------------------------------------------------------------
   {
@@ -550,16 +561,16 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("dfc_b"); }
     // dU = dV . Wfc ; dWfc += dV^T . U
     EpiOut e1 = eo(gU, bf, Co, (long long)N * Co, OUT_STORE);
-    RC(run_gemm(GB, K_(gV, N, C, C, (long long)N * C), bf, MN_(Wfc_op, C, Co, ld_fc, 0), wbf, N, Co, C, BT,
+    RC(run_gemm(G_FC, K_(gV, N, C, C, (long long)N * C), bf, MN_(Wfc_op, C, Co, ld_fc, 0), wbf, N, Co, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     EpiOut e2 = eo(G.fc_w, 0, Co, 0, OUT_ATOMIC);
-    RC(run_gemm(GB, MN_(gV, N, C, C, (long long)N * C), bf, MN_(U, N, Co, Co, (long long)N * Co), bf, C, Co, N, BT,
-                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true));
+    RC(run_gemm(G_FC, MN_(gV, N, C, C, (long long)N * C), bf, MN_(U, N, Co, Co, (long long)N * Co), bf, C, Co, N, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true, 0, true));
     // dWres += sum_b dU_b . other_b^T ; d_bres ; dother_b = Wres^T . dU_b
     if (G.resample_w) {
       EpiOut e3 = eo(G.resample_w, 0, No, 0, OUT_ATOMIC);
-      RC(run_gemm(GB, K_(gU, N, Co, Co, (long long)N * Co), bf, K_(other, No, Co, Co, (long long)No * Co), bf, N, No, Co, BT,
-                  to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true));
+      RC(run_gemm(G_DW, K_(gU, N, Co, Co, (long long)N * Co), bf, K_(other, No, Co, Co, (long long)No * Co), bf, N, No, Co, BT,
+                  to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
     }
     if (G.resample_b && !(d.flags & DGSCT_F_NO_CONV_BIAS)) {
       StageScope _sc(ST_MISC, st); count_launch();
@@ -567,7 +578,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("dres_b");
     }
     EpiOut e4 = eo(dother, bf, Co, (long long)No * Co, OUT_STORE);
-    RC(run_gemm(GB, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gU, N, Co, Co, (long long)N * Co), bf, No, Co, N, BT,
+    RC(run_gemm(G_DO, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gU, N, Co, Co, (long long)N * Co), bf, No, Co, N, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e4), e4, AxIdentity{}, true));
   }
   return DGSCT_OK;

@@ -259,7 +259,7 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
                                                         (float*)(ws + pl.bn2_mean), (float*)(ws + pl.bn2_rstd), upd);
   DGSCT_LAUNCH_CHECK("bn2_finalize"); }
   // (B4) out = gate * LN_post(bn2(Uo))  (or AVS order)                          net_trans.py:667-672
-  {
+  if (!(d.flags & DGSCT_F_NO_OUTPUT)) {
     OutLnArgs a{};
     a.u = UoBuf; a.in_bf16 = uo_bf; a.out = out; a.out_bf16 = bf; a.scale = bn2_scale; a.shift = bn2_shift;
     const bool lnp = d.flags & DGSCT_F_LN_POST;
@@ -604,7 +604,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
                                                           P.bn2_rv, d.eps_bn, d.bn_momentum, bn2_scale, bn2_shift,
                                                           (float*)(ws + pl.bn2_mean), (float*)(ws + pl.bn2_rstd), upd);
     DGSCT_LAUNCH_CHECK("bn2_finalize"); }
-  {
+  if (!(d.flags & DGSCT_F_NO_OUTPUT)) {
     OutLnArgs a{};
     a.u = Uo; a.in_bf16 = 0; a.out = out; a.out_bf16 = 1; a.scale = bn2_scale; a.shift = bn2_shift;
     const bool lnp = d.flags & DGSCT_F_LN_POST;

@@ -30,6 +30,8 @@ struct Params {
   int a_batched, b_batched;     // tensor-map coordinate 2 is the batch index (else 0)
   int BN;                       // tile N per frame (multiple of 16, <= 256)
   int fpack;                    // frames packed side by side along the instruction N (MN-major batched B, shared A)
+  int kb_frames;                // >0: a tile accumulates over this many consecutive frames (K extended over the batch:
+                                // weight gradients sum_b A_b . B_b^T); the epilogue then receives the frame-GROUP index
   int BK;                       // K elements per pipeline stage (64 or 32)
   int stages;
   int a_stage_bytes, b_stage_bytes;
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
   const int n_blocks = (p.N + p.BN - 1) / p.BN, m_blocks = (p.M + BM - 1) / BM;
   const int tiles_per_batch = n_blocks * m_blocks;
   const int fpack = p.fpack;                              // frames per tile (1 unless packed)
-  const int num_tiles = tiles_per_batch * ((p.batch + fpack - 1) / fpack);
+  const int kbf = p.kb_frames;
+  const int num_tiles = tiles_per_batch * (kbf > 0 ? (p.batch + kbf - 1) / kbf : (p.batch + fpack - 1) / fpack);
   const int BNI = p.BN * fpack;                           // instruction N
 
   if (warp == 0 && lane == 0) {
@@ -255,9 +258,12 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
       int it = 0;   // running k-block counter across tiles (ring position)
       bool ok = true;
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        const int b = (t / tiles_per_batch) * fpack, r = t % tiles_per_batch;
+        const int grp = t / tiles_per_batch, r = t % tiles_per_batch;
+        const int bfirst = kbf > 0 ? grp * kbf : grp * fpack;
+        const int nfr = kbf > 0 ? min(kbf, p.batch - bfirst) : 1;
         const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
+        for (int kk = 0; kk < nfr * num_k; ++kk, ++it) {
+          const int b = bfirst + kk / num_k, kb = kk % num_k;
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           ok = mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, p.err_flag);
@@ -303,7 +309,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         if (!ok) break;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
-        for (int kb = 0; kb < num_k; ++kb, ++it) {
+        const int grp = t / tiles_per_batch;
+        const int nfr = kbf > 0 ? min(kbf, p.batch - grp * kbf) : 1;
+        for (int kb = 0; kb < nfr * num_k; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           ok = mbar_wait(smem_u32(&full_bar[s]), ph, p.err_flag);
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
     int ti = 0;
     bool ok = true;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-      const int b0 = (t / tiles_per_batch) * fpack, r = t % tiles_per_batch;
+      const int b0 = kbf > 0 ? (t / tiles_per_batch) : (t / tiles_per_batch) * fpack, r = t % tiles_per_batch;
       const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
       const int acc = acc_bufs == 2 ? (ti & 1) : 0;
       const uint32_t acc_ph = acc_bufs == 2 ? ((ti >> 1) & 1) : (ti & 1);
@@ -394,7 +402,7 @@ int* tc_err_flag_device_ptr();
 // Fills `p` (tensor maps, tile recipe) for D = A . B^T.  Returns DGSCT_OK, or DGSCT_ERR_UNSUPPORTED when the
 // operands cannot be described to TMA (alignment) so the caller can take the SIMT kernel instead.
 int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint = 0,
-                int stages_hint = 0);
+                int stages_hint = 0, bool sum_over_batch = false);
 size_t smem_bytes(const Params& p);
 int num_sms();
 bool operands_ok(const OperandDesc& A, const OperandDesc& B, int K);
@@ -408,7 +416,8 @@ inline cudaError_t launch(const Params& p, EPI epi, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) * ceil_div(p.batch, p.fpack);
+  const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) *
+                          (p.kb_frames > 0 ? ceil_div(p.batch, p.kb_frames) : ceil_div(p.batch, p.fpack));
   const long long slots = (long long)num_sms() * p.ctas_per_sm;
   const int grid = (int)(tiles < slots ? tiles : slots);
   gemm_tc_kernel<EPI><<<grid, THREADS, smem, st>>>(p, epi);

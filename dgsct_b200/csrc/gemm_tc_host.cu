@@ -80,7 +80,7 @@ int num_sms() {
 }
 
 int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint,
-                int stages_hint) {
+                int stages_hint, bool sum_over_batch) {
   if (!operands_ok(A, B, K)) return DGSCT_ERR_UNSUPPORTED;
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.a_mn_major = A.mn_major; p.b_mn_major = B.mn_major;
@@ -104,7 +104,8 @@ int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, in
   // frame packing: when every frame's N fits several times in one instruction (N <= 128) and the A tile is shared,
   // put f frames side by side (each frame's swizzle atoms are separate TMA boxes, so the layout is uniform)
   p.fpack = 1;
-  if (B.mn_major && p.b_batched && !p.a_batched && N <= 128 && N == BN && batch > 1 && BN % b_atom == 0 && !getenv("DGSCT_NO_FPACK")) {
+  p.kb_frames = 0;
+  if (!sum_over_batch && B.mn_major && p.b_batched && !p.a_batched && N <= 128 && N == BN && batch > 1 && BN % b_atom == 0 && !getenv("DGSCT_NO_FPACK")) {
     int f = 256 / BN;
     if (f > batch) f = batch;
     if (f > 4) f = 4;
@@ -117,8 +118,17 @@ int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, in
   // Long-K products (main loop dominated, L2-latency sensitive) run two half-smem CTAs per SM: two independent
   // TMA/MMA streams per SM hide each other's barrier round trips (968 vs 713 TFLOP/s on the stage-0 resampler).
   // Short-K products keep one big-smem CTA per SM with a double-buffered accumulator.
+  if (sum_over_batch) {
+    // frames per tile: enough frame groups to fill ~2 tiles per SM, the rest of the batch is accumulated in the tile
+    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    long long groups = (2LL * num_sms() + tiles - 1) / tiles;
+    if (groups < 1) groups = 1;
+    if (groups > batch) groups = batch;
+    p.kb_frames = (int)((batch + groups - 1) / groups);
+  }
+  const long long k_iters = (long long)num_k * (p.kb_frames > 0 ? p.kb_frames : 1);
   const char* force = getenv("DGSCT_TC_CTAS");
-  p.ctas_per_sm = force ? atoi(force) : ((num_k >= 8 && 2 * stage_bytes <= 104 * 1024) ? 2 : 1);
+  p.ctas_per_sm = force ? atoi(force) : ((k_iters >= 8 && 2 * stage_bytes <= 104 * 1024) ? 2 : 1);
   if (p.ctas_per_sm != 2) p.ctas_per_sm = 1;
   const int budget = p.ctas_per_sm == 2 ? 104 * 1024 : 200 * 1024;
   int stages = stages_hint > 0 ? stages_hint : budget / stage_bytes;

@@ -11,7 +11,9 @@ namespace dgsct {
 static const char* kNames[ST_COUNT] = {
     "resample_conv", "resample_fc", "tok_logits", "col_softmax", "tok_update", "x_logits", "row_softmax", "x_update",
     "small_linear", "channel_query", "spatial_query", "spatial_map", "gate_ln", "down_sampler", "bn_finalize",
-    "up_sampler", "out_ln", "misc"};
+    "up_sampler", "out_ln", "misc",
+    "bwd_out", "bwd_updown", "bwd_gate_ln", "bwd_spatial", "bwd_channel", "bwd_small", "bwd_token", "bwd_fc", "bwd_dwres",
+    "bwd_dother"};
 
 const char* stage_name(int s) { return (s >= 0 && s < ST_COUNT) ? kNames[s] : "?"; }
 

@@ -1,0 +1,105 @@
+"""Data-parallel training support for the adapter engine: one process per GPU, clips sharded over
+ranks, adapters replicated, ONE collective per optimizer step -- the all-reduce (mean) of the trainable-parameter
+gradients over NCCL/NVLink, bucketed and launched as each bucket's backward finishes so it overlaps the backward of
+the remaining adapters.  (The reference has no DDP: AVE/AVVP are single-GPU, the others use nn.DataParallel; BatchNorm
+statistics stay per rank exactly as DataParallel replicas do.)
+
+The bucketer is backend-agnostic (NCCL on GPUs, gloo in the CPU tests): it owns flat fp32 buffers and makes every
+``param.grad`` a view into its bucket, so gradients are produced in place and no flatten/unflatten copies exist.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucket:
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = list(params)
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise TypeError("gradient buckets hold fp32 master gradients")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.work: Optional[dist.Work] = None
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce(self, group=None, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Launch the averaging all-reduce of this bucket (asynchronously).  On CUDA the collective runs on ``stream``
+        after the work already queued on the current stream, so later kernels of the backward overlap it."""
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        if stream is not None and self.flat.is_cuda:
+            stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(stream):
+                self.work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        else:
+            self.work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def wait(self, group=None) -> None:
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+            self.flat.div_(dist.get_world_size(group))
+
+
+class GradBucketer:
+    """Groups parameters into buckets of about ``bucket_bytes`` in registration order (call it with the adapters in the
+    order their backward completes, i.e. reversed forward order) and wires ``param.grad`` into the flat buffers.
+    Parameters that never receive a gradient (``gate_tk``, dead ``fc_caption`` / ``temporal_gated`` heads) must be left
+    out -- the all-reduce would still be correct (zeros), just wasteful."""
+
+    def __init__(self, param_groups: Iterable[Sequence[torch.nn.Parameter]], bucket_bytes: int = 32 << 20, group=None):
+        self.group = group
+        self.buckets: List[GradBucket] = []
+        self.owner: List[int] = []            # bucket index of every registered group, in order
+        cur: List[torch.nn.Parameter] = []
+        cur_bytes = 0
+        pending_groups = 0
+        for g in param_groups:
+            g = [p for p in g if p.requires_grad]
+            cur += g
+            cur_bytes += sum(p.numel() for p in g) * 4
+            pending_groups += 1
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(GradBucket(cur))
+                self.owner += [len(self.buckets) - 1] * pending_groups
+                cur, cur_bytes, pending_groups = [], 0, 0
+        if cur:
+            self.buckets.append(GradBucket(cur))
+            self.owner += [len(self.buckets) - 1] * pending_groups
+        self._remaining = [self.owner.count(i) for i in range(len(self.buckets))]
+        self._left = list(self._remaining)
+        dev = self.buckets[0].flat.device if self.buckets else torch.device("cpu")
+        self.comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+
+    def zero_grad(self) -> None:
+        for b in self.buckets:
+            b.zero()
+        self._left = list(self._remaining)
+
+    def group_done(self, group_index: int) -> None:
+        """Tell the bucketer that the backward of registered group ``group_index`` has been enqueued; once every group of
+        a bucket is done its all-reduce is launched."""
+        bi = self.owner[group_index]
+        self._left[bi] -= 1
+        if self._left[bi] == 0:
+            self.buckets[bi].all_reduce(self.group, self.comm_stream)
+
+    def finish(self) -> None:
+        """Wait for every outstanding all-reduce and turn sums into means (call before optimizer.step())."""
+        for b in self.buckets:
+            b.wait(self.group)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.comm_stream.device).wait_stream(self.comm_stream)
+
+    def total_bytes(self) -> int:
+        return sum(b.flat.numel() * 4 for b in self.buckets)

@@ -49,6 +49,7 @@ typedef enum dgsct_dtype { DGSCT_F32 = 0, DGSCT_BF16 = 1 } dgsct_dtype;
 #define DGSCT_F_NO_CONV_BIAS   (1u << 7)  /* resampling matrix has no bias (bicubic variant)            */
 #define DGSCT_F_FORCE_SIMT     (1u << 8)  /* debugging: never take the tcgen05 kernels                  */
 #define DGSCT_F_NO_STAT_UPDATE (1u << 9)  /* TRAIN statistics without touching the running buffers       */
+#define DGSCT_F_NO_OUTPUT      (1u << 10) /* internal (backward recompute): skip the final ln_post/gate pass */
 
 typedef struct dgsct_desc {
   int32_t BT;       /* frames in the batch (clips x T)                        */

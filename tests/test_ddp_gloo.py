@@ -1,0 +1,73 @@
+"""world_size-2 gloo test of the gradient bucketer (the N>1 host logic; no GPU needed)."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from dgsct_b200.ddp import GradBucketer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                   # identical replicas
+    groups = [[torch.nn.Parameter(torch.randn(7, 5)), torch.nn.Parameter(torch.randn(5))],
+              [torch.nn.Parameter(torch.randn(300, 40)), torch.nn.Parameter(torch.randn(3), requires_grad=False)],
+              [torch.nn.Parameter(torch.randn(11))]]
+    bk = GradBucketer(groups, bucket_bytes=1000)            # -> 3 buckets: [g0], [g1], [g2] (g0 < 1000 B merges with g1? no: 160+20 B then 48 KB)
+    nb = len(bk.buckets)
+    for step in range(2):
+        bk.zero_grad()
+        torch.manual_seed(100 * step + rank)               # rank-dependent data
+        for gi in reversed(range(len(groups))):            # backward order
+            for p in groups[gi]:
+                if p.requires_grad:
+                    g = torch.randn_like(p)
+                    p.grad.add_(g)                          # autograd accumulates in place into the bucket view
+            bk.group_done(gi)
+        bk.finish()
+        # expected: mean over ranks of the same random draws
+        exp = []
+        for r in range(world):
+            torch.manual_seed(100 * step + r)
+            cur = []
+            for gi in reversed(range(len(groups))):
+                for p in groups[gi]:
+                    if p.requires_grad:
+                        cur.append(torch.randn_like(p))
+            exp.append(cur)
+        k = 0
+        ok = True
+        for gi in reversed(range(len(groups))):
+            for p in groups[gi]:
+                if p.requires_grad:
+                    mean = sum(e[k] for e in exp) / world
+                    ok = ok and torch.allclose(p.grad, mean, atol=1e-6)
+                    ok = ok and p.grad.data_ptr() >= bk.buckets[bk.owner[gi]].flat.data_ptr()
+                    k += 1
+        q.put((rank, step, ok, nb, bk.total_bytes()))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(4)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[2] for r in res), res
+    assert res[0][3] >= 2 and res[0][4] == (35 + 5 + 12000 + 11) * 4
