@@ -400,6 +400,13 @@ def run_engine(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
     quick = os.environ.get("DGSCT_BENCH_QUICK") == "1"      # profiling runs under ncu: timed region only
     if quick:
+        if os.environ.get("DGSCT_BENCH_PROFILE") == "1":    # ncu --profile-from-start off: exactly one eager step
+            prof_step = step_train if args.mode == "train" else step_resident
+            torch.cuda.synchronize(dev)
+            torch.cuda.profiler.start()
+            prof_step()
+            torch.cuda.synchronize(dev)
+            torch.cuda.profiler.stop()
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "clips_per_s": world * args.B / (ms_step * 1e-3)}), flush=True)
         return
