@@ -215,14 +215,14 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, where):
+def workload_config(args, where, launch=None):
     what = ("train step (forward + backward + grad all-reduce + fused Adam), train-mode BatchNorm" if args.mode == "train"
             else "forward, eval-mode BN")
     return {"workload": f"AVE adapter stack {what}: 48 VisualAdapter calls, Swin-V2-L/192 + HTS-AT/256 token shapes, "
                         f"B={args.B} clips x T={args.T} frames per GPU, K=32 r=8 g=2",
             "B_per_gpu": args.B, "T": args.T, "adapters": 48, "adapter_params": 188.5e6, "mode": args.mode,
             "l2": "per-step working set (377 MB packed bf16 weights + 250 MB tokens + intermediates) exceeds the 126 MB L2; no explicit flush",
-            "launch": "eager" if getattr(args, "no_graph", False) else "cuda-graph replay of the 48-call step",
+            "launch": launch or "host loop",
             "device": where}
 
 
@@ -282,24 +282,40 @@ def run_engine(args, rank, world, local_rank):
             cur.wait_stream(s_vis)
 
     h2d = sum(t.numel() * t.element_size() for t in vis_h + aud_h)
-    last_maps = [None, None]
-    checksum = torch.zeros(1, device=dev)
     d2h_buf = torch.empty(2 * BT * 64 + 1, dtype=torch.float32).pin_memory()
+    # static device inputs of the end-to-end path: every e2e step copies the pinned host tokens into them
+    vis_in = [torch.empty_like(t) for t in vis]
+    aud_in = [torch.empty_like(t) for t in aud]
 
-    def step_e2e():
-        # public API with HOST buffers: H2D of this step's token tensors, 48 module forwards, D2H of the result
-        v = [t.to(dev, non_blocking=True) for t in vis_h]
-        a = [t.to(dev, non_blocking=True) for t in aud_h]
-        acc = None
-        with torch.no_grad():
-            for (kind, s, p, pk), m in zip(stack, modules):
-                x, o = (v[s], a[s]) if kind == "vis" else (a[s], v[s])
-                out, smap = m(x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
-                last_maps[0 if kind == "aud" else 1] = smap
-            res = torch.cat([last_maps[0].reshape(-1).float()[:BT * 64], last_maps[1].reshape(-1).float()[:BT * 36],
-                             out.float().sum().reshape(1)])
-        d2h_buf[:res.numel()].copy_(res, non_blocking=True)
-        return res.numel() * 4
+    def h2d_copy():
+        for d_, h_ in zip(vis_in + aud_in, vis_h + aud_h):
+            d_.copy_(h_, non_blocking=True)
+
+    def on_pair_streams(work):
+        """Run work(entry_index) for the audio and the visual adapter of every position on two streams (fork/join)."""
+        cur = torch.cuda.current_stream(dev)
+        for i in range(0, len(stack), 2):
+            s_aud.wait_stream(cur)
+            s_vis.wait_stream(cur)
+            for idx, strm in ((i, s_aud), (i + 1, s_vis)):
+                with torch.cuda.stream(strm):
+                    work(idx)
+            cur.wait_stream(s_aud)
+            cur.wait_stream(s_vis)
+
+    def capture(fn, what):
+        """CUDA-graph capture of fn() after warming it on a side stream (workspaces, packed weights, allocator)."""
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ret = fn()
+        return g, ret
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -323,7 +339,24 @@ def run_engine(args, rank, world, local_rank):
             ms = float(t.item())
         return ms / steps
 
-    # The 48-call step is launch-bound when issued eagerly from Python (~1000 small launches), so it is captured once
+    # public-API forward (the call a user makes: 48 x VisualAdapter.forward on permuted views) over the static inputs
+    last_maps = [None, None]
+    last_out = [None]
+
+    def api_forward():
+        def one(idx):
+            kind, s, p, pk = stack[idx]
+            m = modules[idx]
+            x, o = (vis_in[s], aud_in[s]) if kind == "vis" else (aud_in[s], vis_in[s])
+            out, smap = m(x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
+            last_maps[0 if kind == "aud" else 1] = smap
+            last_out[0] = out
+        with torch.no_grad():
+            on_pair_streams(one)
+            return torch.cat([last_maps[0].reshape(-1).float()[:BT * 64], last_maps[1].reshape(-1).float()[:BT * 36],
+                              last_out[0].float().sum().reshape(1)])
+
+    # The 48-call step is launch-bound when issued eagerly from Python (~1100 small launches), so it is captured once
     # into a CUDA graph and replayed (same kernels, same buffers; --no-graph times the eager loop instead).
     n0 = L.launch_count()
     for _ in range(2):
@@ -331,19 +364,28 @@ def run_engine(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     launches_per_step = (L.launch_count() - n0) // 2
     run_step = step_resident
-    graph = None
+    launch_mode = "eager"
     if not args.no_graph:
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            step_resident()                      # warm the per-stream workspaces outside the capture
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            step_resident()
+        graph, _ = capture(step_resident, "fwd")
         run_step = graph.replay
+        launch_mode = "cuda-graph replay of the 48-call step"
     fwd_ms = None
-    if args.mode == "train":
+    if args.mode != "train":
+        if not args.no_graph:
+            g_api, res_static = capture(api_forward, "api fwd")
+
+            def step_e2e():
+                h2d_copy()
+                g_api.replay()
+                d2h_buf[:res_static.numel()].copy_(res_static, non_blocking=True)
+                return res_static.numel() * 4
+        else:
+            def step_e2e():
+                h2d_copy()
+                res = api_forward()
+                d2h_buf[:res.numel()].copy_(res, non_blocking=True)
+                return res.numel() * 4
+    else:
         from dgsct_b200.ddp import GradBucketer
         fwd_ms = timed(run_step, max(3, args.steps // 2), 3)            # forward-only reference point (same stack)
         for m in modules:
@@ -352,45 +394,109 @@ def run_engine(args, rank, world, local_rank):
                 m.gate_tk.requires_grad_(False)                        # declared, never used (net_trans.py:487)
         groups = [[p for p in m.parameters() if p.requires_grad] for m in reversed(modules)]   # backward completion order
         bucketer = GradBucketer(groups, bucket_bytes=32 << 20)
-        opt_adam = torch.optim.Adam([p for m in modules for p in m.parameters() if p.requires_grad], lr=1e-5, fused=True)
-        vis_g = [t.clone().requires_grad_(True) for t in vis]
-        aud_g = [t.clone().requires_grad_(True) for t in aud]
+        opt_adam = torch.optim.Adam([p for m in modules for p in m.parameters() if p.requires_grad], lr=1e-5, fused=True,
+                                    capturable=not args.no_graph)
+        for t in vis_in + aud_in:
+            t.requires_grad_(True)
+        h2d_copy_nograd = h2d_copy
+
+        def h2d_copy():      # noqa: F811  (leaf tensors: copy under no_grad)
+            with torch.no_grad():
+                h2d_copy_nograd()
+
+        h2d_copy()
         ggen = torch.Generator(device=dev).manual_seed(7)
         d_vis = [torch.randn(t.shape, generator=ggen, device=dev, dtype=torch.float32).mul_(1e-2).to(dtype) for t in vis]
         d_aud = [torch.randn(t.shape, generator=ggen, device=dev, dtype=torch.float32).mul_(1e-2).to(dtype) for t in aud]
         dm_vis = [torch.randn(t.shape[0], 1, t.shape[1], generator=ggen, device=dev, dtype=torch.float32).to(dtype) for t in vis]
         dm_aud = [torch.randn(t.shape[0], 1, t.shape[1], generator=ggen, device=dev, dtype=torch.float32).to(dtype) for t in aud]
         nmod = len(modules)
+        outs = [None] * nmod
 
-        def step_train(tok_v=None, tok_a=None):
-            tv, ta = (tok_v or vis_g), (tok_a or aud_g)
+        def fwd_one(idx):
+            kind, s, p, pk = stack[idx]
+            x, o = (vis_in[s], aud_in[s]) if kind == "vis" else (aud_in[s], vis_in[s])
+            outs[idx] = modules[idx](x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
+
+        def bwd_one(idx):
+            kind, s, p, pk = stack[idx]
+            out, smap = outs[idx]
+            dgo = (d_vis[s] if kind == "vis" else d_aud[s]).permute(0, 2, 1).unsqueeze(-1)
+            dgm = dm_vis[s] if kind == "vis" else dm_aud[s]
+            torch.autograd.backward([out, smap], [dgo, dgm])
+
+        train_streams = [2]
+
+        def step_train():
+            """forward through the 48 adapters (public nn.Module API), backward in reverse order with the gradient
+            all-reduce launched per finished bucket, fused Adam.  With train_streams == 2 the audio and the visual
+            adapter of one position (independent: they read the same two token tensors) run on two streams, forward
+            and backward (autograd replays each node on its forward stream)."""
+            cur = torch.cuda.current_stream(dev)
             bucketer.zero_grad()
-            for t in tv + ta:
+            for t in vis_in + aud_in:
                 t.grad = None
-            outs = []
-            for (kind, s, p, pk), m in zip(stack, modules):           # forward through all 48 adapters
-                x, o = (tv[s], ta[s]) if kind == "vis" else (ta[s], tv[s])
-                out, smap = m(x.permute(0, 2, 1).unsqueeze(-1), o.permute(0, 2, 1).unsqueeze(-1))
-                outs.append((kind, s, out, smap))
-            for j, (kind, s, out, smap) in enumerate(reversed(outs)):  # backward in reverse order, all-reduce per bucket
-                dgo = (d_vis[s] if kind == "vis" else d_aud[s]).permute(0, 2, 1).unsqueeze(-1)
-                dgm = dm_vis[s] if kind == "vis" else dm_aud[s]
-                torch.autograd.backward([out, smap], [dgo, dgm])
-                bucketer.group_done(j)
+            if train_streams[0] == 2:
+                on_pair_streams(fwd_one)
+            else:
+                for idx in range(nmod):
+                    fwd_one(idx)
+            for i in range(nmod - 2, -1, -2):                         # reverse position order
+                if train_streams[0] == 2:
+                    s_aud.wait_stream(cur)
+                    s_vis.wait_stream(cur)
+                    for idx, strm in ((i + 1, s_vis), (i, s_aud)):
+                        with torch.cuda.stream(strm):
+                            bwd_one(idx)
+                    cur.wait_stream(s_aud)
+                    cur.wait_stream(s_vis)
+                else:
+                    bwd_one(i + 1)
+                    bwd_one(i)
+                outs[i] = outs[i + 1] = None                          # drop the autograd graph of this position
+                bucketer.group_done(nmod - 1 - (i + 1))
+                bucketer.group_done(nmod - 1 - i)
             bucketer.finish()
             opt_adam.step()
+            return torch.stack([vis_in[0].grad.float().abs().sum(), aud_in[0].grad.float().abs().sum()])
 
-        run_step = step_train
+        for m in modules:
+            m.fused_grad_accumulation = True      # kernels add straight into the bucket views (param.grad)
+            m.save_activations = not args.recompute
         n0 = L.launch_count()
         step_train()
         torch.cuda.synchronize(dev)
         launches_per_step = L.launch_count() - n0
+        run_step = step_train
+        launch_mode = "eager"
+        res_static = None
+        if not args.no_graph:
+            for ns in (2, 1):
+                train_streams[0] = ns
+                try:
+                    g_train, res_static = capture(step_train, "train")
+                    run_step = g_train.replay
+                    launch_mode = (f"cuda-graph replay of the whole train step (fwd + bwd + all-reduce + Adam), "
+                                   f"{ns} stream(s)")
+                    break
+                except Exception as e:                                # e.g. an op that cannot be captured
+                    print(f"[bench] train-step graph capture with {ns} stream(s) failed ({type(e).__name__}: "
+                          f"{str(e).splitlines()[0]})", file=sys.stderr)
+                    torch.cuda.synchronize(dev)
+                    run_step = step_train
+                    res_static = None
+                    for k_ in range(nmod):
+                        outs[k_] = None
+        if res_static is None:
+            train_streams[0] = 1                                      # eager: autograd stream syncs cost more than they hide
 
-        def step_e2e():      # noqa: F811  (train-mode end-to-end: host tokens in, fwd+bwd+all-reduce+Adam, scalar out)
-            v = [t.to(dev, non_blocking=True).requires_grad_(True) for t in vis_h]
-            a = [t.to(dev, non_blocking=True).requires_grad_(True) for t in aud_h]
-            step_train(v, a)
-            res = torch.stack([v[0].grad.float().abs().sum(), a[0].grad.float().abs().sum()])
+        def step_e2e():      # noqa: F811  (host tokens in, fwd+bwd+all-reduce+Adam, two gradient checksums out)
+            h2d_copy()
+            res = res_static
+            if res_static is not None:
+                run_step()
+            else:
+                res = step_train()
             d2h_buf[:2].copy_(res, non_blocking=True)
             return 8
 
@@ -462,7 +568,7 @@ def run_engine(args, rank, world, local_rank):
         line = {"metric": METRIC[args.mode], "value": value,
                 "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "impl": "engine", "config": workload_config(args, torch.cuda.get_device_name(dev)),
+                "impl": "engine", "config": workload_config(args, torch.cuda.get_device_name(dev), launch_mode),
                 "e2e": {"value": world * args.B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
@@ -504,6 +610,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["fwd", "train"],
                     help="train: fwd + bwd + gradient all-reduce + Adam over the 48 adapters (BASELINE config 2/3); fwd: forward only")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python loop instead of CUDA-graph replay")
+    ap.add_argument("--recompute", action="store_true",
+                    help="train: keep no activations, the backward recomputes the forward (default: saved activations)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -10,6 +10,7 @@ _SO = os.path.join(_HERE, "csrc", "libdgsct.so")
 
 F_TRAIN, F_USE_BN, F_USE_GATE, F_LN_BEFORE, F_LN_POST, F_GATE_BEFORE_LN, F_TEMPORAL, F_NO_CONV_BIAS, F_FORCE_SIMT = (
     1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8)
+F_KEEP = 1 << 11
 DT_F32, DT_BF16 = 0, 1
 
 
@@ -48,6 +49,7 @@ class Taps(C.Structure):
 
 EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgsct_workspace_bytes",
            "dgsct_packed_bytes", "dgsct_pack_params", "dgsct_bwd_workspace_bytes", "dgsct_adapter_bwd",
+           "dgsct_bwd_saved_workspace_bytes", "dgsct_adapter_bwd_saved",
            "dgsct_adapter_fwd", "dgsct_bicubic_matrix", "dgsct_num_stages", "dgsct_stage_name",
            "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
            "dgsct_tc_error_flag"]
@@ -88,6 +90,11 @@ def lib() -> C.CDLL:
     L.dgsct_adapter_bwd.restype = C.c_int
     L.dgsct_adapter_bwd.argtypes = [C.POINTER(Desc), C.POINTER(Params)] + [C.c_void_p] * 8 + [C.POINTER(Grads), C.c_void_p,
                                                                                              C.c_size_t, C.c_void_p]
+    L.dgsct_bwd_saved_workspace_bytes.restype = C.c_size_t
+    L.dgsct_bwd_saved_workspace_bytes.argtypes = [C.POINTER(Desc)]
+    L.dgsct_adapter_bwd_saved.restype = C.c_int
+    L.dgsct_adapter_bwd_saved.argtypes = [C.POINTER(Desc), C.POINTER(Params)] + [C.c_void_p] * 9 + [C.POINTER(Grads), C.c_void_p,
+                                                                                                   C.c_size_t, C.c_void_p]
     L.dgsct_packed_bytes.restype = C.c_size_t
     L.dgsct_packed_bytes.argtypes = [C.POINTER(Desc)]
     L.dgsct_pack_params.restype = C.c_int

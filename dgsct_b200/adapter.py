@@ -144,12 +144,18 @@ def _describe(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other
 
 def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor,
                         training: bool = False, want_taps: bool = False, force_simt: bool = False,
-                        packed: Optional[torch.Tensor] = None, pack_only: bool = False):
+                        packed: Optional[torch.Tensor] = None, pack_only: bool = False,
+                        keep: Optional[list] = None):
     """Token-major entry: x (BT,N,C), other (BT,No,Co) contiguous CUDA tensors (fp32 or bf16); ``params`` maps
     reference state_dict names to fp32 CUDA tensors.  ``cfg`` keys: K, r, g, T, alpha, beta, gamma, resampler,
     ln_before, ln_post, gate_before_ln, use_bn, use_gate, temporal, eps_ln, eps_bn, bn_momentum.
-    Returns (out (BT,N,C), smap (BT,N), tmap (BT,) fp32 | None[, taps dict])."""
-    d, P, keep, x, other = _describe(cfg, params, x, other, training, force_simt)
+    Returns (out (BT,N,C), smap (BT,N), tmap (BT,) fp32 | None[, taps dict]).
+    ``keep``: pass an empty list to run the forward with DGSCT_F_KEEP into a workspace of its own (every intermediate
+    the backward needs survives the call); the list receives that workspace tensor, to be handed to
+    ``adapter_backward_raw(saved=...)``."""
+    d, P, _alive, x, other = _describe(cfg, params, x, other, training, force_simt)
+    if keep is not None:
+        d.flags |= L.F_KEEP
     BT, N, Cc = x.shape
     dev = x.device
     lib = L.lib()
@@ -164,7 +170,11 @@ def adapter_forward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Ten
         with torch.cuda.device(dev):
             L.check(lib.dgsct_pack_params(C.byref(d), C.byref(P), C.c_void_p(buf.data_ptr() + off), C.c_void_p(stream)), "pack_params")
         return buf[off:off + pb]
-    ws = _workspace(dev, stream, nbytes + 256)
+    if keep is not None:
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)      # owned by the caller (autograd ctx)
+        keep.append(ws)
+    else:
+        ws = _workspace(dev, stream, nbytes + 256)
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
     out = torch.empty_like(x)
     smap = torch.empty(BT, N, dtype=x.dtype, device=dev)
@@ -200,10 +210,15 @@ _GRAD_NAMES = {v: k for k, v in _PARAM_MAP.items() if "running" not in k}
 
 def adapter_backward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor,
                          d_out: torch.Tensor, d_smap: Optional[torch.Tensor] = None, d_tmap: Optional[torch.Tensor] = None,
-                         training: bool = True, packed: Optional[torch.Tensor] = None):
-    """Gradients of the adapter w.r.t. x, other and every parameter (dgsct_adapter_bwd).  The forward keeps no state:
-    the library recomputes it inside this call.  Returns (dx, dother, {state_dict name: fp32 grad})."""
-    d, P, keep, x, other = _describe(cfg, params, x, other, training)
+                         training: bool = True, packed: Optional[torch.Tensor] = None,
+                         saved: Optional[torch.Tensor] = None, grad_targets: Optional[Dict[str, torch.Tensor]] = None):
+    """Gradients of the adapter w.r.t. x, other and every parameter.  With ``saved`` (the workspace kept by a
+    ``keep=[]`` forward) the call is the backward proper (dgsct_adapter_bwd_saved); without it the library recomputes
+    the forward inside the call (dgsct_adapter_bwd).  The C ABI ADDS parameter gradients into the buffers it is given:
+    names present in ``grad_targets`` (contiguous fp32 tensors, e.g. ``param.grad`` views of a gradient bucket) are
+    accumulated in place; every other gradient lands in one freshly zeroed flat buffer.
+    Returns (dx, dother, {state_dict name: fp32 grad} for the names NOT in grad_targets)."""
+    d, P, _alive, x, other = _describe(cfg, params, x, other, training)
     dev = x.device
     lib = L.lib()
     d_out = d_out.to(x.dtype).contiguous()
@@ -214,44 +229,74 @@ def adapter_backward_raw(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Te
     G = L.Grads()
     grads: Dict[str, torch.Tensor] = {}
     bicubic = cfg.get("resampler", "conv") == "bicubic"
+    fresh = []
     for field, name in _GRAD_NAMES.items():
         t = params.get(name)
         if t is None or (bicubic and field in ("resample_w", "resample_b")):
             continue
         if field in ("t_w", "t_b") and not cfg.get("temporal", False):
             continue
-        g = torch.zeros_like(t, dtype=torch.float32)
-        grads[name] = g
-        setattr(G, field, g.data_ptr())
-    nbytes = lib.dgsct_bwd_workspace_bytes(C.byref(d))
+        tgt = grad_targets.get(name) if grad_targets else None
+        if tgt is not None:
+            if tgt.dtype != torch.float32 or not tgt.is_contiguous() or tgt.numel() != t.numel() or tgt.device != dev:
+                raise TypeError(f"gradient target for {name} must be a contiguous float32 tensor of {t.numel()} elements on {dev}")
+            setattr(G, field, tgt.data_ptr())
+        else:
+            fresh.append((field, name, t))
+    if fresh:
+        offs, total = [], 0
+        for _, _, t in fresh:
+            offs.append(total)
+            total += (t.numel() + 3) // 4 * 4               # keep every view 16-byte aligned
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        for (field, name, t), o in zip(fresh, offs):
+            g = flat[o:o + t.numel()].view(t.shape)
+            grads[name] = g
+            setattr(G, field, g.data_ptr())
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if saved is not None:
+        nbytes = lib.dgsct_bwd_saved_workspace_bytes(C.byref(d))
+    else:
+        nbytes = lib.dgsct_bwd_workspace_bytes(C.byref(d))
     if nbytes == 0:
         raise ValueError("dgsct: invalid adapter description for backward")
-    stream = torch.cuda.current_stream(dev).cuda_stream
     ws = _workspace(dev, ("bwd", stream), nbytes + 256)
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
     dx = torch.empty_like(x)
     dother = torch.empty_like(other)
+    pk = C.c_void_p(packed.data_ptr() if packed is not None else 0)
+    tail = (C.c_void_p(x.data_ptr()), C.c_void_p(other.data_ptr()), C.c_void_p(d_out.data_ptr()),
+            C.c_void_p(d_smap.data_ptr() if d_smap is not None else 0),
+            C.c_void_p(d_tmap.data_ptr() if d_tmap is not None else 0),
+            C.c_void_p(dx.data_ptr()), C.c_void_p(dother.data_ptr()), C.byref(G),
+            C.c_void_p(ws_ptr), C.c_size_t(nbytes), C.c_void_p(stream))
     with torch.cuda.device(dev):
-        rc = lib.dgsct_adapter_bwd(C.byref(d), C.byref(P), C.c_void_p(packed.data_ptr() if packed is not None else 0),
-                                   C.c_void_p(x.data_ptr()), C.c_void_p(other.data_ptr()), C.c_void_p(d_out.data_ptr()),
-                                   C.c_void_p(d_smap.data_ptr() if d_smap is not None else 0),
-                                   C.c_void_p(d_tmap.data_ptr() if d_tmap is not None else 0),
-                                   C.c_void_p(dx.data_ptr()), C.c_void_p(dother.data_ptr()), C.byref(G),
-                                   C.c_void_p(ws_ptr), C.c_size_t(nbytes), C.c_void_p(stream))
+        if saved is not None:
+            saved_ptr = (saved.data_ptr() + 255) // 256 * 256
+            rc = lib.dgsct_adapter_bwd_saved(C.byref(d), C.byref(P), pk, C.c_void_p(saved_ptr), *tail)
+        else:
+            rc = lib.dgsct_adapter_bwd(C.byref(d), C.byref(P), pk, *tail)
     L.check(rc, "adapter_bwd")
     return dx, dother, grads
 
 
 class _AdapterFn(torch.autograd.Function):
-    """autograd bridge: forward and backward both run in libdgsct.so (no PyTorch autograd fallback).  The forward
-    saves only its inputs; the backward call recomputes the intermediates (activation recomputation)."""
+    """autograd bridge: forward and backward both run in libdgsct.so (no PyTorch autograd fallback).
+    ``module.save_activations`` (default True): the training forward keeps its intermediates in a workspace owned by
+    the autograd context and the backward runs from them; False: only the inputs are saved and the backward call
+    recomputes the forward (activation recomputation, for memory-constrained runs).
+    ``module.fused_grad_accumulation`` (default False): parameter gradients are accumulated by the kernels straight
+    into existing contiguous fp32 ``param.grad`` tensors (e.g. views of a GradBucketer bucket) and autograd receives
+    None for them -- no temporary gradient tensors, no AccumulateGrad add."""
 
     @staticmethod
     def forward(ctx, module, names, xt, ot, *flat_params):
         cfg, params = module._cfg(), module._param_dict()
         packed = module._packed_weights(cfg, params, xt, ot)
-        out, smap, tmap = adapter_forward_raw(cfg, params, xt, ot, training=module.training, packed=packed)
+        keep = [] if getattr(module, "save_activations", True) else None
+        out, smap, tmap = adapter_forward_raw(cfg, params, xt, ot, training=module.training, packed=packed, keep=keep)
         ctx.module, ctx.names, ctx.training, ctx.packed = module, names, module.training, packed
+        ctx.saved_ws = keep[0] if keep else None
         ctx.save_for_backward(xt, ot)
         if tmap is not None:
             return out, smap, tmap
@@ -267,8 +312,16 @@ class _AdapterFn(torch.autograd.Function):
             d_out = torch.zeros_like(xt)
         d_smap = gouts[1] if len(gouts) > 1 else None
         d_tmap = gouts[2] if len(gouts) > 2 else None
+        targets = None
+        if getattr(module, "fused_grad_accumulation", False):
+            targets = {}
+            for n, p in module.named_parameters():
+                g = p.grad
+                if n in ctx.names and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == xt.device:
+                    targets[n] = g
         dx, dother, grads = adapter_backward_raw(cfg, params, xt, ot, d_out, d_smap, d_tmap, training=ctx.training,
-                                                 packed=ctx.packed)
+                                                 packed=ctx.packed, saved=ctx.saved_ws, grad_targets=targets)
+        ctx.saved_ws = None
         flat = []
         for n in ctx.names:
             g = grads.get(n)

@@ -182,14 +182,14 @@ struct BwdPlan {
   size_t total;
 };
 
-static BwdPlan make_bwd_plan(const dgsct_desc& d) {
+static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   BwdPlan p{};
   const size_t BT = d.BT, N = d.N, C = d.C, Co = d.Co, K = d.K, Cd = d.C / d.r, H = d.C / 2;
   const size_t es = d.io_dtype == DGSCT_BF16 ? 2 : 4;
   const size_t ldz = pad8((int)Cd);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  p.fwd = take(make_fwd_plan(d, true).total);
+  p.fwd = take(have_saved ? 256 : make_fwd_plan(d, true).total);      // recompute region (unused with saved activations)
   p.gUo = take(BT * N * C * es);
   p.gZ = take(BT * N * ldz * es);
   p.gY = take(BT * N * C * es);
@@ -217,14 +217,14 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d) {
   return p;
 }
 
-size_t bwd_workspace_bytes(const dgsct_desc& d) { return make_bwd_plan(d).total; }
+size_t bwd_workspace_bytes(const dgsct_desc& d, bool have_saved) { return make_bwd_plan(d, have_saved).total; }
 
 int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packed_in, const void* x, const void* other,
                 const void* dout, const void* dsmap, const float* dtmap, void* dx, void* dother, const dgsct_grads& G,
-                char* ws, cudaStream_t st) {
+                char* ws, cudaStream_t st, const char* saved) {
   dgsct_desc d = d_in;
   d.flags |= DGSCT_F_NO_STAT_UPDATE | DGSCT_F_NO_OUTPUT;   // the recompute pass must not touch the running buffers
-  const BwdPlan bp = make_bwd_plan(d);
+  const BwdPlan bp = make_bwd_plan(d, saved != nullptr);
   const FwdPlan fp = make_fwd_plan(d, true);
   const PackPlan pp = make_pack_plan(d);
   const int BT = d.BT, N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2, ldz = pad8(Cd);
@@ -234,11 +234,12 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   const bool train = d.flags & DGSCT_F_TRAIN, use_bn = d.flags & DGSCT_F_USE_BN;
   const long long R = (long long)BT * N;
   const float invN = 1.f / (float)N;
-  char* fw = ws + bp.fwd;
-
-  // ---- 0. recompute the forward, keeping every intermediate ---------------------------------------------------
+  // ---- 0. the forward's intermediates: saved by a DGSCT_F_KEEP forward, or recomputed here with the keep plan ----------
+  char* fw = saved ? const_cast<char*>(saved) : ws + bp.fwd;      // (read-only when saved, except the packed-weights slot)
   const char* pk = (const char*)packed_in;
-  if (tcp) {
+  if (saved) {
+    if (tcp && !pk) pk = fw + fp.packed;                          // packed inside the keep forward's workspace
+  } else if (tcp) {
     if (!pk) { RC(pack_params(d, P, fw + fp.packed, st)); pk = fw + fp.packed; }
     RC(adapter_fwd_tc(d, P, pk, x, other, ws + bp.out_fwd, ws + bp.smap_fwd, (float*)(ws + bp.tmap_fwd), nullptr, fw, st, true));
   } else {

@@ -55,6 +55,7 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
   }
   if (d.io_dtype == DGSCT_BF16) {
     p.Pb = take(BT * N * K * 2);
+    p.csm_part = take(BT * (size_t)CSM_MAX_CHUNKS * 2 * K * 4);
     p.TpB = take(BT * K * C * 2);
     p.Zr = take(BT * N * (size_t)pad8((int)Cd) * 2);
     p.Uo32 = take(BT * N * C * 4);                    // up-sampler output stays fp32 until ln_post
@@ -437,7 +438,11 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
     if (K <= 256) {
       const int groups = 256 / K;
-      col_softmax_bf16_kernel<<<BT, 256, (size_t)groups * K * 4, st>>>(L, Pb, N, K);
+      const dim3 grid(csm_num_chunks(N), BT);
+      float* part = (float*)(ws + pl.csm_part);
+      count_launch();
+      col_softmax_partial_kernel<<<grid, 256, (size_t)2 * groups * K * 4, st>>>(L, part, N, K);
+      col_softmax_apply_kernel<<<grid, 256, 0, st>>>(L, part, Pb, N, K);
     } else {
       return DGSCT_ERR_UNSUPPORTED;
     }
@@ -529,7 +534,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   {
     bf16* Xc = (bf16*)(ws + pl.XcBuf);
     { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
-      scale_cols_kernel<<<2048, 256, 0, st>>>(X1, mvec, Xc, rowsBT, N, C);
+      launch_scale_cols(X1, mvec, Xc, rowsBT, N, C, st);
       DGSCT_LAUNCH_CHECK("scale_cols"); }
     tc::EpiSpatialRowsum te{P.v2_b, aq2, P.s_w, ssum, aq_ld, N, 0.f};
     EpiSpatialRowsum se{P.v2_b, aq2, P.s_w, ssum, aq_ld, N};

@@ -9,6 +9,7 @@ struct FwdPlan {
   size_t bufA, bufV, bufX1, bufL, Tp, Z;
   size_t acc_begin, osum, qsum, ssum, bn1_sum, bn1_sq, bn2_sum, bn2_sq, acc_end;
   size_t aq1, aq2, h, m, tau, sig, bn1_scale, bn1_shift, bn2_scale, bn2_shift;
+  size_t csm_part;                                // column-softmax partials (BT, chunks, 2, K) fp32
   size_t Pb, TpB, Zr, Uo32, packed, aq, vec_bf;   // tensor-core path: bf16 P, bf16 latent tokens, bf16 relu(bn1(Z)), fp32 up-sampler
                                                   // output, packed weights, [aq1 | aq2] fp32 (BT, C+H), bf16 per-frame vectors
   // Regions that alias others unless the plan is built with keep = true (training forward: everything the
@@ -31,9 +32,10 @@ size_t packed_bytes(const dgsct_desc& d);
 int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, const void* other, void* out,
                      void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep = false);
 
-size_t bwd_workspace_bytes(const dgsct_desc& d);
+// `saved` = workspace of a forward run with the keep plan (DGSCT_F_KEEP), or NULL to recompute the forward inside `ws`
+size_t bwd_workspace_bytes(const dgsct_desc& d, bool have_saved = false);
 int adapter_bwd(const dgsct_desc& d, const dgsct_params& P, const void* packed, const void* x, const void* other,
                 const void* dout, const void* dsmap, const float* dtmap, void* dx, void* dother, const dgsct_grads& G,
-                char* ws, cudaStream_t st);
+                char* ws, cudaStream_t st, const char* saved = nullptr);
 
 }  // namespace dgsct

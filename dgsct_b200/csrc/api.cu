@@ -34,7 +34,7 @@ const char* dgsct_last_cuda_error(void) { return g_err; }
 
 size_t dgsct_workspace_bytes(const dgsct_desc* desc) {
   if (validate_desc(desc) != DGSCT_OK) return 0;
-  return make_fwd_plan(*desc).total;
+  return make_fwd_plan(*desc, (desc->flags & DGSCT_F_KEEP) != 0).total;
 }
 
 size_t dgsct_packed_bytes(const dgsct_desc* desc) {
@@ -72,11 +72,12 @@ int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const 
   if ((d.flags & DGSCT_F_LN_BEFORE) && (!P.lnb_w || !P.lnb_b)) return DGSCT_ERR_NULL;
   if ((d.flags & DGSCT_F_LN_POST) && (!P.lnp_w || !P.lnp_b)) return DGSCT_ERR_NULL;
   if ((d.flags & DGSCT_F_TEMPORAL) && (!P.t_w || !P.t_b)) return DGSCT_ERR_NULL;
-  if (workspace_bytes < make_fwd_plan(d).total || ((uintptr_t)workspace & 255)) return DGSCT_ERR_WORKSPACE;
+  const bool keep = (d.flags & DGSCT_F_KEEP) != 0;
+  if (workspace_bytes < make_fwd_plan(d, keep).total || ((uintptr_t)workspace & 255)) return DGSCT_ERR_WORKSPACE;
   if (packed && ((uintptr_t)packed & 255)) return DGSCT_ERR_WORKSPACE;
   if (d.io_dtype == DGSCT_BF16 && !(d.flags & DGSCT_F_FORCE_SIMT))
-    return adapter_fwd_tc(d, P, packed, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream);
-  return adapter_fwd_simt(d, P, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream);
+    return adapter_fwd_tc(d, P, packed, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream, keep);
+  return adapter_fwd_simt(d, P, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream, keep);
 }
 
 size_t dgsct_bwd_workspace_bytes(const dgsct_desc* desc) {
@@ -84,12 +85,13 @@ size_t dgsct_bwd_workspace_bytes(const dgsct_desc* desc) {
   return bwd_workspace_bytes(*desc);
 }
 
-int dgsct_adapter_bwd(const dgsct_desc* desc, const dgsct_params* params, const void* packed, const void* x, const void* other,
-                      const void* d_out, const void* d_spatial_map, const float* d_temporal_map, void* dx, void* dother,
-                      const dgsct_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+static int bwd_entry(const dgsct_desc* desc, const dgsct_params* params, const void* packed, const void* saved, const void* x,
+                     const void* other, const void* d_out, const void* d_spatial_map, const float* d_temporal_map, void* dx,
+                     void* dother, const dgsct_grads* grads, void* workspace, size_t workspace_bytes, void* stream, bool need_saved) {
   int rc = validate_desc(desc);
   if (rc != DGSCT_OK) return rc;
   if (!params || !x || !other || !d_out || !dx || !dother || !grads || !workspace) return DGSCT_ERR_NULL;
+  if (need_saved && !saved) return DGSCT_ERR_NULL;
   const dgsct_desc& d = *desc;
   const dgsct_grads& G = *grads;
   if (!G.fc_w || !G.fc_b || !G.a1_w || !G.a1_b || !G.v1_w || !G.v1_b || !G.bott_w || !G.bott_b || !G.v2_w || !G.v2_b ||
@@ -100,10 +102,31 @@ int dgsct_adapter_bwd(const dgsct_desc* desc, const dgsct_params* params, const 
   if ((d.flags & DGSCT_F_LN_BEFORE) && (!G.lnb_w || !G.lnb_b)) return DGSCT_ERR_NULL;
   if ((d.flags & DGSCT_F_LN_POST) && (!G.lnp_w || !G.lnp_b)) return DGSCT_ERR_NULL;
   if ((d.flags & DGSCT_F_TEMPORAL) && (!G.t_w || !G.t_b)) return DGSCT_ERR_NULL;
-  if (workspace_bytes < bwd_workspace_bytes(d) || ((uintptr_t)workspace & 255)) return DGSCT_ERR_WORKSPACE;
+  if (workspace_bytes < bwd_workspace_bytes(d, saved != nullptr) || ((uintptr_t)workspace & 255)) return DGSCT_ERR_WORKSPACE;
   if (packed && ((uintptr_t)packed & 255)) return DGSCT_ERR_WORKSPACE;
+  if (saved && ((uintptr_t)saved & 255)) return DGSCT_ERR_WORKSPACE;
   return adapter_bwd(d, *params, packed, x, other, d_out, d_spatial_map, d_temporal_map, dx, dother, G, (char*)workspace,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, (const char*)saved);
+}
+
+int dgsct_adapter_bwd(const dgsct_desc* desc, const dgsct_params* params, const void* packed, const void* x, const void* other,
+                      const void* d_out, const void* d_spatial_map, const float* d_temporal_map, void* dx, void* dother,
+                      const dgsct_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_entry(desc, params, packed, nullptr, x, other, d_out, d_spatial_map, d_temporal_map, dx, dother, grads, workspace,
+                   workspace_bytes, stream, false);
+}
+
+size_t dgsct_bwd_saved_workspace_bytes(const dgsct_desc* desc) {
+  if (validate_desc(desc) != DGSCT_OK) return 0;
+  return bwd_workspace_bytes(*desc, true);
+}
+
+int dgsct_adapter_bwd_saved(const dgsct_desc* desc, const dgsct_params* params, const void* packed,
+                            const void* saved_forward_workspace, const void* x, const void* other, const void* d_out,
+                            const void* d_spatial_map, const float* d_temporal_map, void* dx, void* dother,
+                            const dgsct_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_entry(desc, params, packed, saved_forward_workspace, x, other, d_out, d_spatial_map, d_temporal_map, dx, dother,
+                   grads, workspace, workspace_bytes, stream, true);
 }
 
 // Cubic convolution coefficients (A = -0.75), the kernel torch uses for mode='bicubic'.

@@ -94,6 +94,52 @@ __global__ void scale_cols_kernel(const bf16* __restrict__ x1, const float* __re
         __floats2bfloat162_rn(__bfloat162float(v.x) * (1.f + mm.x), __bfloat162float(v.y) * (1.f + mm.y));
   }
 }
+// 16-byte version (C % 8 == 0): two vectors in flight per thread
+__global__ void __launch_bounds__(256) scale_cols_vec_kernel(const bf16* __restrict__ x1, const float* __restrict__ m,
+                                                             bf16* __restrict__ out, long long rows, int N, int C) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    const long long i1 = i0 + stride;
+    const bool two = i1 < total;
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(x1) + i0);
+    const uint4 u1 = two ? __ldg(reinterpret_cast<const uint4*>(x1) + i1) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const long long i = h ? i1 : i0;
+      const uint4 u = h ? u1 : u0;
+      const long long row = i / nvec;
+      const int c = (int)(i - row * nvec) * 8;
+      const int b = (int)(row / N);
+      const float4 ma = __ldg(reinterpret_cast<const float4*>(m + (size_t)b * C + c));
+      const float4 mb = __ldg(reinterpret_cast<const float4*>(m + (size_t)b * C + c) + 1);
+      const float mm[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+        const __nv_bfloat162 r = __floats2bfloat162_rn(__bfloat162float(t.x) * (1.f + mm[2 * q]),
+                                                       __bfloat162float(t.y) * (1.f + mm[2 * q + 1]));
+        o[q] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+      reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+inline void launch_scale_cols(const bf16* x1, const float* m, bf16* out, long long rows, int N, int C, cudaStream_t st) {
+  if (C % 8 == 0) {
+    const long long total = rows * (C / 8);
+    long long blocks = (total + 511) / 512;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (blocks < 1) blocks = 1;
+    scale_cols_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(x1, m, out, rows, N, C);
+  } else {
+    scale_cols_kernel<<<2048, 256, 0, st>>>(x1, m, out, rows, N, C);
+  }
+}
 
 // zr (rows, ldz) bf16 = relu(z * scale[c] + shift[c])      (bn1 + ReLU, net_trans.py:636-638)
 __global__ void bn_relu_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -106,31 +152,73 @@ __global__ void bn_relu_kernel(const float* __restrict__ z, const float* __restr
   }
 }
 
-// softmax over tokens (dim 1) of L (BT, N, K) fp32 -> P (BT, N, K) bf16; one block per frame, coalesced
-__global__ void col_softmax_bf16_kernel(const float* __restrict__ L, bf16* __restrict__ P, int N, int K) {
-  extern __shared__ float sm[];          // [groups][K] partials
-  const int b = blockIdx.x;
+// softmax over tokens (dim 1) of L (BT, N, K) fp32 -> P (BT, N, K) bf16                       (net_trans.py:576)
+// Two kernels over a (row-chunk, frame) grid so that a frame is not confined to one block (BT = 80 frames would leave
+// half of the 148 SMs idle): (1) per-chunk column maxima and exp-sums, (2) combine the <= 32 partials of the frame
+// (redundantly per block -- a few hundred flops) and write the normalised probabilities.
+constexpr int CSM_MAX_CHUNKS = 32;
+__host__ __device__ inline int csm_chunk_rows(int N) {           // rows per chunk: >= 64, at most CSM_MAX_CHUNKS chunks
+  int rows = (N + CSM_MAX_CHUNKS - 1) / CSM_MAX_CHUNKS;
+  if (rows < 64) rows = 64;
+  return rows;
+}
+__host__ __device__ inline int csm_num_chunks(int N) { const int r = csm_chunk_rows(N); return (N + r - 1) / r; }
+
+// part (BT, S, 2, K): [.,.,0,k] = max over the chunk, [.,.,1,k] = sum exp(l - max)
+__global__ void __launch_bounds__(256) col_softmax_partial_kernel(const float* __restrict__ L, float* __restrict__ part, int N, int K) {
+  extern __shared__ float sm[];          // [2][groups][K]
+  const int s = blockIdx.x, b = blockIdx.y, S = gridDim.x;
   const int groups = blockDim.x / K;
   const int k = threadIdx.x % K, g = threadIdx.x / K;
   const bool active = g < groups;
+  const int rows = csm_chunk_rows(N);
+  const int n0 = s * rows, n1 = min(N, n0 + rows);
   const float* base = L + (size_t)b * N * K;
-  float mx = -INFINITY;
-  if (active)
-    for (int n = g; n < N; n += groups) mx = fmaxf(mx, base[(size_t)n * K + k]);
-  if (active) sm[g * K + k] = mx;
+  float mx = -INFINITY, sum = 0.f;
+  if (active) {
+    for (int n = n0 + g; n < n1; n += groups) {                  // online max / sum
+      const float l = base[(size_t)n * K + k];
+      if (l > mx) { sum *= __expf(mx - l); mx = l; }
+      sum += __expf(l - mx);
+    }
+    sm[g * K + k] = mx;
+    sm[(groups + g) * K + k] = sum;
+  }
   __syncthreads();
-  if (active) for (int j = 0; j < groups; ++j) mx = fmaxf(mx, sm[j * K + k]);
-  __syncthreads();
-  float s = 0.f;
-  if (active)
-    for (int n = g; n < N; n += groups) s += __expf(base[(size_t)n * K + k] - mx);
-  if (active) sm[g * K + k] = s;
-  __syncthreads();
-  if (active) { s = 0.f; for (int j = 0; j < groups; ++j) s += sm[j * K + k]; }
-  const float inv = 1.f / s;
-  bf16* pb = P + (size_t)b * N * K;
-  if (active)
-    for (int n = g; n < N; n += groups) pb[(size_t)n * K + k] = __float2bfloat16_rn(__expf(base[(size_t)n * K + k] - mx) * inv);
+  if (active && g == 0) {
+    float M = -INFINITY;
+    for (int j = 0; j < groups; ++j) M = fmaxf(M, sm[j * K + k]);
+    float Z = 0.f;
+    for (int j = 0; j < groups; ++j) {
+      const float mj = sm[j * K + k];
+      if (mj > -INFINITY) Z += sm[(groups + j) * K + k] * __expf(mj - M);
+    }
+    float* o = part + ((size_t)b * S + s) * 2 * K;
+    o[k] = M;
+    o[K + k] = Z;
+  }
+}
+__global__ void __launch_bounds__(256) col_softmax_apply_kernel(const float* __restrict__ L, const float* __restrict__ part,
+                                                                bf16* __restrict__ P, int N, int K) {
+  const int s = blockIdx.x, b = blockIdx.y, S = gridDim.x;
+  const int groups = blockDim.x / K;
+  const int k = threadIdx.x % K, g = threadIdx.x / K;
+  if (g >= groups) return;
+  const float* pb = part + (size_t)b * S * 2 * K;
+  float M = -INFINITY;
+  for (int j = 0; j < S; ++j) M = fmaxf(M, pb[(size_t)j * 2 * K + k]);
+  float Z = 0.f;
+  for (int j = 0; j < S; ++j) {
+    const float mj = pb[(size_t)j * 2 * K + k];
+    if (mj > -INFINITY) Z += pb[(size_t)j * 2 * K + K + k] * __expf(mj - M);
+  }
+  const float inv = 1.f / Z;
+  const int rows = csm_chunk_rows(N);
+  const int n0 = s * rows, n1 = min(N, n0 + rows);
+  const float* base = L + (size_t)b * N * K;
+  bf16* out = P + (size_t)b * N * K;
+  for (int n = n0 + g; n < n1; n += groups)
+    out[(size_t)n * K + k] = __float2bfloat16_rn(__expf(base[(size_t)n * K + k] - M) * inv);
 }
 
 }  // namespace dgsct

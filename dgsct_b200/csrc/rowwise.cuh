@@ -213,50 +213,67 @@ __device__ __forceinline__ void ldf8(const float* __restrict__ p, float (&f)[8])
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-template <int VPL>
+// Row geometry: a token row of C channels is nvec = C/8 16-byte vectors.  LPR lanes share one row (LPR a power of two
+// <= 32), each lane owns VPL vectors (lane sub, sub+LPR, ...), so a warp processes 32/LPR rows at once with every lane
+// busy and VPL independent 16-byte loads in flight per lane -- narrow rows (C = 96: 12 vectors) no longer leave 20 of 32
+// lanes idle.  Statistics are reduced with xor-shuffles inside the LPR-lane group.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) gate_ln_vec_kernel(GateLnArgs a) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsub = lane / LPR;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = a.C >> 3;
+  const float invC = 1.f / (float)a.C;
   const bf16* x1 = reinterpret_cast<const bf16*>(a.x1);
   bf16* y = reinterpret_cast<bf16*>(a.y);
-  for (long long row = warp0; row < a.rows; row += nwarps) {
-    const int b = (int)(row / a.N);
-    const float base = a.beta * a.sig[row] + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha;
+  for (long long base = warp0 * RPW; base < a.rows; base += nwarps * RPW) {
+    const long long row = base + rsub;
+    const bool rv = row < a.rows;
+    const int b = rv ? (int)(row / a.N) : 0;
+    const float gbase = rv ? (a.beta * a.sig[row] + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha) : 0.f;
     float v[VPL][8];
+    uint4 raw[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      raw[i] = (rv && vi < nvec) ? __ldg(reinterpret_cast<const uint4*>(x1 + row * a.C + vi * 8)) : make_uint4(0, 0, 0, 0);
+    }
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        const uint4 u = *reinterpret_cast<const uint4*>(x1 + row * a.C + vi * 8);
+      const int vi = sub + LPR * i;
+      unpack8(raw[i], v[i]);
+      if (rv && vi < nvec) {
         float mm[8];
-        unpack8(u, v[i]);
         ldf8(a.m + (size_t)b * a.C + vi * 8, mm);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { v[i][j] *= fmaf(a.alpha, mm[j], base); sum += v[i][j]; }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) { v[i][j] *= fmaf(a.alpha, mm[j], gbase); sum += v[i][j]; }
       }
     }
     float mean = 0.f, rstd = 1.f;
     if (a.ln_w) {
-      mean = warp_sum(sum) / a.C;
+      mean = group_sum<LPR>(sum) * invC;
       float sq = 0.f;
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
-        if (lane + 32 * i < nvec) {
+        if (sub + LPR * i < nvec) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; sq += dlt * dlt; }
         }
-      rstd = rsqrtf(warp_sum(sq) / a.C + a.eps);
+      rstd = rsqrtf(group_sum<LPR>(sq) * invC + a.eps);
     }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
         if (a.ln_w) {
           float w[8], bb[8];
           ldf8(a.ln_w + vi * 8, w);
@@ -274,50 +291,60 @@ __global__ void __launch_bounds__(256) gate_ln_vec_kernel(GateLnArgs a) {
   }
 }
 
-template <int VPL>
+template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) out_ln_vec_kernel(OutLnArgs a) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsub = lane / LPR;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = a.C >> 3;
+  const float invC = 1.f / (float)a.C;
   const float* u = reinterpret_cast<const float*>(a.u);
   bf16* out = reinterpret_cast<bf16*>(a.out);
   const float g = a.gate ? a.gate[0] : 1.f;
   const float gpre = a.gate_before_ln ? g : 1.f, gpost = a.gate_before_ln ? 1.f : g;
-  for (long long row = warp0; row < a.rows; row += nwarps) {
+  for (long long base = warp0 * RPW; base < a.rows; base += nwarps * RPW) {
+    const long long row = base + rsub;
+    const bool rv = row < a.rows;
     float v[VPL][8];
-    float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        float sc[8], sh[8];
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
         ldf8(u + row * a.C + vi * 8, v[i]);
-        ldf8(a.scale + vi * 8, sc);
-        ldf8(a.shift + vi * 8, sh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { v[i][j] = fmaf(v[i][j], sc[j], sh[j]) * gpre; sum += v[i][j]; }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
       }
     }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
+        float sc[8], sh[8];
+        ldf8(a.scale + vi * 8, sc);
+        ldf8(a.shift + vi * 8, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] = fmaf(v[i][j], sc[j], sh[j]) * gpre; sum += v[i][j]; }
+      }
+    }
     float mean = 0.f, rstd = 1.f;
     if (a.ln_w) {
-      mean = warp_sum(sum) / a.C;
+      mean = group_sum<LPR>(sum) * invC;
       float sq = 0.f;
 #pragma unroll
       for (int i = 0; i < VPL; ++i)
-        if (lane + 32 * i < nvec) {
+        if (sub + LPR * i < nvec) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; sq += dlt * dlt; }
         }
-      rstd = rsqrtf(warp_sum(sq) / a.C + a.eps);
+      rstd = rsqrtf(group_sum<LPR>(sq) * invC + a.eps);
     }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
         if (a.ln_w) {
           float w[8], bb[8];
           ldf8(a.ln_w + vi * 8, w);
@@ -334,36 +361,57 @@ __global__ void __launch_bounds__(256) out_ln_vec_kernel(OutLnArgs a) {
   }
 }
 
+// (LPR, VPL) for a row of nvec 16-byte vectors: an exact power-of-two split with 3-4 vectors per lane when one exists
+// (every Swin-V2 / HTS-AT / CLIP width does), otherwise a whole warp per row with ceil(nvec/32) guarded vectors.
+struct RowGeom { int lpr, vpl; };
+inline RowGeom row_geometry(int nvec) {
+  const int cand[] = {4, 3, 6, 8, 2, 1};
+  for (int vpl : cand) {
+    if (nvec % vpl) continue;
+    const int lpr = nvec / vpl;
+    if (lpr <= 32 && lpr >= 1 && (lpr & (lpr - 1)) == 0) return RowGeom{lpr, vpl};
+  }
+  return RowGeom{32, (nvec + 31) / 32};
+}
+
+// Invokes f.template run<LPR, VPL>() for the geometry of `nvec`; false when no instantiation covers it.
+template <typename F>
+inline bool dispatch_row_geometry(int nvec, F&& f) {
+  const RowGeom g = row_geometry(nvec);
+#define DGSCT_ROW_CASE(L_, V_) if (g.lpr == L_ && g.vpl == V_) { f.template run<L_, V_>(); return true; }
+  DGSCT_ROW_CASE(1, 1) DGSCT_ROW_CASE(1, 2) DGSCT_ROW_CASE(1, 3) DGSCT_ROW_CASE(1, 4) DGSCT_ROW_CASE(1, 6)
+  DGSCT_ROW_CASE(2, 1) DGSCT_ROW_CASE(2, 3) DGSCT_ROW_CASE(2, 4)
+  DGSCT_ROW_CASE(4, 3) DGSCT_ROW_CASE(4, 4) DGSCT_ROW_CASE(8, 3) DGSCT_ROW_CASE(8, 4) DGSCT_ROW_CASE(16, 3) DGSCT_ROW_CASE(16, 4)
+  DGSCT_ROW_CASE(32, 1) DGSCT_ROW_CASE(32, 2) DGSCT_ROW_CASE(32, 3) DGSCT_ROW_CASE(32, 4) DGSCT_ROW_CASE(32, 5) DGSCT_ROW_CASE(32, 6)
+  DGSCT_ROW_CASE(32, 7) DGSCT_ROW_CASE(32, 8)
+#undef DGSCT_ROW_CASE
+  return false;
+}
+
+inline unsigned row_grid(long long rows, int lpr) {
+  const long long rows_per_block = 8LL * (32 / lpr);
+  const long long blocks_needed = (rows + rows_per_block - 1) / rows_per_block;
+  const long long cap = 148LL * 16;
+  return (unsigned)(blocks_needed < cap ? (blocks_needed < 1 ? 1 : blocks_needed) : cap);
+}
+
+struct GateLnLaunch {
+  const GateLnArgs& a; cudaStream_t st;
+  template <int LPR, int VPL> void run() { gate_ln_vec_kernel<LPR, VPL><<<row_grid(a.rows, LPR), 256, 0, st>>>(a); }
+};
+struct OutLnLaunch {
+  const OutLnArgs& a; cudaStream_t st;
+  template <int LPR, int VPL> void run() { out_ln_vec_kernel<LPR, VPL><<<row_grid(a.rows, LPR), 256, 0, st>>>(a); }
+};
+
 // launch the vectorised kernel when the row width allows it; return false if the caller must use the scalar one
 inline bool launch_gate_ln_vec(const GateLnArgs& a, cudaStream_t st) {
   if (a.C % 8 || !a.in_bf16 || !a.out_bf16 || a.C > 2048) return false;
-  const int vpl = (a.C / 8 + 31) / 32;
-  const long long blocks_needed = (a.rows + 7) / 8;
-  const unsigned grid = (unsigned)(blocks_needed < 148LL * 16 ? blocks_needed : 148LL * 16);
-  switch (vpl) {
-    case 1: gate_ln_vec_kernel<1><<<grid, 256, 0, st>>>(a); break;
-    case 2: gate_ln_vec_kernel<2><<<grid, 256, 0, st>>>(a); break;
-    case 3: gate_ln_vec_kernel<3><<<grid, 256, 0, st>>>(a); break;
-    case 4: gate_ln_vec_kernel<4><<<grid, 256, 0, st>>>(a); break;
-    case 5: case 6: gate_ln_vec_kernel<6><<<grid, 256, 0, st>>>(a); break;
-    default: gate_ln_vec_kernel<8><<<grid, 256, 0, st>>>(a); break;
-  }
-  return true;
+  return dispatch_row_geometry(a.C / 8, GateLnLaunch{a, st});
 }
 inline bool launch_out_ln_vec(const OutLnArgs& a, cudaStream_t st) {
   if (a.C % 8 || a.in_bf16 || !a.out_bf16 || a.C > 2048) return false;
-  const int vpl = (a.C / 8 + 31) / 32;
-  const long long blocks_needed = (a.rows + 7) / 8;
-  const unsigned grid = (unsigned)(blocks_needed < 148LL * 16 ? blocks_needed : 148LL * 16);
-  switch (vpl) {
-    case 1: out_ln_vec_kernel<1><<<grid, 256, 0, st>>>(a); break;
-    case 2: out_ln_vec_kernel<2><<<grid, 256, 0, st>>>(a); break;
-    case 3: out_ln_vec_kernel<3><<<grid, 256, 0, st>>>(a); break;
-    case 4: out_ln_vec_kernel<4><<<grid, 256, 0, st>>>(a); break;
-    case 5: case 6: out_ln_vec_kernel<6><<<grid, 256, 0, st>>>(a); break;
-    default: out_ln_vec_kernel<8><<<grid, 256, 0, st>>>(a); break;
-  }
-  return true;
+  return dispatch_row_geometry(a.C / 8, OutLnLaunch{a, st});
 }
 
 }  // namespace dgsct

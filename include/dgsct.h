@@ -50,6 +50,8 @@ typedef enum dgsct_dtype { DGSCT_F32 = 0, DGSCT_BF16 = 1 } dgsct_dtype;
 #define DGSCT_F_FORCE_SIMT     (1u << 8)  /* debugging: never take the tcgen05 kernels                  */
 #define DGSCT_F_NO_STAT_UPDATE (1u << 9)  /* TRAIN statistics without touching the running buffers       */
 #define DGSCT_F_NO_OUTPUT      (1u << 10) /* internal (backward recompute): skip the final ln_post/gate pass */
+#define DGSCT_F_KEEP           (1u << 11) /* training forward: every intermediate the backward needs survives in `workspace`
+                                             (non-aliasing plan, larger dgsct_workspace_bytes) for dgsct_adapter_bwd_saved */
 
 typedef struct dgsct_desc {
   int32_t BT;       /* frames in the batch (clips x T)                        */
@@ -139,6 +141,17 @@ int dgsct_adapter_bwd(const dgsct_desc *desc, const dgsct_params *params, const 
                       const void *other, const void *d_out, const void *d_spatial_map, const float *d_temporal_map,
                       void *dx, void *dother, const dgsct_grads *grads, void *workspace, size_t workspace_bytes,
                       void *stream);
+
+/* Backward from SAVED activations: `saved_forward_workspace` is the workspace of the dgsct_adapter_fwd call made with
+ * DGSCT_F_KEEP for the same desc / parameters / inputs (untouched since).  No recomputation happens, so the call costs
+ * the backward proper; the price is the memory of one kept workspace per adapter call in flight (0.1-0.6 GB at the AVE
+ * shapes, ~12 GB for the 48 calls of a step: small against 180 GB of HBM3e).  `desc` is the forward's, with or without
+ * DGSCT_F_KEEP. */
+size_t dgsct_bwd_saved_workspace_bytes(const dgsct_desc *desc);
+int dgsct_adapter_bwd_saved(const dgsct_desc *desc, const dgsct_params *params, const void *packed,
+                            const void *saved_forward_workspace, const void *x, const void *other, const void *d_out,
+                            const void *d_spatial_map, const float *d_temporal_map, void *dx, void *dother,
+                            const dgsct_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Stage profiler (used by bench.py for the per-kernel roofline).  When enabled every pipeline stage is
  * bracketed by CUDA events on the launching stream; collect() synchronises on them, writes accumulated

@@ -144,3 +144,65 @@ def test_autograd_bridge_trains_a_module():
         for q in ad.parameters():
             if q.grad is not None:
                 q -= 1e-3 * q.grad
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_saved_activation_backward_equals_recompute(dtype):
+    """dgsct_adapter_bwd_saved (forward run with DGSCT_F_KEEP, no recomputation) against dgsct_adapter_bwd."""
+    C, N, Co, No = 384, 256, 768, 144
+    cfg = dataclasses.asdict(O.make_config("ave", C, N, Co, No))
+    p = _dev(O.random_params(O.make_config("ave", C, N, Co, No), seed=31))
+    x, other = O.random_inputs(O.make_config("ave", C, N, Co, No), 10, seed=32)
+    x, other = x.to(dtype).cuda(), other.to(dtype).cuda()
+    g = torch.Generator().manual_seed(33)
+    d_out = torch.randn(10, N, C, generator=g).to(dtype).cuda()
+    d_smap = torch.randn(10, N, generator=g).to(dtype).cuda()
+    rm0 = {k: v.clone() for k, v in p.items() if "running" in k}
+    ref_dx, ref_do, ref_g = adapter_backward_raw(cfg, p, x, other, d_out, d_smap, None, training=True)
+    out_ref, smap_ref, _ = adapter_forward_raw(cfg, {k: (rm0[k].clone() if k in rm0 else v) for k, v in p.items()}, x, other, training=True)
+    keep = []
+    p2 = {k: (rm0[k].clone() if k in rm0 else v) for k, v in p.items()}
+    out, smap, _ = adapter_forward_raw(cfg, p2, x, other, training=True, keep=keep)
+    assert len(keep) == 1
+    assert rel_l2(out.float().cpu(), out_ref.float().cpu()) < 1e-6 and rel_l2(smap.float().cpu(), smap_ref.float().cpu()) < 1e-6
+    dx, do, gr = adapter_backward_raw(cfg, p2, x, other, d_out, d_smap, None, training=True, saved=keep[0])
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 2e-3       # atomics reorder fp32 sums; bf16 re-rounds nothing new
+    assert rel_l2(dx.float().cpu(), ref_dx.float().cpu()) < tol and rel_l2(do.float().cpu(), ref_do.float().cpu()) < tol
+    for k, v in ref_g.items():
+        if float(v.abs().max()) > 1e-6:
+            assert rel_l2(gr[k].cpu(), v.cpu()) < 10 * tol, k
+
+
+def test_fused_grad_accumulation_adds_into_param_grad():
+    opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=2, is_before_layernorm=1, is_post_layernorm=1)
+    C, N, Co, No = 192, 1024, 384, 576
+
+    def make():
+        ad = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, num_tk=32, conv_dim_in=No, conv_dim_out=N,
+                                      linear_in=Co, linear_out=C).cuda().train()
+        ad.load_state_dict(O.random_params(O.make_config("ave", C, N, Co, No), seed=5), strict=False)
+        ad.gate_tk.requires_grad_(False)
+        return ad
+
+    g = torch.Generator().manual_seed(6)
+    f_x = torch.randn(10, N, C, generator=g).bfloat16().cuda()
+    f_o = torch.randn(10, No, Co, generator=g).bfloat16().cuda()
+
+    def run(ad):
+        out, smap = ad(f_x.clone().requires_grad_(True).permute(0, 2, 1).unsqueeze(-1), f_o.permute(0, 2, 1).unsqueeze(-1))
+        (out.float().sum() * 1e-2 + smap.float()[:, 0, ::7].sum()).backward()
+
+    a, b = make(), make()
+    run(a)                                                  # plain autograd: fresh gradients
+    for q in b.parameters():                                # fused: pre-existing .grad holding ones
+        if q.requires_grad:
+            q.grad = torch.ones_like(q)
+    b.fused_grad_accumulation = True
+    run(b)
+    torch.cuda.synchronize()
+    for (n, qa), (_, qb) in zip(a.named_parameters(), b.named_parameters()):
+        if qa.grad is None:
+            continue
+        scale = float(qa.grad.abs().max()) + 1.0
+        assert float((qb.grad - 1.0 - qa.grad).abs().max()) < 2e-2 * scale, n
