@@ -45,14 +45,14 @@ namespace tc {
 // tensor-core twin (row-major output only; transposed outputs use EpiOutT)
 template <bool OUT_BF16, int MODE, bool RESID, bool BCAST, bool CSCALE>
 struct EpiOut {
+  static constexpr bool kHasChunk32 = (MODE == OUT_STORE) || (MODE == OUT_ADD && OUT_BF16);
+  static constexpr int kStageBytes = OUT_BF16 ? 2048 : 4096;
+  static constexpr bool kRowIndependent = true;
   void* out; long long ld, sb; float alpha; const float* alpha_ptr; float al;
   const float* colscale; int cs_ld; const bf16* resid; const float* bcast; int bc_ld; float bc_scale;
   __device__ __forceinline__ void begin(int, int, bool) { al = alpha * (alpha_ptr ? alpha_ptr[0] : 1.f); }
   __device__ __forceinline__ void end(int, int, bool) {}
-  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
-    const int nvalid = nvalid16(n0, N);
-    if (!row_ok || nvalid <= 0) return;
-    const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
+  __device__ __forceinline__ void transform(int b, int n0, float (&v)[16], int nvalid) const {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] *= al;
     if (CSCALE) {
@@ -67,6 +67,12 @@ struct EpiOut {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaf(bc_scale, bc[j], v[j]);
     }
+  }
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    if (!row_ok || nvalid <= 0) return;
+    const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
+    transform(b, n0, v, nvalid);
     if (RESID) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
@@ -86,6 +92,28 @@ struct EpiOut {
       }
       store_row16<OUT_BF16>(out, idx, v, nvalid);
     }
+  }
+  // 32 columns through the warp's staging buffer: residual / accumulate loads and the store are row-contiguous
+  __device__ __forceinline__ void chunk32(int b, int m, int n0, float (&v0)[16], float (&v1)[16], bool two, bool row_ok,
+                                          int N, uint8_t* stage) {
+    const int nv0 = nvalid16(n0, N), nv1 = two ? nvalid16(n0 + 16, N) : 0;
+    const long long off = (long long)b * sb + (long long)m * ld;
+    const int bs = row_ok ? b : 0;                       // rows past M still execute (warp-cooperative I/O): keep loads in range
+    transform(bs, n0, v0, nv0);
+    if (two) transform(bs, n0 + 16, v1, nv1);
+    if (RESID) {
+      float r0[16], r1[16];
+      warp_load_block32_bf16(resid, off, n0, nv0 + nv1, row_ok, stage, r0, r1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v0[j] += r0[j]; v1[j] += r1[j]; }
+    }
+    if (MODE == OUT_ADD && OUT_BF16) {
+      float r0[16], r1[16];
+      warp_load_block32_bf16(reinterpret_cast<const bf16*>(out), off, n0, nv0 + nv1, row_ok, stage, r0, r1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v0[j] += r0[j]; v1[j] += r1[j]; }
+    }
+    warp_store_block32<OUT_BF16>(out, off, n0, v0, v1, nv0 + nv1, row_ok, stage);
   }
 };
 struct EpiNone {   // placeholder for products that never take the tensor-core kernel
@@ -133,7 +161,8 @@ static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const t
   count_launch();
   if (g.allow_tc && a_bf16 && b_bf16 && ax_identity) {
     tc::Params p;
-    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint, 0, sum_b);
+    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint, 0, sum_b, tc::epi_row_independent<TE>::value,
+                                   tc::epi_stage_bytes<TE>::value);
     if (rc == DGSCT_OK) {
       cudaError_t e = tc::launch(p, te, g.st);
       if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
@@ -178,7 +207,7 @@ struct BwdPlan {
   size_t fwd;                        // keep-mode forward workspace
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
   size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, dWup_d, dWd_d, zero_end;
-  size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd;
+  size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part;
   size_t total;
 };
 
@@ -212,6 +241,7 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.coefA = take(C * 4); p.coefB = take(C * 4); p.coefC = take(C * 4);
   p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
   p.opm = take(BT * C * 4);
+  p.csm_part = take(BT * (size_t)CSM_MAX_CHUNKS * K * 4);
   p.out_fwd = take(BT * N * C * es); p.smap_fwd = take(BT * N * es); p.tmap_fwd = take(BT * 4);
   p.total = off;
   return p;
@@ -307,6 +337,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   const int ew_grid = 148 * 8;
 
   // ---- 1. output stage: gate, ln_post, bn2 ----------------------------------------------------------------------
+  bool bn2_sums_done = false;
   {
     BwdOutArgs a{};
     a.dout = dout; a.dout_bf16 = bf; a.uo = Uo; a.scale = sc2; a.shift = sh2;
@@ -321,20 +352,19 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     if (!attr1) { DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr1 = true; }
     StageScope _sc(ST_OUT_LN, st); count_launch();
     { cudaError_t pre = cudaGetLastError(); if (pre != cudaSuccess) { set_cuda_error(pre, "before bwd_out"); return DGSCT_ERR_CUDA; } }
-    bwd_out_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
-    { cudaError_t e_ = cudaGetLastError();
-      if (e_ != cudaSuccess) {
-        fprintf(stderr, "bwd_out launch failed: grid %d block %d smem %zu C %d rows %lld\n", rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, C, (long long)R);
-        set_cuda_error(e_, "bwd_out"); return DGSCT_ERR_CUDA; } }
+    // vectorised kernel: also produces the bn2-backward column sums (colA = sum dB2, colB = sum dB2*Uo)
+    bn2_sums_done = launch_bwd_out_vec(a, use_bn ? colA : nullptr, use_bn ? colB : nullptr, st);
+    if (!bn2_sums_done) bwd_out_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
+    KCHECK("bwd_out");
   }
   // bn2 backward: dUo = A*dB2 + B*Uo + Cc
   if (use_bn) {
     StageScope _sc(ST_BN_FINALIZE, st); count_launch(3);
-    col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, st>>>(gUo, bf, C, Uo, 0, C, R, C, colA, colB);
+    if (!bn2_sums_done) col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, st>>>(gUo, bf, C, Uo, 0, C, R, C, colA, colB);
     bn_bwd_coeffs_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, 1, train, colA, colB, (const float*)(fw + fp.bn2_mean),
                                                            (const float*)(fw + fp.bn2_rstd), P.bn2_w, (double)R, coefA, coefB, coefC,
                                                            G.bn2_w, G.bn2_b);
-    affine_combine_kernel<<<ew_grid, 256, 0, st>>>(gUo, bf, C, Uo, C, coefA, coefB, coefC, R, C);
+    launch_affine_combine(gUo, bf, C, Uo, C, coefA, coefB, coefC, R, C, ew_grid, st);
     KCHECK("bn2_bwd");
   }
   // ---- 2. up projection: dZr = dUo . Wup ; dWup += dUo^T . Zr ---------------------------------------------------
@@ -369,7 +399,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       bn_bwd_coeffs_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, 1, train, colA, colB, (const float*)(fw + fp.bn1_mean),
                                                               (const float*)(fw + fp.bn1_rstd), P.bn1_w, (double)R, coefA, coefB, coefC,
                                                               G.bn1_w, G.bn1_b);
-      affine_combine_kernel<<<ew_grid, 256, 0, st>>>(gZ, bf, ldz, Z, Cd, coefA, coefB, coefC, R, Cd);
+      launch_affine_combine(gZ, bf, ldz, Z, Cd, coefA, coefB, coefC, R, Cd, ew_grid, st);
     }
     KCHECK("bn1_bwd");
   }
@@ -399,7 +429,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     static bool attr2 = false;
     if (!attr2) { DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_gate_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr2 = true; }
     StageScope _sc(ST_BWD_GATE_LN, st); count_launch();
-    bwd_gate_ln_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
+    if (!launch_bwd_gate_ln_vec(a, BT, st))
+      bwd_gate_ln_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
     KCHECK("bwd_gate_ln");
   }
   // ---- 5. spatial gate --------------------------------------------------------------------------------------------
@@ -541,7 +572,11 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
                 to_tc_full<tc::EpiOut<false, OUT_STORE, false, false, false>>(e5), e5, AxIdentity{}, true));
     { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
       if (K > 256) return DGSCT_ERR_UNSUPPORTED;
-      col_softmax_bwd_kernel<<<BT, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, gQ, bf, N, K);
+      { const dim3 grid(csm_num_chunks(N), BT);
+        float* part = (float*)(ws + bp.csm_part);
+        count_launch();
+        col_softmax_bwd_partial_kernel<<<grid, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, part, N, K);
+        col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
       KCHECK("col_softmax_bwd"); }
     // dV = P . dTp + dL1 . T + dobar / N
     EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;

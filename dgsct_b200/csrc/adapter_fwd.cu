@@ -319,7 +319,8 @@ static int gemm_auto(int stage, const char* name, bool allow_tc, const tc::Opera
   count_launch();
   if (allow_tc) {
     tc::Params p;
-    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint);
+    const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint, 0, false, tc::epi_row_independent<TE>::value,
+                                   tc::epi_stage_bytes<TE>::value);
     if (rc == DGSCT_OK) {
       cudaError_t e = tc::launch(p, te, st);
       if (e != cudaSuccess) { set_cuda_error(e, name); return DGSCT_ERR_CUDA; }

@@ -375,26 +375,69 @@ __global__ void row_softmax_bwd_kernel(void* __restrict__ dq, const void* __rest
 }
 
 // per frame, columns of (N,K): dL1 = P*(dP - sum_n dP*P)   (dP fp32 in, dL1 act dtype out)
-__global__ void col_softmax_bwd_kernel(const float* __restrict__ dP, const void* __restrict__ P, int p_bf, void* __restrict__ dL1,
-                                       int out_bf, int N, int K) {
+// Two kernels over a (row-chunk, frame) grid like the forward's column softmax (a frame per block would leave half of
+// the SMs idle at BT = 80): per-chunk partial dot products, then combine + apply.
+__global__ void __launch_bounds__(256) col_softmax_bwd_partial_kernel(const float* __restrict__ dP, const void* __restrict__ P, int p_bf,
+                                                                      float* __restrict__ part, int N, int K) {
   extern __shared__ float sm[];             // [groups][K]
-  const int b = blockIdx.x;
+  const int s_ = blockIdx.x, b = blockIdx.y, S = gridDim.x;
   const int groups = blockDim.x / K;
   const int k = threadIdx.x % K, g = threadIdx.x / K;
   const bool active = g < groups;
+  const int rows = csm_chunk_rows(N);
+  const int n0 = s_ * rows, n1 = min(N, n0 + rows);
   const size_t base = (size_t)b * N * K;
-  float s = 0.f;
-  if (active)
-    for (int n = g; n < N; n += groups) s += dP[base + (size_t)n * K + k] * ld_act(P, base + (size_t)n * K + k, p_bf);
-  if (active) sm[g * K + k] = s;
+  float acc = 0.f;
+  if (active) {
+    for (int n = n0 + g; n < n1; n += groups) acc += dP[base + (size_t)n * K + k] * ld_act(P, base + (size_t)n * K + k, p_bf);
+    sm[g * K + k] = acc;
+  }
   __syncthreads();
-  if (active) { s = 0.f; for (int j = 0; j < groups; ++j) s += sm[j * K + k]; }
-  if (active)
-    for (int n = g; n < N; n += groups) {
-      const size_t i = base + (size_t)n * K + k;
-      st_act(dL1, i, ld_act(P, i, p_bf) * (dP[i] - s), out_bf);
-    }
+  if (active && g == 0) {
+    float t = 0.f;
+    for (int j = 0; j < groups; ++j) t += sm[j * K + k];
+    part[((size_t)b * S + s_) * K + k] = t;
+  }
 }
+__global__ void __launch_bounds__(256) col_softmax_bwd_apply_kernel(const float* __restrict__ dP, const void* __restrict__ P, int p_bf,
+                                                                    const float* __restrict__ part, void* __restrict__ dL1, int out_bf,
+                                                                    int N, int K) {
+  const int s_ = blockIdx.x, b = blockIdx.y, S = gridDim.x;
+  const int groups = blockDim.x / K;
+  const int k = threadIdx.x % K, g = threadIdx.x / K;
+  if (g >= groups) return;
+  float t = 0.f;
+  for (int j = 0; j < S; ++j) t += part[((size_t)b * S + j) * K + k];
+  const int rows = csm_chunk_rows(N);
+  const int n0 = s_ * rows, n1 = min(N, n0 + rows);
+  const size_t base = (size_t)b * N * K;
+  for (int n = n0 + g; n < n1; n += groups) {
+    const size_t i = base + (size_t)n * K + k;
+    st_act(dL1, i, ld_act(P, i, p_bf) * (dP[i] - t), out_bf);
+  }
+}
+
+// vectorised in-place g = A[c]*g + B[c]*x + Cc[c] for bf16 g (pitch g_ld) and fp32 x (pitch x_ld); C % 8 == 0, 16-byte rows
+__global__ void __launch_bounds__(256) affine_combine_vec_kernel(bf16* __restrict__ g, long long g_ld, const float* __restrict__ x,
+                                                                 long long x_ld, const float* __restrict__ A, const float* __restrict__ B,
+                                                                 const float* __restrict__ Cc, long long rows, int C) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i - r * nvec) * 8;
+    const uint4 raw = *reinterpret_cast<const uint4*>(g + r * g_ld + c);
+    float v[8], xv[8], a[8], bb[8], cc[8];
+    unpack8(raw, v);
+    ldf8(x + r * x_ld + c, xv);
+    ldf8(A + c, a); ldf8(B + c, bb); ldf8(Cc + c, cc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(a[j], v[j], fmaf(bb[j], xv[j], cc[j]));
+    *reinterpret_cast<uint4*>(g + r * g_ld + c) = pack8(v);
+  }
+}
+inline void launch_affine_combine(void* g, int g_bf16, long long g_ld, const float* x, long long x_ld, const float* A, const float* B,
+                                  const float* Cc, long long rows, int C, int ew_grid, cudaStream_t st);
 
 // out[k,c] += sum_b in[b,k,c]     (gradient of the shared latent tokens through T' = T + ...)
 __global__ void sum_frames_kernel(const float* __restrict__ in, int BT, size_t per_frame, float* __restrict__ out) {
@@ -466,6 +509,352 @@ __global__ void densify_grouped_kernel(const float* __restrict__ src, int out_ch
   if (i >= out_ch * ld) return;
   const int o = i / ld, c = i % ld;
   dst[i] = (c < in_ch && c / ipg == o / opg) ? src[(size_t)o * ipg + (c - (o / opg) * ipg)] : 0.f;
+}
+
+
+// =====================================================================================================================
+// Vectorised (bf16, 16-byte) versions of the two LayerNorm-backward row kernels.  Same row geometry as rowwise.cuh
+// (LPR lanes per row, VPL vectors of 8 channels per lane), so a lane owns FIXED columns for all of its rows: the column
+// reductions (d ln weight / bias, the BatchNorm-backward sums, the channel-gate gradient) are accumulated in registers
+// over the block's rows and flushed once per block -- the scalar kernels issue one shared-memory (and, for the channel
+// gate, one GLOBAL) atomic per element.
+// =====================================================================================================================
+template <int LPR>
+__device__ __forceinline__ float rowgroups_sum(float v) {      // sum over the 32/LPR row groups of a warp (same columns)
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out = gate * LN_post(B2) [AVE] or LN_post(gate * B2) [AVS], B2 = uo*scale + shift.  Also accumulates the bn2-backward
+// column sums colA[c] += sum dB2, colB[c] += sum dB2*uo (NULL to skip) so that no separate reduction pass is needed.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256, 1) bwd_out_vec_kernel(BwdOutArgs a, float* __restrict__ colA, float* __restrict__ colB) {
+  extern __shared__ float sm[];                 // [4][C] block partials: d_lnw, d_lnb, colA, colB
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR;
+  const int C = a.C, nvec = C >> 3;
+  const float invC = 1.f / (float)C;
+  for (int c = threadIdx.x; c < 4 * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const bf16* dout = reinterpret_cast<const bf16*>(a.dout);
+  bf16* db2 = reinterpret_cast<bf16*>(a.db2);
+  const float g = a.gate ? a.gate[0] : 1.f;
+  const float gpre = a.gate_before_ln ? g : 1.f, gpost = a.gate_before_ln ? 1.f : g;
+  float cw[VPL][8], cb[VPL][8], ca[VPL][8], cq[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { cw[i][j] = 0.f; cb[i][j] = 0.f; ca[i][j] = 0.f; cq[i][j] = 0.f; }
+  float gate_acc = 0.f;
+  const long long step = (long long)gridDim.x * 8 * RPW;
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * RPW; base < a.rows; base += step) {
+    const long long row = base + rsub;
+    const bool rv = row < a.rows;
+    float v[VPL][8], dy[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
+        float sc[8], sh[8];
+        ldf8(a.uo + row * C + vi * 8, v[i]);
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dout + row * C + vi * 8));
+        ldf8(a.scale + vi * 8, sc);
+        ldf8(a.shift + vi * 8, sh);
+        unpack8(raw, dy[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] = fmaf(v[i][j], sc[j], sh[j]) * gpre; sum += v[i][j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] = 0.f; dy[i][j] = 0.f; }
+      }
+    }
+    float rstd = 1.f, s1 = 0.f, s2 = 0.f;
+    if (a.ln_w) {
+      const float mean = group_sum<LPR>(sum) * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (sub + LPR * i < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; sq += dlt * dlt; }
+        }
+      rstd = rsqrtf(group_sum<LPR>(sq) * invC + a.eps);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = sub + LPR * i;
+        if (rv && vi < nvec) {
+          float w[8], bb[8];
+          ldf8(a.ln_w + vi * 8, w);
+          ldf8(a.ln_b + vi * 8, bb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xhat = (v[i][j] - mean) * rstd;
+            const float dL = dy[i][j] * gpost;
+            if (!a.gate_before_ln && a.gate) gate_acc += dy[i][j] * fmaf(xhat, w[j], bb[j]);   // AVE: d_gate = sum dOut * L
+            cw[i][j] += dL * xhat;
+            cb[i][j] += dL;
+            const float dxh = dL * w[j];
+            s1 += dxh; s2 += dxh * xhat;
+            v[i][j] = xhat; dy[i][j] = dxh;
+          }
+        }
+      }
+      s1 = group_sum<LPR>(s1) * invC;
+      s2 = group_sum<LPR>(s2) * invC;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
+        float u[8], o[8];
+        ldf8(a.uo + row * C + vi * 8, u);                 // second touch of the row: L1/L2 hit
+        if (a.ln_w) {
+          if (a.gate_before_ln && a.gate) {
+            float sc[8], sh[8];
+            ldf8(a.scale + vi * 8, sc);
+            ldf8(a.shift + vi * 8, sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gate_acc += rstd * (dy[i][j] - s1 - v[i][j] * s2) * fmaf(u[j], sc[j], sh[j]);   // AVS: dv * B2
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rstd * (dy[i][j] - s1 - v[i][j] * s2) * gpre;
+        } else {
+          if (a.gate) {
+            float sc[8], sh[8];
+            ldf8(a.scale + vi * 8, sc);
+            ldf8(a.shift + vi * 8, sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gate_acc += dy[i][j] * fmaf(u[j], sc[j], sh[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = dy[i][j] * g;
+        }
+        *reinterpret_cast<uint4*>(db2 + row * C + vi * 8) = pack8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ca[i][j] += o[j]; cq[i][j] += o[j] * u[j]; }
+      }
+    }
+  }
+  // flush: row groups of the warp -> block partials in shared memory -> one global atomic per column per block
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = sub + LPR * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float w_ = rowgroups_sum<LPR>(cw[i][j]), b_ = rowgroups_sum<LPR>(cb[i][j]);
+      const float a_ = rowgroups_sum<LPR>(ca[i][j]), q_ = rowgroups_sum<LPR>(cq[i][j]);
+      if (rsub == 0 && vi < nvec) {
+        const int c = vi * 8 + j;
+        atomicAdd(&sm[c], w_); atomicAdd(&sm[C + c], b_); atomicAdd(&sm[2 * C + c], a_); atomicAdd(&sm[3 * C + c], q_);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (a.ln_w) {
+      if (a.d_lnw) atomicAdd(&a.d_lnw[c], sm[c]);
+      if (a.d_lnb) atomicAdd(&a.d_lnb[c], sm[C + c]);
+    }
+    if (colA) atomicAdd(&colA[c], sm[2 * C + c]);
+    if (colB) atomicAdd(&colB[c], sm[3 * C + c]);
+  }
+  if (a.gate && a.d_gate) {
+    gate_acc = warp_sum(gate_acc);
+    if (lane == 0 && gate_acc != 0.f) atomicAdd(a.d_gate, gate_acc);
+  }
+}
+
+// LN_before + gate-combine backward; grid (row chunks, BT): a block stays inside one frame, so the channel-gate gradient
+// dm[b, c] is a per-lane register sum as well.
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256, 1) bwd_gate_ln_vec_kernel(BwdGateLnArgs a, int rows_per_chunk) {
+  extern __shared__ float sm[];                 // [3][C] block partials: d_lnw, d_lnb, dm
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR;
+  const int C = a.C, nvec = C >> 3, b = blockIdx.y;
+  const float invC = 1.f / (float)C;
+  for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const bf16* x1 = reinterpret_cast<const bf16*>(a.x1);
+  const bf16* dyp = reinterpret_cast<const bf16*>(a.dy);
+  bf16* dx1 = reinterpret_cast<bf16*>(a.dx1);
+  const float* mrow = a.m + (size_t)b * C;
+  const float tau_term = a.tau ? a.gamma * a.tau[b] : 0.f;
+  float cw[VPL][8], cb[VPL][8], cm[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { cw[i][j] = 0.f; cb[i][j] = 0.f; cm[i][j] = 0.f; }
+  float tau_acc = 0.f;
+  const int n_begin = blockIdx.x * rows_per_chunk;
+  const int n_end = min(a.N, n_begin + rows_per_chunk);
+  for (int nb = n_begin + warp * RPW; nb < n_end; nb += 8 * RPW) {
+    const int n = nb + rsub;
+    const bool rv = n < n_end;
+    const long long row = (long long)b * a.N + n;
+    const float gbase = rv ? (a.beta * a.sig[row] + tau_term + 1.f - a.alpha) : 0.f;
+    float v[VPL][8], dv[VPL][8];
+    uint4 raw[VPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(x1 + row * C + vi * 8));
+        const uint4 rd = __ldg(reinterpret_cast<const uint4*>(dyp + row * C + vi * 8));
+        float mm[8];
+        ldf8(mrow + vi * 8, mm);
+        unpack8(raw[i], v[i]);
+        unpack8(rd, dv[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] *= fmaf(a.alpha, mm[j], gbase); sum += v[i][j]; }
+      } else {
+        raw[i] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[i][j] = 0.f; dv[i][j] = 0.f; }
+      }
+    }
+    if (a.ln_w) {
+      const float mean = group_sum<LPR>(sum) * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        if (sub + LPR * i < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; sq += dlt * dlt; }
+        }
+      const float rstd = rsqrtf(group_sum<LPR>(sq) * invC + a.eps);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int vi = sub + LPR * i;
+        if (rv && vi < nvec) {
+          float w[8];
+          ldf8(a.ln_w + vi * 8, w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xhat = (v[i][j] - mean) * rstd;
+            cw[i][j] += dv[i][j] * xhat;
+            cb[i][j] += dv[i][j];
+            const float dxh = dv[i][j] * w[j];
+            s1 += dxh; s2 += dxh * xhat;
+            v[i][j] = xhat; dv[i][j] = dxh;
+          }
+        }
+      }
+      s1 = group_sum<LPR>(s1) * invC;
+      s2 = group_sum<LPR>(s2) * invC;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dv[i][j] = rstd * (dv[i][j] - s1 - v[i][j] * s2);      // dYg
+    }
+    float rowdot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
+        float xr[8], mm[8], o[8];
+        unpack8(raw[i], xr);
+        ldf8(mrow + vi * 8, mm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dgm = dv[i][j] * xr[j];
+          rowdot += dgm;
+          cm[i][j] += dgm;
+          o[j] = dv[i][j] * fmaf(a.alpha, mm[j], gbase);
+        }
+        *reinterpret_cast<uint4*>(dx1 + row * C + vi * 8) = pack8(o);
+      }
+    }
+    rowdot = group_sum<LPR>(rowdot);
+    if (rv && sub == 0) {
+      a.dsig[row] = a.beta * rowdot;
+      tau_acc += rowdot;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = sub + LPR * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float w_ = rowgroups_sum<LPR>(cw[i][j]), b_ = rowgroups_sum<LPR>(cb[i][j]), m_ = rowgroups_sum<LPR>(cm[i][j]);
+      if (rsub == 0 && vi < nvec) {
+        const int c = vi * 8 + j;
+        atomicAdd(&sm[c], w_); atomicAdd(&sm[C + c], b_); atomicAdd(&sm[2 * C + c], m_);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (a.ln_w) {
+      if (a.d_lnw) atomicAdd(&a.d_lnw[c], sm[c]);
+      if (a.d_lnb) atomicAdd(&a.d_lnb[c], sm[C + c]);
+    }
+    atomicAdd(&a.dm_acc[(size_t)b * C + c], a.alpha * sm[2 * C + c]);
+  }
+  if (a.dtau) {
+    tau_acc = warp_sum(tau_acc);
+    if (lane == 0 && tau_acc != 0.f) atomicAdd(&a.dtau[b], a.gamma * tau_acc);
+  }
+}
+
+struct BwdOutLaunch {
+  const BwdOutArgs& a; float* colA; float* colB; cudaStream_t st; bool* ok;
+  template <int LPR, int VPL> void run() {
+    if (VPL > 4) { *ok = false; return; }
+    const long long rows_per_block = 8LL * (32 / LPR);
+    long long blocks = (a.rows + rows_per_block - 1) / rows_per_block;
+    if (blocks > 2 * 148) blocks = 2 * 148;
+    bwd_out_vec_kernel<LPR, (VPL > 4 ? 1 : VPL)><<<(unsigned)blocks, 256, (size_t)4 * a.C * 4, st>>>(a, colA, colB);
+    *ok = true;
+  }
+};
+// returns false when the caller must run the scalar kernel (+ its own column reduction)
+inline bool launch_bwd_out_vec(const BwdOutArgs& a, float* colA, float* colB, cudaStream_t st) {
+  if (a.C % 8 || !a.dout_bf16 || !a.db2_bf16 || a.C > 2048) return false;
+  bool ok = false;
+  if (!dispatch_row_geometry(a.C / 8, BwdOutLaunch{a, colA, colB, st, &ok})) return false;
+  return ok;
+}
+
+struct BwdGateLnLaunch {
+  const BwdGateLnArgs& a; int BT; cudaStream_t st; bool* ok;
+  template <int LPR, int VPL> void run() {
+    if (VPL > 4) { *ok = false; return; }
+    const int rows_per_iter = 8 * (32 / LPR);
+    int chunks = (a.N + rows_per_iter - 1) / rows_per_iter;          // at least one block iteration per chunk
+    const int want = (4 * 148 + BT - 1) / BT;                        // ~4 blocks per SM overall
+    if (chunks > want) chunks = want;
+    if (chunks < 1) chunks = 1;
+    int rpc = (a.N + chunks - 1) / chunks;
+    rpc = (rpc + rows_per_iter - 1) / rows_per_iter * rows_per_iter;
+    chunks = (a.N + rpc - 1) / rpc;
+    bwd_gate_ln_vec_kernel<LPR, (VPL > 4 ? 1 : VPL)><<<dim3(chunks, BT), 256, (size_t)3 * a.C * 4, st>>>(a, rpc);
+    *ok = true;
+  }
+};
+inline bool launch_bwd_gate_ln_vec(const BwdGateLnArgs& a, int BT, cudaStream_t st) {
+  if (a.C % 8 || !a.dy_bf16 || !a.x1_bf16 || !a.dx1_bf16 || a.C > 2048) return false;
+  bool ok = false;
+  if (!dispatch_row_geometry(a.C / 8, BwdGateLnLaunch{a, BT, st, &ok})) return false;
+  return ok;
+}
+
+inline void launch_affine_combine(void* g, int g_bf16, long long g_ld, const float* x, long long x_ld, const float* A, const float* B,
+                                  const float* Cc, long long rows, int C, int ew_grid, cudaStream_t st) {
+  if (g_bf16 && C % 8 == 0 && g_ld % 8 == 0 && x_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const long long total = rows * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (blocks < 1) blocks = 1;
+    affine_combine_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<bf16*>(g), g_ld, x, x_ld, A, B, Cc, rows, C);
+  } else {
+    affine_combine_kernel<<<ew_grid, 256, 0, st>>>(g, g_bf16, g_ld, x, x_ld, A, B, Cc, rows, C);
+  }
 }
 
 }  // namespace dgsct

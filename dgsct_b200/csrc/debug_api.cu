@@ -1,7 +1,6 @@
 // Debug / bring-up entry points of the C ABI (used by tests/test_gpu_gemm_tc.py).
 #include "epilogues.cuh"
 #include "tc_epilogues.cuh"
-#include "gemm_tc_np.cuh"
 
 using namespace dgsct;
 
@@ -18,7 +17,8 @@ int dgsct_debug_gemm_bf16(const void* A, const void* B, float* D, int M, int N, 
     tc::OperandDesc a{A, a_mn_major, lda, sa, a_mn_major ? K : M, a_mn_major ? M : K};
     tc::OperandDesc b{B, b_mn_major, ldb, sb, b_mn_major ? K : N, b_mn_major ? N : K};
     tc::Params p;
-    int rc = tc::make_params(p, a, b, M, N, K, batch, bn_hint & 0xFFFF, use_tc == 2 ? 0 : stages_hint);
+    // (staging sized for the fp32 functor; the bf16 one needs half of it)
+    int rc = tc::make_params(p, a, b, M, N, K, batch, bn_hint & 0xFFFF, stages_hint, false, true, 4096);
     if (rc) return rc;
     // bn_hint bit 16: store D as bf16 into the same buffer (timing experiments); bits 20..21: epilogue ablation
     const int out_bf16 = (bn_hint >> 16) & 1;
@@ -29,11 +29,11 @@ int dgsct_debug_gemm_bf16(const void* A, const void* B, float* D, int M, int N, 
       e.alpha = 1.f; e.out = D; e.ld = N; e.sb = (long long)M * N;
       if ((bn_hint >> 24) & 1) e.out = nullptr;   // timing experiment: no global stores
       if ((bn_hint >> 25) & 1) e.sb = 0;          // timing experiment: every frame writes the same (L2-resident) tile
-      err = (use_tc == 2) ? tc::launch_np(p, e, st, stages_hint > 0 ? stages_hint : 96) : tc::launch(p, e, st);
+      err = tc::launch(p, e, st);
     } else {
       tc::EpiStore<false, ACT_NONE, false, false> e{};
       e.alpha = 1.f; e.out = D; e.ld = N; e.sb = (long long)M * N;
-      err = (use_tc == 2) ? tc::launch_np(p, e, st, stages_hint > 0 ? stages_hint : 96) : tc::launch(p, e, st);
+      err = tc::launch(p, e, st);
     }
     if (err != cudaSuccess) { set_cuda_error(err, "debug_gemm_tc"); return DGSCT_ERR_CUDA; }
     return DGSCT_OK;

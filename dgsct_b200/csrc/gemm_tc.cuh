@@ -38,7 +38,14 @@ struct Params {
   int a_boxes, b_boxes, a_box_bytes, b_box_bytes;
   uint32_t tmem_cols;
   int acc_bufs;                 // TMEM accumulators per CTA: 2 = epilogue overlaps the next tile's MMAs, 1 = single
-  int ctas_per_sm;              // 1: one big-smem CTA per SM; 2: two half-smem CTAs per SM (long-K products)
+  int ctas_per_sm;              // 1: one big-smem CTA per SM; 2: two half-smem CTAs per SM
+  int b_resident;               // shared (unbatched) B small enough to stay in shared memory for the CTA's lifetime: it is
+                                // loaded once (all n-blocks x k-blocks) and the ring streams A only
+  int stage_out;                // short-K products: functors with chunk32() write their tile through a per-warp shared-memory
+                                // staging buffer (this many bytes per epilogue warp, 0 = off) so that global stores / residual
+                                // loads are row-contiguous 64-128 B segments
+  int rows_per_frame;           // > 0: A is (batch*rows_per_frame, K) contiguous and B is shared, so the frames are flattened
+                                // into one M extent (no per-frame tile padding); the epilogue recovers (b, m) per row
   int* err_flag;                // device int set to non-zero when a bounded wait expires
   int debug_mode;               // bring-up only: 1 = epilogue skips the TMEM loads, 2 = skips loads and functor
 };
@@ -138,6 +145,23 @@ struct epi_whole_row { static constexpr bool value = false; };
 template <typename T>
 struct epi_whole_row<T, decltype((void)T::kWholeRow)> { static constexpr bool value = T::kWholeRow; };
 
+// functors that accept whole 32-column blocks and a staging buffer declare chunk32(...) (see tc_epilogues.cuh)
+template <typename T, typename = void>
+struct epi_has_chunk32 { static constexpr bool value = false; };
+template <typename T>
+struct epi_has_chunk32<T, decltype((void)T::kHasChunk32)> { static constexpr bool value = T::kHasChunk32; };
+// functors whose chunk() tolerates a different frame index b in every lane (no warp-wide per-frame reduction)
+template <typename T, typename = void>
+struct epi_row_independent { static constexpr bool value = false; };
+template <typename T>
+struct epi_row_independent<T, decltype((void)T::kRowIndependent)> { static constexpr bool value = T::kRowIndependent; };
+
+// staging bytes a functor needs per epilogue warp: 32 rows x 64 B (bf16 blocks) or x 128 B (fp32 blocks)
+template <typename T, typename = void>
+struct epi_stage_bytes { static constexpr int value = 0; };
+template <typename T>
+struct epi_stage_bytes<T, decltype((void)T::kStageBytes)> { static constexpr int value = T::kHasChunk32 ? T::kStageBytes : 0; };
+
 // shared-memory matrix descriptor (tcgen05): start address, leading/stride byte offsets (16-B units),
 // descriptor version 1, swizzle mode in bits [61,64)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, int sw_bytes) {
@@ -213,16 +237,21 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  // layout: [ring: stages x (A [+ B])] [resident B: n_blocks x num_k x b_stage_bytes] [barriers] [output staging]
+  const int stage_bytes = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
+  const int num_k = (p.K + p.BK - 1) / p.BK;
+  const int n_blocks = (p.N + p.BN - 1) / p.BN, m_blocks = (p.M + BM - 1) / BM;
+  uint8_t* bres = smem + (size_t)p.stages * stage_bytes;
+  const size_t bres_bytes = p.b_resident ? (size_t)n_blocks * num_k * p.b_stage_bytes : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bres + bres_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* tmem_full_bar = bars + 2 * MAX_STAGES;        // [2]
   uint64_t* tmem_empty_bar = bars + 2 * MAX_STAGES + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  uint64_t* bres_bar = bars + 2 * MAX_STAGES + 5;
+  uint8_t* out_stage = reinterpret_cast<uint8_t*>(bars) + 256;   // 16-byte aligned (bars is 1024-aligned)
 
-  const int num_k = (p.K + p.BK - 1) / p.BK;
-  const int n_blocks = (p.N + p.BN - 1) / p.BN, m_blocks = (p.M + BM - 1) / BM;
   const int tiles_per_batch = n_blocks * m_blocks;
   const int fpack = p.fpack;                              // frames per tile (1 unless packed)
   const int kbf = p.kb_frames;
@@ -240,6 +269,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[a]), EPI_WARPS);
     }
+    mbar_init(smem_u32(bres_bar), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
@@ -254,9 +284,23 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
     if (lane == 0) {
       // ===== TMA producer =====
       const int a_atom = p.a_sw / 2, b_atom = p.b_sw / 2;   // elements per swizzle row
-      const uint32_t tx_bytes = (uint32_t)(p.a_boxes * p.a_box_bytes + fpack * p.b_boxes * p.b_box_bytes);
+      const uint32_t tx_bytes = (uint32_t)(p.a_boxes * p.a_box_bytes + (p.b_resident ? 0 : fpack * p.b_boxes * p.b_box_bytes));
       int it = 0;   // running k-block counter across tiles (ring position)
       bool ok = true;
+      if (p.b_resident) {                                   // the whole (shared) B operand, once
+        const uint32_t rb = smem_u32(bres_bar);
+        mbar_expect_tx(rb, (uint32_t)(n_blocks * num_k * p.b_boxes * p.b_box_bytes));
+        for (int j = 0; j < n_blocks; ++j)
+          for (int kb = 0; kb < num_k; ++kb) {
+            const uint32_t dst = smem_u32(bres + (size_t)(j * num_k + kb) * p.b_stage_bytes);
+            if (p.b_mn_major) {
+              for (int q = 0; q < p.b_boxes; ++q)
+                tma_load_3d(dst + q * p.b_box_bytes, &p.mapB, j * p.BN + q * b_atom, kb * p.BK, 0, rb);
+            } else {
+              tma_load_3d(dst, &p.mapB, kb * p.BK, j * p.BN, 0, rb);
+            }
+          }
+      }
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
         const int grp = t / tiles_per_batch, r = t % tiles_per_batch;
         const int bfirst = kbf > 0 ? grp * kbf : grp * fpack;
@@ -279,7 +323,8 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           } else {
             tma_load_3d(sa, &p.mapA, k0, m0, p.a_batched ? b : 0, fb);
           }
-          if (p.b_mn_major) {
+          if (p.b_resident) {
+          } else if (p.b_mn_major) {
             for (int f = 0; f < fpack; ++f)       // a frame past the batch is out of bounds for TMA: zero fill
               for (int j = 0; j < p.b_boxes; ++j)
                 tma_load_3d(sb + (f * p.b_boxes + j) * p.b_box_bytes, &p.mapB, n0 + j * b_atom, k0, p.b_batched ? b + f : 0, fb);
@@ -302,6 +347,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
       const int ksteps = p.BK / 16;
       int it = 0, ti = 0;
       bool ok = true;
+      if (p.b_resident) ok = mbar_wait(smem_u32(bres_bar), 0, p.err_flag);
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x, ++ti) {
         const int acc = acc_bufs == 2 ? (ti & 1) : 0;
         const uint32_t acc_ph = acc_bufs == 2 ? ((ti >> 1) & 1) : (ti & 1);
@@ -310,6 +356,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
         const int grp = t / tiles_per_batch;
+        const int nblk = (t % tiles_per_batch) % n_blocks;
         const int nfr = kbf > 0 ? min(kbf, p.batch - grp * kbf) : 1;
         for (int kb = 0; kb < nfr * num_k; ++kb, ++it) {
           const int s = it % p.stages;
@@ -318,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           if (!ok) break;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + p.a_stage_bytes;
+          const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)(nblk * num_k + kb) * p.b_stage_bytes) : sa + p.a_stage_bytes;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, p.a_sw);
             const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, p.b_sw);
@@ -347,11 +394,15 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       tc_fence_after();
-      const int m = m0 + lane_grp * 32 + lane;
+      int m = m0 + lane_grp * 32 + lane, bq = b0;
       const bool row_ok = m < p.M;
+      if (p.rows_per_frame > 0) {                         // (b, m) of this lane's row inside the flattened M extent
+        bq = row_ok ? m / p.rows_per_frame : 0;           // rows past the end keep a valid frame index for loads
+        if (row_ok) m -= bq * p.rows_per_frame;
+      }
       const uint32_t lane_base = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(lane_grp * 32) << 16);
       if (p.debug_mode < 2 && !(whole_row && half == 1)) {
-        epi.begin(b0, m, row_ok);
+        epi.begin(bq, m, row_ok);
         const int c_begin = whole_row ? 0 : half * 32, c_step = whole_row ? 32 : 64;
         for (int c = c_begin; c < BNI; c += c_step) {
           float v0[16], v1[16];
@@ -363,16 +414,22 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v0[j] = (float)(c + j); v1[j] = (float)(c + 16 + j); }
           }
+          if constexpr (epi_has_chunk32<EPI>::value) {
+            if (p.stage_out && fpack == 1) {
+              epi.chunk32(bq, m, n0 + c, v0, v1, two, row_ok, p.N, out_stage + (size_t)(warp - 2) * p.stage_out);
+              continue;
+            }
+          }
           if (fpack == 1) {
-            epi.chunk(b0, m, n0 + c, v0, row_ok, p.N);
-            if (two) epi.chunk(b0, m, n0 + c + 16, v1, row_ok, p.N);
+            epi.chunk(bq, m, n0 + c, v0, row_ok, p.N);
+            if (two) epi.chunk(bq, m, n0 + c + 16, v1, row_ok, p.N);
           } else {                               // packed frames: 16-column chunks never straddle a frame (BN % 16 == 0)
             const int f0 = c / p.BN, f1 = (c + 16) / p.BN;
             epi.chunk(b0 + f0, m, c - f0 * p.BN, v0, row_ok && (b0 + f0 < p.batch), p.N);
             if (two) epi.chunk(b0 + f1, m, c + 16 - f1 * p.BN, v1, row_ok && (b0 + f1 < p.batch), p.N);
           }
         }
-        epi.end(b0, m, row_ok);
+        epi.end(bq, m, row_ok);
       }
       tc_fence_before();
       __syncwarp();
@@ -402,7 +459,7 @@ int* tc_err_flag_device_ptr();
 // Fills `p` (tensor maps, tile recipe) for D = A . B^T.  Returns DGSCT_OK, or DGSCT_ERR_UNSUPPORTED when the
 // operands cannot be described to TMA (alignment) so the caller can take the SIMT kernel instead.
 int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint = 0,
-                int stages_hint = 0, bool sum_over_batch = false);
+                int stages_hint = 0, bool sum_over_batch = false, bool allow_flatten = false, int stage_bytes_per_warp = 0);
 size_t smem_bytes(const Params& p);
 int num_sms();
 bool operands_ok(const OperandDesc& A, const OperandDesc& B, int K);

@@ -65,7 +65,12 @@ static int encode(CUtensorMap* map, const OperandDesc& o, int batch, int box0, i
   return r == CUDA_SUCCESS ? DGSCT_OK : DGSCT_ERR_UNSUPPORTED;
 }
 
-size_t smem_bytes(const Params& p) { return 1024 + (size_t)p.stages * (p.a_stage_bytes + p.b_stage_bytes) + 256; }
+size_t smem_bytes(const Params& p) {
+  const int num_k = (p.K + p.BK - 1) / p.BK, n_blocks = (p.N + p.BN - 1) / p.BN;
+  const size_t ring = (size_t)p.stages * (p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes));
+  const size_t bres = p.b_resident ? (size_t)n_blocks * num_k * p.b_stage_bytes : 0;
+  return 1024 + ring + bres + 256 + (size_t)EPI_WARPS * p.stage_out;
+}
 
 int num_sms() {
   static thread_local int n = 0, dev = -1;
@@ -79,9 +84,21 @@ int num_sms() {
   return n;
 }
 
-int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint,
-                int stages_hint, bool sum_over_batch) {
-  if (!operands_ok(A, B, K)) return DGSCT_ERR_UNSUPPORTED;
+int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint,
+                int stages_hint, bool sum_over_batch, bool allow_flatten, int stage_bytes_per_warp) {
+  if (!operands_ok(A_in, B, K)) return DGSCT_ERR_UNSUPPORTED;
+  OperandDesc A = A_in;
+  // Frames flattened into one M extent: A[b] (M, K) rows are contiguous across frames and B is shared, so
+  // (batch, M) is just (batch*M) rows -- no 128-row tile padding per frame (N = 36/64/144 tokens at the deep stages).
+  p.rows_per_frame = 0;
+  if (allow_flatten && !A.mn_major && A.batch_stride != 0 && B.batch_stride == 0 && A.batch_stride == (long long)M * A.ld &&
+      !sum_over_batch && batch > 1 && (long long)M * batch < (1LL << 30) && !getenv("DGSCT_NO_FLATTEN")) {
+    p.rows_per_frame = M;
+    A.rows = M * batch;
+    A.batch_stride = 0;
+    M = M * batch;
+    batch = 1;
+  }
   p.M = M; p.N = N; p.K = K; p.batch = batch;
   p.a_mn_major = A.mn_major; p.b_mn_major = B.mn_major;
   p.a_batched = A.batch_stride != 0; p.b_batched = B.batch_stride != 0;
@@ -113,30 +130,72 @@ int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, in
   }
   p.a_stage_bytes = round_up(p.a_boxes * p.a_box_bytes, 1024);
   p.b_stage_bytes = round_up(p.fpack * p.b_boxes * p.b_box_bytes, 1024);
-  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int num_k = (K + p.BK - 1) / p.BK;
-  // Long-K products (main loop dominated, L2-latency sensitive) run two half-smem CTAs per SM: two independent
-  // TMA/MMA streams per SM hide each other's barrier round trips (968 vs 713 TFLOP/s on the stage-0 resampler).
-  // Short-K products keep one big-smem CTA per SM with a double-buffered accumulator.
+  const int n_blocks = (N + BN - 1) / BN;
   if (sum_over_batch) {
     // frames per tile: enough frame groups to fill ~2 tiles per SM, the rest of the batch is accumulated in the tile
-    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const long long tiles = (long long)((M + BM - 1) / BM) * n_blocks;
     long long groups = (2LL * num_sms() + tiles - 1) / tiles;
     if (groups < 1) groups = 1;
     if (groups > batch) groups = batch;
     p.kb_frames = (int)((batch + groups - 1) / groups);
   }
   const long long k_iters = (long long)num_k * (p.kb_frames > 0 ? p.kb_frames : 1);
+  const bool short_k = k_iters < 8;
+  const int BNI = BN * p.fpack;
+  // Short-K products are bound by shared-memory fill traffic and by the epilogue's global stores, not by the MMAs:
+  //  * a shared B operand that fits stays resident for the CTA's lifetime (it used to be re-streamed for every tile);
+  //  * the output tile is staged through shared memory for row-contiguous stores;
+  //  * two CTAs per SM (when both keep a double-buffered accumulator) hide each other's TMA round trips.
+  p.stage_out = (short_k && p.fpack == 1 && !getenv("DGSCT_NO_STAGE_OUT")) ? stage_bytes_per_warp : 0;
+  const size_t out_stage = (size_t)EPI_WARPS * p.stage_out;
+  const size_t bres_total = (size_t)n_blocks * num_k * p.b_stage_bytes;
+  const bool bres_possible = !p.b_batched && !sum_over_batch && p.fpack == 1 && !getenv("DGSCT_NO_BRES");
   const char* force = getenv("DGSCT_TC_CTAS");
-  p.ctas_per_sm = force ? atoi(force) : ((k_iters >= 8 && 2 * stage_bytes <= 104 * 1024) ? 2 : 1);
-  if (p.ctas_per_sm != 2) p.ctas_per_sm = 1;
-  const int budget = p.ctas_per_sm == 2 ? 104 * 1024 : 200 * 1024;
-  int stages = stages_hint > 0 ? stages_hint : budget / stage_bytes;
-  if (stages < 2) stages = 2;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const size_t cta_budget[3] = {0, 220 * 1024, 110 * 1024};
+  auto plan = [&](int ctas, bool bres, int& stages_out) {
+    const size_t fixed = 1024 + 256 + out_stage + (bres ? bres_total : 0);
+    if (fixed >= cta_budget[ctas]) return false;
+    const size_t ring_stage = (size_t)p.a_stage_bytes + (bres ? 0 : p.b_stage_bytes);
+    long long st = (long long)((cta_budget[ctas] - fixed) / ring_stage);
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    stages_out = (int)st;
+    return st >= 2;
+  };
+  int ctas = 1, stages = 0;
+  bool bres = false;
+  if (short_k) {
+    // measured (scripts/gemm_skinny.py): a second CTA per SM is worth more than a deeper ring or a resident B, so it
+    // comes first; B stays resident whenever it fits next to >= 3 A stages
+    const bool two_ok = BNI <= 128;                      // 2 x (double-buffered accumulator <= 256 columns) per SM
+    int st = 0;
+    if (two_ok && bres_possible && bres_total <= 48 * 1024 && plan(2, true, st) && st >= 3) { ctas = 2; bres = true; stages = st; }
+    else if (two_ok && plan(2, false, st)) { ctas = 2; stages = st; }
+    else if (bres_possible && bres_total <= 112 * 1024 && plan(1, true, st) && st >= 3) { ctas = 1; bres = true; stages = st; }
+    else if (plan(1, false, st)) { ctas = 1; stages = st; }
+    else return DGSCT_ERR_UNSUPPORTED;
+  } else {
+    // Long-K products (main loop dominated): two half-smem CTAs per SM when two stages each fit -- two independent
+    // TMA/MMA streams hide each other's barrier round trips (968 vs 713 TFLOP/s on the stage-0 resampler).
+    int st = 0;
+    const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+    if (2 * stage_bytes <= 104 * 1024 && plan(2, false, st)) { ctas = 2; stages = st; }
+    else if (plan(1, false, st)) { ctas = 1; stages = st; }
+    else return DGSCT_ERR_UNSUPPORTED;
+  }
+  if (force) {
+    const int f = atoi(force);
+    int st = 0;
+    if ((f == 1 || f == 2) && f != ctas && plan(f, bres && (f == 1 || bres_total <= 48 * 1024), st)) {
+      bres = bres && (f == 1 || bres_total <= 48 * 1024);
+      ctas = f; stages = st;
+    }
+  }
+  if (stages_hint > 0 && stages_hint < stages) stages = stages_hint < 2 ? 2 : stages_hint;
+  p.ctas_per_sm = ctas;
+  p.b_resident = bres ? 1 : 0;
   p.stages = stages;
   if (smem_bytes(p) > 227 * 1024) return DGSCT_ERR_UNSUPPORTED;
-  const int BNI = BN * p.fpack;
   const int max_cols = p.ctas_per_sm == 2 ? 256 : 512;
   p.acc_bufs = (2 * BNI <= max_cols) ? 2 : 1;
   uint32_t cols = 32;

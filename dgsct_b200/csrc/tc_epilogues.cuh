@@ -62,9 +62,146 @@ __device__ __forceinline__ void store_row16(void* out, size_t idx, const float (
 
 __device__ __forceinline__ int nvalid16(int n0, int N) { const int r = N - n0; return r < 0 ? 0 : (r > 16 ? 16 : r); }
 
+// ---- warp-cooperative block I/O through the per-warp staging buffer (Params::stage_out) -------------------------------
+// A warp owns a 32-row x 32-column block of the output, lane = row.  Written straight from registers every store
+// instruction touches 32 different rows (16 bytes each: 32 L2 requests, half-filled sectors).  Staged through shared
+// memory (XOR-swizzled 16-byte chunks, conflict free both ways) each instruction instead covers whole 64-byte (bf16) or
+// 128-byte (fp32) row segments.  `my_row_off` = element offset of this lane's row in the destination (any per-row
+// mapping: frames, flattened frames, padded pitches); `ncols` = valid columns of the block (0..32).
+constexpr unsigned FULL = 0xffffffffu;
+
+template <bool BF16>
+__device__ __forceinline__ void warp_store_block32(void* out, long long my_row_off, int n0, const float (&v0)[16],
+                                                   const float (&v1)[16], int ncols, bool row_ok, uint8_t* stage) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (BF16) {
+    uint4 c[4];
+    c[0] = make_uint4(pack_bf16x2(v0[0], v0[1]), pack_bf16x2(v0[2], v0[3]), pack_bf16x2(v0[4], v0[5]), pack_bf16x2(v0[6], v0[7]));
+    c[1] = make_uint4(pack_bf16x2(v0[8], v0[9]), pack_bf16x2(v0[10], v0[11]), pack_bf16x2(v0[12], v0[13]), pack_bf16x2(v0[14], v0[15]));
+    c[2] = make_uint4(pack_bf16x2(v1[0], v1[1]), pack_bf16x2(v1[2], v1[3]), pack_bf16x2(v1[4], v1[5]), pack_bf16x2(v1[6], v1[7]));
+    c[3] = make_uint4(pack_bf16x2(v1[8], v1[9]), pack_bf16x2(v1[10], v1[11]), pack_bf16x2(v1[12], v1[13]), pack_bf16x2(v1[14], v1[15]));
+    const int f = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ f) << 4)) = c[j];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = 8 * i + (lane >> 2), ch = lane & 3;
+      const uint4 val = *reinterpret_cast<const uint4*>(stage + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+      const long long roff = __shfl_sync(FULL, my_row_off, r);
+      const int rok = __shfl_sync(FULL, (int)row_ok, r);
+      const int col = ch * 8;
+      if (rok && col < ncols) {
+        bf16* dst = reinterpret_cast<bf16*>(out) + roff + n0 + col;
+        if (col + 8 <= ncols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          *reinterpret_cast<uint4*>(dst) = val;
+        } else {
+          const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (col + e < ncols) {
+              const unsigned short h = (unsigned short)((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+              reinterpret_cast<unsigned short*>(dst)[e] = h;
+            }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+      *reinterpret_cast<float4*>(stage + lane * 128 + (((j + 4) ^ (lane & 7)) << 4)) = make_float4(v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3), ch = lane & 7;
+      const float4 val = *reinterpret_cast<const float4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+      const long long roff = __shfl_sync(FULL, my_row_off, r);
+      const int rok = __shfl_sync(FULL, (int)row_ok, r);
+      const int col = ch * 4;
+      if (rok && col < ncols) {
+        float* dst = reinterpret_cast<float*>(out) + roff + n0 + col;
+        if (col + 4 <= ncols && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          *reinterpret_cast<float4*>(dst) = val;
+        } else {
+          const float w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e < ncols) dst[e] = w[e];
+        }
+      }
+    }
+  }
+}
+
+// the reverse for a bf16 source: r0|r1 receive this lane's 32 columns (0 where invalid)
+__device__ __forceinline__ void warp_load_block32_bf16(const bf16* src, long long my_row_off, int n0, int ncols, bool row_ok,
+                                                       uint8_t* stage, float (&r0)[16], float (&r1)[16]) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2), ch = lane & 3;
+    const long long roff = __shfl_sync(FULL, my_row_off, r);
+    const int rok = __shfl_sync(FULL, (int)row_ok, r);
+    const int col = ch * 8;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (rok && col < ncols) {
+      const bf16* p = src + roff + n0 + col;
+      if (col + 8 <= ncols && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        val = *reinterpret_cast<const uint4*>(p);
+      } else {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (col + e < ncols) w[e >> 1] |= (uint32_t)reinterpret_cast<const unsigned short*>(p)[e] << ((e & 1) * 16);
+        val = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    *reinterpret_cast<uint4*>(stage + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)) = val;
+  }
+  __syncwarp();
+  const int f = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(stage + lane * 64 + ((j ^ f) << 4));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+      if (j < 2) { r0[8 * j + 2 * q] = __bfloat162float(t.x); r0[8 * j + 2 * q + 1] = __bfloat162float(t.y); }
+      else { r1[8 * (j - 2) + 2 * q] = __bfloat162float(t.x); r1[8 * (j - 2) + 2 * q + 1] = __bfloat162float(t.y); }
+    }
+  }
+}
+
+// Per-frame column sums of a warp's 16-column chunk when the lanes' rows may belong to different frames (flattened M
+// extent): one masked 16-shuffle reduction per frame present in the warp (one when the slab lies inside a frame).
+// f(bb, col_of_lane, sum, owner) is called for every frame bb with the owning lanes' totals.
+template <typename F>
+__device__ __forceinline__ void segmented_colsum16(const float (&v)[16], int b, bool row_ok, int n0, int N, F&& f) {
+  const int lane = threadIdx.x & 31;
+  const int b_lo = __reduce_min_sync(FULL, row_ok ? b : 0x7fffffff);
+  const int b_hi = __reduce_max_sync(FULL, row_ok ? b : -1);
+  const int col = n0 + colsum16_owner_col(lane);
+  const bool owner = ((lane & 1) == 0) && col < N;
+  for (int bb = b_lo; bb <= b_hi; ++bb) {
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = (row_ok && b == bb) ? v[j] : 0.f;
+    const float s = warp_colsum16(w);
+    f(bb, col, s, owner);
+  }
+}
+
 // out[b, m, n] = act(alpha*acc + bias_m[m] + bias_n[n])  (+ per-frame column sums, + global fp64 column moments)
 template <bool OUT_BF16, int ACT, bool COLSUM, bool STATS>
 struct EpiStore {
+  static constexpr bool kHasChunk32 = true;
+  static constexpr int kStageBytes = OUT_BF16 ? 2048 : 4096;
+  static constexpr bool kRowIndependent = true;
   void* out; long long ld, sb;
   const float* bias_m; const float* bias_n;
   float alpha;
@@ -72,8 +209,7 @@ struct EpiStore {
   double* stat_sum; double* stat_sq;
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
-  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
-    const int nvalid = nvalid16(n0, N);
+  __device__ __forceinline__ void transform(int m, int n0, float (&v)[16], bool row_ok, int nvalid) const {
     const float bm = (bias_m && row_ok) ? bias_m[m] : 0.f;
     if (bias_n) {
       float bn[16];
@@ -91,25 +227,44 @@ struct EpiStore {
       if (ACT == ACT_SIGMOID) x = __frcp_rn(1.f + __expf(-x));
       v[j] = x;
     }
-    if (out && row_ok && nvalid > 0) store_row16<OUT_BF16>(out, (size_t)((long long)b * sb + (long long)m * ld + n0), v, nvalid);
+  }
+  __device__ __forceinline__ void reduce(int b, int n0, float (&v)[16], bool row_ok, int nvalid, int N) const {
     if (COLSUM || STATS) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = (row_ok && j < nvalid) ? v[j] : 0.f;
-      float q[16];
+      if (COLSUM) {
+        float* cs = colsum; const int nt = ncols_total;
+        segmented_colsum16(v, b, row_ok, n0, N, [cs, nt](int bb, int col, float s, bool owner) {
+          if (owner) atomicAdd(&cs[(long long)bb * nt + col], s);
+        });
+      }
       if (STATS) {
+        float q[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) q[j] = v[j] * v[j];
-      }
-      const float s = warp_colsum16(v);
-      const int lane = threadIdx.x & 31;
-      const int col = n0 + colsum16_owner_col(lane);
-      const bool owner = ((lane & 1) == 0) && col < N;
-      if (COLSUM && owner) atomicAdd(&colsum[(long long)b * ncols_total + col], s);
-      if (STATS) {
+        const float s = warp_colsum16(v);
         const float s2 = warp_colsum16(q);
-        if (owner) { atomicAdd(&stat_sum[col], (double)s); atomicAdd(&stat_sq[col], (double)s2); }
+        const int lane = threadIdx.x & 31;
+        const int col = n0 + colsum16_owner_col(lane);
+        if (((lane & 1) == 0) && col < N) { atomicAdd(&stat_sum[col], (double)s); atomicAdd(&stat_sq[col], (double)s2); }
       }
     }
+  }
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    transform(m, n0, v, row_ok, nvalid);
+    if (out && row_ok && nvalid > 0) store_row16<OUT_BF16>(out, (size_t)((long long)b * sb + (long long)m * ld + n0), v, nvalid);
+    reduce(b, n0, v, row_ok, nvalid, N);
+  }
+  // 32 columns at once through the warp's staging buffer (v1 holds columns n0+16.. when `two`)
+  __device__ __forceinline__ void chunk32(int b, int m, int n0, float (&v0)[16], float (&v1)[16], bool two, bool row_ok,
+                                          int N, uint8_t* stage) {
+    const int nv0 = nvalid16(n0, N), nv1 = two ? nvalid16(n0 + 16, N) : 0;
+    transform(m, n0, v0, row_ok, nv0);
+    if (two) transform(m, n0 + 16, v1, row_ok, nv1);
+    if (out) warp_store_block32<OUT_BF16>(out, (long long)b * sb + (long long)m * ld, n0, v0, v1, nv0 + nv1, row_ok, stage);
+    reduce(b, n0, v0, row_ok, nv0, N);
+    if (two) reduce(b, n0 + 16, v1, row_ok, nv1, N);
   }
 };
 
@@ -136,6 +291,9 @@ struct EpiTokUpdate {
 
 // out[b,m,n] = resid[b,m,n] + gate[0]*acc      (bf16 in / bf16 out)
 struct EpiResidual {
+  static constexpr bool kHasChunk32 = true;
+  static constexpr int kStageBytes = 2048;
+  static constexpr bool kRowIndependent = true;
   bf16* out; const bf16* resid; long long ld, sb; const float* gate; float g;
   __device__ __forceinline__ void begin(int, int, bool) { g = gate[0]; }
   __device__ __forceinline__ void end(int, int, bool) {}
@@ -160,10 +318,21 @@ struct EpiResidual {
     }
     store_row16<true>(out, idx, v, nvalid);
   }
+  __device__ __forceinline__ void chunk32(int b, int m, int n0, float (&v0)[16], float (&v1)[16], bool two, bool row_ok,
+                                          int N, uint8_t* stage) {
+    const int ncols = nvalid16(n0, N) + (two ? nvalid16(n0 + 16, N) : 0);
+    const long long off = (long long)b * sb + (long long)m * ld;
+    float r0[16], r1[16];
+    warp_load_block32_bf16(resid, off, n0, ncols, row_ok, stage, r0, r1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { v0[j] = fmaf(g, v0[j], r0[j]); v1[j] = fmaf(g, v1[j], r1[j]); }
+    warp_store_block32<true>(out, off, n0, v0, v1, ncols, row_ok, stage);
+  }
 };
 
 // colsum[b,n] += mul[b,n] * sum_m relu(acc + bias[n])
 struct EpiReluMulColsum {
+  static constexpr bool kRowIndependent = true;
   const float* bias; const float* mul; float* colsum; int ncols; int mul_ld;
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
@@ -173,15 +342,16 @@ struct EpiReluMulColsum {
     load16_guard(bias + n0, bn, nvalid);
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = (row_ok && j < nvalid) ? fmaxf(v[j] + bn[j], 0.f) : 0.f;
-    const float s = warp_colsum16(v);
-    const int lane = threadIdx.x & 31;
-    const int col = n0 + colsum16_owner_col(lane);
-    if (((lane & 1) == 0) && col < N) atomicAdd(&colsum[(long long)b * ncols + col], mul ? s * mul[(long long)b * mul_ld + col] : s);
+    float* cs = colsum; const float* mu = mul; const int nc = ncols, mld = mul_ld;
+    segmented_colsum16(v, b, row_ok, n0, N, [cs, mu, nc, mld](int bb, int col, float s, bool owner) {
+      if (owner) atomicAdd(&cs[(long long)bb * nc + col], mu ? s * mu[(long long)bb * mld + col] : s);
+    });
   }
 };
 
 // rowsum[b,m] += sum_n relu(acc + bias[n]) * mul[b,n] * w[n]
 struct EpiSpatialRowsum {
+  static constexpr bool kRowIndependent = true;
   const float* bias; const float* mul; const float* w; float* rowsum; int mul_ld; int nrows; float acc;
   __device__ __forceinline__ void begin(int, int, bool) { acc = 0.f; }
   __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
@@ -201,6 +371,7 @@ struct EpiSpatialRowsum {
 // Q[b,m,0:32] = softmax_k(acc[0:32])    (N == 32, one N-block), bf16
 struct EpiRowSoftmax32 {
   static constexpr bool kWholeRow = true;
+  static constexpr bool kRowIndependent = true;
   bf16* out; long long ld, sb; float lo[16];
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
@@ -229,14 +400,14 @@ struct EpiRowSoftmax32 {
 
 // zr[b,m,n] = relu(acc*scale[n] + shift[n]) (bf16) ; optional fp32 tap of acc        (bn1 + ReLU folded)
 struct EpiAffineRelu {
+  static constexpr bool kHasChunk32 = true;
+  static constexpr int kStageBytes = 2048;
+  static constexpr bool kRowIndependent = true;
   bf16* zr; long long ldz; int rows_per_batch; const float* scale; const float* shift; float* ztap; int Cd;
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
-  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
-    const int nvalid = nvalid16(n0, N);
-    if (!row_ok || nvalid <= 0) return;
-    const long long row = (long long)b * rows_per_batch + m;
-    if (ztap) {
+  __device__ __forceinline__ void transform(long long row, int n0, float (&v)[16], bool row_ok, int nvalid) const {
+    if (ztap && row_ok) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j < nvalid) ztap[row * Cd + n0 + j] = v[j];
@@ -246,7 +417,21 @@ struct EpiAffineRelu {
     load16_guard(shift + n0, sh, nvalid);
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+  }
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    if (!row_ok || nvalid <= 0) return;
+    const long long row = (long long)b * rows_per_batch + m;
+    transform(row, n0, v, row_ok, nvalid);
     store_row16<true>(zr, (size_t)(row * ldz + n0), v, nvalid);
+  }
+  __device__ __forceinline__ void chunk32(int b, int m, int n0, float (&v0)[16], float (&v1)[16], bool two, bool row_ok,
+                                          int N, uint8_t* stage) {
+    const int nv0 = nvalid16(n0, N), nv1 = two ? nvalid16(n0 + 16, N) : 0;
+    const long long row = (long long)b * rows_per_batch + m;
+    transform(row, n0, v0, row_ok, nv0);
+    if (two) transform(row, n0 + 16, v1, row_ok, nv1);
+    warp_store_block32<true>(zr, row * ldz, n0, v0, v1, nv0 + nv1, row_ok, stage);
   }
 };
 

@@ -59,6 +59,14 @@ CASES = [
     (192, 32, 300, 2, 1, 1, False, False),       # latent-token update: both operands token-major
     (100, 192, 32, 2, 0, 1, False, False),       # x update: K = 32
     (1536, 32, 36, 2, 1, 1, False, False),
+    # short-K, shared B: resident B + staged (row-contiguous) stores + frames flattened into one M extent
+    (36, 40, 96, 7, 0, 0, False, True),          # 36-token frames: 32-row slabs straddle frames
+    (70, 90, 40, 5, 0, 0, False, True),          # output rows not 16-byte aligned (scalar tail of the staged store)
+    (144, 200, 130, 3, 0, 0, False, True),       # ragged N and K
+    (4096, 32, 96, 3, 0, 0, False, True),        # token logits at the stage-0 audio shape
+    (576, 384, 384, 2, 0, 0, False, True),       # two n-blocks, B too large to stay resident next to a second CTA
+    (64, 1536, 192, 4, 0, 0, False, True),       # six n-blocks, resident B covers all of them
+    (300, 96, 64, 3, 0, 0, False, False),        # per-frame B: no flattening, no resident B
 ]
 
 
