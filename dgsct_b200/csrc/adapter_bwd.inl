@@ -45,7 +45,9 @@ namespace tc {
 // tensor-core twin (row-major output only; transposed outputs use EpiOutT)
 template <bool OUT_BF16, int MODE, bool RESID, bool BCAST, bool CSCALE>
 struct EpiOut {
-  static constexpr bool kHasChunk32 = (MODE == OUT_STORE) || (MODE == OUT_ADD && OUT_BF16);
+  // staged (row-contiguous) I/O only for pure stores: staging a residual / accumulate LOAD measured slower than the direct
+  // per-row access (see EpiResidual)
+  static constexpr bool kHasChunk32 = (MODE == OUT_STORE) && !RESID;
   static constexpr int kStageBytes = OUT_BF16 ? 2048 : 4096;
   static constexpr bool kRowIndependent = true;
   void* out; long long ld, sb; float alpha; const float* alpha_ptr; float al;
@@ -156,7 +158,8 @@ static GemmOperand simt_operand(const tc::OperandDesc& o, int is_bf16) {
 // batch entry and adds atomically.
 template <typename TE, typename AX>
 static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const tc::OperandDesc& B, int b_bf16, int M, int N, int K,
-                    int batch, TE te, const EpiOut& se, AX ax, bool ax_identity, int bn_hint = 0, bool sum_b = false) {
+                    int batch, TE te, const EpiOut& se, AX ax, bool ax_identity, int bn_hint = 0, bool sum_b = false,
+                    bool split_k_ok = false) {
   StageScope _sc(g.stage, g.st);
   count_launch();
   if (g.allow_tc && a_bf16 && b_bf16 && ax_identity) {
@@ -170,8 +173,17 @@ static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const t
     }
     if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
   }
-  GemmShape sh{M, N, K, batch, 1};
-  cudaError_t e = launch_gemm_simt(sh, simt_operand(A, a_bf16), simt_operand(B, b_bf16), ax, se, g.st);
+  GemmShape sh{M, N, K, batch, 1, 1};
+  EpiOut se2 = se;
+  // skinny per-frame-vector products (M = BT rows): split the contraction over CTAs and add atomically.  The output is
+  // fp32 and either accumulating (OUT_ADD) or zero-initialised by the caller (OUT_STORE targets live in the zero region).
+  if (split_k_ok && M <= 128 && K >= 256 && batch == 1 && !se.out_bf16 && !se.resid && se.mode != OUT_ATOMIC) {
+    const int ctas = ceil_div(N, SG_BN) * ceil_div(M, SG_BM);
+    int ks = (2 * 148 + ctas - 1) / ctas;
+    if (ks > K / 64) ks = K / 64;
+    if (ks > 1) { sh.ksplit = ks; se2.mode = OUT_ATOMIC; }
+  }
+  cudaError_t e = launch_gemm_simt(sh, simt_operand(A, a_bf16), simt_operand(B, b_bf16), ax, se2, g.st);
   if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
   return DGSCT_OK;
 }
@@ -236,8 +248,9 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.daq = take(BT * (C + H) * 4); p.dobar = take(BT * C * 4); p.dr1 = take(BT * C * 4);
   p.colA = take(C * 4); p.colB = take(C * 4);
   p.dWup_d = take(C * ldz * 4); p.dWd_d = take(Cd * C * 4);
+  p.vB = take(BT * C * 4); p.vC = take(BT * C * 4);     // split-K targets of the skinny products (added atomically)
   p.zero_end = off;
-  p.vA = take(BT * C * 4); p.vB = take(BT * C * 4); p.vC = take(BT * C * 4); p.vD = take(BT * C * 4);
+  p.vA = take(BT * C * 4); p.vD = take(BT * C * 4);
   p.coefA = take(C * 4); p.coefB = take(C * 4); p.coefC = take(C * 4);
   p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
   p.opm = take(BT * C * 4);
@@ -485,7 +498,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     EpiOut e1 = eo(G.c_w, 0, H, 0, OUT_ADD);
     RC(run_gemm(GS, MN_(vA, BT, C, C, 0), 0, MN_(hsrc, BT, H, h_ld, 0), 0, C, H, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
     EpiOut e2 = eo(vB, 0, H, 0, OUT_STORE);
-    RC(run_gemm(GS, K_(vA, BT, C, C, 0), 0, MN_(P.c_w, C, H, H, 0), 0, BT, H, C, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
+    RC(run_gemm(GS, K_(vA, BT, C, C, 0), 0, MN_(P.c_w, C, H, H, 0), 0, BT, H, C, 1, tc::EpiNone{}, e2, AxIdentity{}, true, 0, false, true));
     // dph = dh * 1[h>0] -> vB in place ; d_bb += colsum ; dWb (H,C) += dph^T q ; dq = dph . Wb -> vC (BT,C)
     count_launch(2);
     vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, vB, H, hsrc, h_ld, 0.f, vB, H, BT, H);
@@ -494,7 +507,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     EpiOut e3 = eo(G.bott_w, 0, C, 0, OUT_ADD);
     RC(run_gemm(GS, MN_(vB, BT, H, H, 0), 0, MN_(qvec, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
     EpiOut e4 = eo(vC, 0, C, 0, OUT_STORE);
-    RC(run_gemm(GS, K_(vB, BT, H, H, 0), 0, MN_(P.bott_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e4, AxIdentity{}, true));
+    RC(run_gemm(GS, K_(vB, BT, H, H, 0), 0, MN_(P.bott_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e4, AxIdentity{}, true, 0, false, true));
     // q = aq1 * r1sum / N : daq1 = dq * r1sum / N ; dr1 = dq * aq1 / N
     count_launch(2);
     vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_MUL_SCALE, vC, C, r1sum, C, invN, daq1, daq_ld, BT, C);
@@ -532,8 +545,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     EpiOut e2 = eo(G.a2_w, 0, C, 0, OUT_ADD);
     RC(run_gemm(GS, MN_(vC, BT, H, H, 0), 0, MN_(vA, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
     EpiOut e3 = eo(dobar, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, K_(vB, BT, C, C, 0), 0, MN_(P.a1_w, C, C, C, 0), 0, BT, C, C, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
-    RC(run_gemm(GS, K_(vC, BT, H, H, 0), 0, MN_(P.a2_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
+    RC(run_gemm(GS, K_(vB, BT, C, C, 0), 0, MN_(P.a1_w, C, C, C, 0), 0, BT, C, C, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
+    RC(run_gemm(GS, K_(vC, BT, H, H, 0), 0, MN_(P.a2_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
     if (d.flags & DGSCT_F_TEMPORAL) {
       count_launch();
       temporal_bwd_kernel<<<BT, 128, 0, st>>>(use_tau ? dtau : nullptr, dtmap, tau, vA, P.t_w, C, dobar, G.t_w, G.t_b);

@@ -21,6 +21,9 @@ struct GemmOperand {
 
 struct GemmShape {
   int M, N, K, batch, groups;
+  int ksplit;   // > 1: the contraction is split over this many CTAs per tile (grid.z); the epilogue must then ADD ATOMICALLY
+                // into a zero-initialised (or accumulating) output.  Used for the skinny per-frame-vector products
+                // (M = BT rows, K = C up to 1536) whose 64x64 tiling yields only a few dozen CTAs.
 };
 
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 32, SG_THREADS = 256;
@@ -34,8 +37,11 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmShape sh, Gem
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Bs[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
-  const int z = blockIdx.z;
+  const int ks = sh.ksplit > 1 ? sh.ksplit : 1;
+  const int z = blockIdx.z / ks, kz = blockIdx.z % ks;
   const int b = z / sh.groups, gi = z % sh.groups;
+  const int kchunk = ((sh.K + ks - 1) / ks + SG_BK - 1) / SG_BK * SG_BK;
+  const int k_begin = kz * kchunk, k_end = min(sh.K, k_begin + kchunk);
   const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
   const char* Ap = reinterpret_cast<const char*>(A.p);
   const char* Bp = reinterpret_cast<const char*>(B.p);
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmShape sh, Gem
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const bool a_kfast = (A.s_k == 1), b_kfast = (B.s_k == 1);
-  for (int k0 = 0; k0 < sh.K; k0 += SG_BK) {
+  for (int k0 = k_begin; k0 < k_end; k0 += SG_BK) {
     // ---- stage A tile (BM x BK) -> As[k][m]
 #pragma unroll
     for (int i = 0; i < (SG_BM * SG_BK) / SG_THREADS; ++i) {
@@ -58,7 +64,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmShape sh, Gem
       if (a_kfast) { kk = e % SG_BK; mm = e / SG_BK; } else { mm = e % SG_BM; kk = e / SG_BM; }
       int gm = m0 + mm, gk = k0 + kk;
       float v = 0.f;
-      if (gm < sh.M && gk < sh.K) {
+      if (gm < sh.M && gk < k_end) {
         v = ld_act(Ap, (size_t)(a_off + (long long)gm * A.s_row + (long long)gk * A.s_k), A.is_bf16);
         v = ax(b, gi, gk, v);
       }
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(GemmShape sh, Gem
       if (b_kfast) { kk = e % SG_BK; nn = e / SG_BK; } else { nn = e % SG_BN; kk = e / SG_BN; }
       int gn = n0 + nn, gk = k0 + kk;
       float v = 0.f;
-      if (gn < sh.N && gk < sh.K)
+      if (gn < sh.N && gk < k_end)
         v = ld_act(Bp, (size_t)(b_off + (long long)gn * B.s_row + (long long)gk * B.s_k), B.is_bf16);
       Bs[kk][nn] = v;
     }
@@ -96,7 +102,7 @@ template <typename AX, typename EPI>
 inline cudaError_t launch_gemm_simt(const GemmShape& sh, const GemmOperand& A, const GemmOperand& B, AX ax, EPI epi,
                                     cudaStream_t st) {
   if (sh.M <= 0 || sh.N <= 0 || sh.batch <= 0) return cudaSuccess;
-  dim3 grid(ceil_div(sh.N, SG_BN), ceil_div(sh.M, SG_BM), sh.batch * sh.groups);
+  dim3 grid(ceil_div(sh.N, SG_BN), ceil_div(sh.M, SG_BM), sh.batch * sh.groups * (sh.ksplit > 1 ? sh.ksplit : 1));
   gemm_simt_kernel<AX, EPI><<<grid, SG_THREADS, 0, st>>>(sh, A, B, ax, epi);
   return cudaGetLastError();
 }

@@ -291,7 +291,10 @@ struct EpiTokUpdate {
 
 // out[b,m,n] = resid[b,m,n] + gate[0]*acc      (bf16 in / bf16 out)
 struct EpiResidual {
-  static constexpr bool kHasChunk32 = true;
+  // measured (bench.py stage table, DGSCT_NO_STAGE_OUT A/B): staging the residual LOAD costs more than the row-contiguous
+  // accesses save (x_update 2.33 ms staged vs 1.79 ms direct over the 48 calls), so this functor keeps the direct path;
+  // pure stores keep the staged one (up_sampler fp32: 1.27 vs 1.74 ms)
+  static constexpr bool kHasChunk32 = false;
   static constexpr int kStageBytes = 2048;
   static constexpr bool kRowIndependent = true;
   bf16* out; const bf16* resid; long long ld, sb; const float* gate; float g;

@@ -80,6 +80,7 @@ class GradBucketer:
         self._left = list(self._remaining)
         dev = self.buckets[0].flat.device if self.buckets else torch.device("cpu")
         self.comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        self._comm_used = False
 
     def zero_grad(self) -> None:
         for b in self.buckets:
@@ -93,13 +94,17 @@ class GradBucketer:
         self._left[bi] -= 1
         if self._left[bi] == 0:
             self.buckets[bi].all_reduce(self.group, self.comm_stream)
+            self._comm_used = self._comm_used or self.buckets[bi].work is not None
 
     def finish(self) -> None:
         """Wait for every outstanding all-reduce and turn sums into means (call before optimizer.step())."""
         for b in self.buckets:
             b.wait(self.group)
-        if self.comm_stream is not None:
+        # join the communication stream only if a collective was launched on it this step: with one rank nothing was,
+        # and waiting on a stream that is not part of an ongoing CUDA-graph capture would invalidate the capture
+        if self.comm_stream is not None and self._comm_used:
             torch.cuda.current_stream(self.comm_stream.device).wait_stream(self.comm_stream)
+        self._comm_used = False
 
     def total_bytes(self) -> int:
         return sum(b.flat.numel() * 4 for b in self.buckets)
