@@ -6,6 +6,10 @@
 // (textually included at the end of adapter_fwd.cu: one translation unit owns every header-defined kernel)
 #include "bwd_kernels.cuh"
 
+#include <stdlib.h>
+
+#include <vector>
+
 namespace dgsct {
 
 // ---- generic output epilogues for the backward products ------------------------------------------------------------
@@ -215,6 +219,28 @@ static T to_tcT(const EpiOut& e) {
 #define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 #define KCHECK(name) DGSCT_LAUNCH_CHECK(name)
 
+// ---- side stream for the parameter-gradient products ------------------------------------------------------------------
+// Every weight gradient (sum_b A_b . B_b^T, accumulated atomically into G.*) is off the critical path of the backward: the
+// activation gradients never read it.  They are therefore issued on an auxiliary stream forked from the caller's stream
+// (event record / wait: graph-capturable, so inside a captured train step they become parallel branches) and joined before
+// the call returns.  One auxiliary stream per (thread, device, caller stream), created on first use.
+struct SideStream { cudaStream_t s; cudaEvent_t ev; };
+static SideStream* side_stream_for(cudaStream_t main) {
+  struct Key { int dev; cudaStream_t st; SideStream side; };
+  static thread_local std::vector<Key> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  for (Key& k : cache)
+    if (k.dev == dev && k.st == main) return &k.side;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(main, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;   // never create inside a capture
+  SideStream sd{};
+  if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&sd.ev, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(sd.s); return nullptr; }
+  cache.push_back(Key{dev, main, sd});
+  return &cache.back().side;
+}
+
 struct BwdPlan {
   size_t fwd;                        // keep-mode forward workspace
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
@@ -346,6 +372,29 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       G_TK{ST_BWD_TOKEN, "bwd_token", st, tcp}, G_FC{ST_BWD_FC, "bwd_fc", st, tcp}, G_DW{ST_BWD_DWRES, "bwd_dwres", st, tcp},
       G_DO{ST_BWD_DOTHER, "bwd_dother", st, tcp};
   (void)GB;
+  // weight-gradient products go to the side stream (same stream when unavailable, profiling, or DGSCT_NO_SIDE is set)
+  // (tensor-core path only: the exact-fp32 path rebuilds relu(bn1(Z)) in a buffer that is reused later)
+  SideStream* side = (!tcp || prof_enabled() || getenv("DGSCT_NO_SIDE")) ? nullptr : side_stream_for(st);
+  const cudaStream_t sst = side ? side->s : st;
+  bool side_used = false;
+  auto fork_side = [&]() -> int {        // the side stream waits for everything enqueued on `st` so far
+    if (!side) return DGSCT_OK;
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, st));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->ev, 0));
+    side_used = true;
+    return DGSCT_OK;
+  };
+  auto join_side = [&]() -> int {        // `st` waits for the side stream
+    if (!side || !side_used) return DGSCT_OK;
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, side->s));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev, 0));
+    side_used = false;
+    return DGSCT_OK;
+  };
+  const Gemm S_UD{ST_BWD_UPDOWN, "bwd_updown_dw", sst, tcp}, S_SP{ST_BWD_SPATIAL, "bwd_spatial_dw", sst, tcp},
+      S_CH{ST_BWD_CHANNEL, "bwd_channel_dw", sst, tcp}, S_TK{ST_BWD_TOKEN, "bwd_token_dw", sst, tcp},
+      S_FC{ST_BWD_FC, "bwd_fc_dw", sst, tcp}, S_DW{ST_BWD_DWRES, "bwd_dwres", sst, tcp};
+  (void)G_DW;
   const int rgrid = (int)((R + 7) / 8 < 148 * 4 ? (R + 7) / 8 : 148 * 4);
   const int ew_grid = 148 * 8;
 
@@ -394,11 +443,12 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     EpiOut e1 = eo(gZ, bf, ldz, (long long)N * ldz, OUT_STORE);
     RC(run_gemm(G_UD, K_(gUo, N, C, C, (long long)N * C), bf, MN_(Wup_op, C, Cd, ld_up, 0), wbf, N, Cd, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    RC(fork_side());                                                  // gUo is final; Zr is a saved/recomputed activation
     EpiOut e2 = eo(dWup_d, 0, ldz, 0, OUT_ATOMIC);
-    RC(run_gemm(G_UD, MN_(gUo, N, C, C, (long long)N * C), bf, MN_(Zr, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
+    RC(run_gemm(S_UD, MN_(gUo, N, C, C, (long long)N * C), bf, MN_(Zr, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
                 to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true, 0, true));
-    { StageScope _sc(ST_MISC, st); count_launch();
-      ungroup_grad_kernel<<<ceil_div(C * (Cd / d.g), 256), 256, 0, st>>>(dWup_d, C, Cd, d.g, ldz, G.up_w);
+    { StageScope _sc(ST_MISC, sst); count_launch();
+      ungroup_grad_kernel<<<ceil_div(C * (Cd / d.g), 256), 256, 0, sst>>>(dWup_d, C, Cd, d.g, ldz, G.up_w);
       KCHECK("ungroup_up"); }
   }
   // relu + bn1 backward on dZr -> dZ (in place in gZ)
@@ -421,11 +471,12 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     EpiOut e1 = eo(gY, bf, C, (long long)N * C, OUT_STORE);
     RC(run_gemm(G_UD, K_(gZ, N, Cd, ldz, (long long)N * ldz), bf, MN_(Wd_op, Cd, C, ld_dn, 0), wbf, N, C, Cd, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    RC(fork_side());                                                  // gZ is final (bn1 backward applied)
     EpiOut e2 = eo(dWd_d, 0, C, 0, OUT_ATOMIC); e2.transposed = 1;      // D(c, cd) -> dWd_d[cd, c]
-    RC(run_gemm(G_UD, MN_(Y, N, C, C, (long long)N * C), bf, MN_(gZ, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
+    RC(run_gemm(S_UD, MN_(Y, N, C, C, (long long)N * C), bf, MN_(gZ, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
                 to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e2), e2, AxIdentity{}, true, 0, true));
-    { StageScope _sc(ST_MISC, st); count_launch();
-      ungroup_grad_kernel<<<ceil_div(Cd * (C / d.g), 256), 256, 0, st>>>(dWd_d, Cd, C, d.g, C, G.down_w);
+    { StageScope _sc(ST_MISC, sst); count_launch();
+      ungroup_grad_kernel<<<ceil_div(Cd * (C / d.g), 256), 256, 0, sst>>>(dWd_d, Cd, C, d.g, C, G.down_w);
       KCHECK("ungroup_down"); }
   }
   // ---- 4. ln_before + gate combine ------------------------------------------------------------------------------
@@ -477,8 +528,9 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("opm"); }
     // dWv2[j,c] += sum_b (1+m[b,c]) sum_n dz2[b,n,j] X1[b,n,c]
     if (tcp) {      // Xc = X1 (1+m) was kept by the forward: plain sum over frames
+      RC(fork_side());                                                // S2 = dz2 is not written again in this call
       EpiOut e3 = eo(G.v2_w, 0, C, 0, OUT_ATOMIC);
-      RC(run_gemm(G_SP, MN_(S2, N, H, H, (long long)N * H), 1, MN_(fw + fp.XcBuf, N, C, C, (long long)N * C), 1, H, C, N, BT,
+      RC(run_gemm(S_SP, MN_(S2, N, H, H, (long long)N * H), 1, MN_(fw + fp.XcBuf, N, C, C, (long long)N * C), 1, H, C, N, BT,
                   to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
     } else {
       EpiOut e3 = eo(G.v2_w, 0, C, 0, OUT_ATOMIC); e3.colscale = opm; e3.cs_ld = C;
@@ -525,8 +577,9 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     EpiOut e2 = eo(gX1, bf, C, (long long)N * C, OUT_ADD);
     RC(run_gemm(G_CH, K_(S1, N, C, C, (long long)N * C), bf, MN_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e2), e2, AxIdentity{}, true));
+    RC(fork_side());                                                  // S1 = dz1 is not written again in this call
     EpiOut e3 = eo(G.v1_w, 0, C, 0, OUT_ATOMIC);
-    RC(run_gemm(G_CH, MN_(S1, N, C, C, (long long)N * C), bf, MN_(X1, N, C, C, (long long)N * C), bf, C, C, N, BT,
+    RC(run_gemm(S_CH, MN_(S1, N, C, C, (long long)N * C), bf, MN_(X1, N, C, C, (long long)N * C), bf, C, C, N, BT,
                 to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
   }
   {
@@ -599,37 +652,41 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
     // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
+    RC(fork_side());                                                  // gQ = dL1 is final; sum_frames already added its share
     EpiOut e8 = eo(G.tokens, 0, C, 0, OUT_ATOMIC); e8.transposed = 1;
-    RC(run_gemm(G_TK, MN_(V, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
+    RC(run_gemm(S_TK, MN_(V, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
                 to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true, 0, true));
   }
   // ---- 8. token resampler ---------------------------------------------------------------------------------------------
   {
-    { StageScope _sc(ST_MISC, st); count_launch();
-      col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, st>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
+    RC(fork_side());                                                  // gV is final
+    { StageScope _sc(ST_MISC, sst); count_launch();
+      col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
       KCHECK("dfc_b"); }
     // dU = dV . Wfc ; dWfc += dV^T . U
     EpiOut e1 = eo(gU, bf, Co, (long long)N * Co, OUT_STORE);
     RC(run_gemm(G_FC, K_(gV, N, C, C, (long long)N * C), bf, MN_(Wfc_op, C, Co, ld_fc, 0), wbf, N, Co, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     EpiOut e2 = eo(G.fc_w, 0, Co, 0, OUT_ATOMIC);
-    RC(run_gemm(G_FC, MN_(gV, N, C, C, (long long)N * C), bf, MN_(U, N, Co, Co, (long long)N * Co), bf, C, Co, N, BT,
+    RC(run_gemm(S_FC, MN_(gV, N, C, C, (long long)N * C), bf, MN_(U, N, Co, Co, (long long)N * Co), bf, C, Co, N, BT,
                 to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true, 0, true));
     // dWres += sum_b dU_b . other_b^T ; d_bres ; dother_b = Wres^T . dU_b
+    RC(fork_side());                                                  // gU is final
     if (G.resample_w) {
       EpiOut e3 = eo(G.resample_w, 0, No, 0, OUT_ATOMIC);
-      RC(run_gemm(G_DW, K_(gU, N, Co, Co, (long long)N * Co), bf, K_(other, No, Co, Co, (long long)No * Co), bf, N, No, Co, BT,
+      RC(run_gemm(S_DW, K_(gU, N, Co, Co, (long long)N * Co), bf, K_(other, No, Co, Co, (long long)No * Co), bf, N, No, Co, BT,
                   to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
     }
     if (G.resample_b && !(d.flags & DGSCT_F_NO_CONV_BIAS)) {
-      StageScope _sc(ST_MISC, st); count_launch();
-      rowsum_frames_kernel<<<N, 256, 0, st>>>(gU, bf, BT, N, Co, G.resample_b);
+      StageScope _sc(ST_MISC, sst); count_launch();
+      rowsum_frames_kernel<<<N, 256, 0, sst>>>(gU, bf, BT, N, Co, G.resample_b);
       KCHECK("dres_b");
     }
     EpiOut e4 = eo(dother, bf, Co, (long long)No * Co, OUT_STORE);
     RC(run_gemm(G_DO, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gU, N, Co, Co, (long long)N * Co), bf, No, Co, N, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e4), e4, AxIdentity{}, true));
   }
+  RC(join_side());
   return DGSCT_OK;
 }
 

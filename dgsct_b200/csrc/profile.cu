@@ -31,6 +31,7 @@ static cudaEvent_t get_event() {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool prof_enabled() { return g_on.load(std::memory_order_relaxed) != 0; }
 
 void prof_begin(int, cudaStream_t st) {
   if (!g_on.load(std::memory_order_relaxed)) return;

@@ -18,6 +18,7 @@ const char* stage_name(int s);
 void prof_begin(int stage, cudaStream_t st);
 void prof_end(int stage, cudaStream_t st);
 void count_launch(int n = 1);
+bool prof_enabled();
 
 struct StageScope {
   int stage; cudaStream_t st;
