@@ -551,8 +551,13 @@ def run_engine(args, rank, world, local_rank):
         flops_conv = sum(2 * BT * dims(k, s)[1] * dims(k, s)[3] * dims(k, s)[2] for k, _, _, s in layer_list())
         t_conv = prof.get("resample_conv", (0.0, 0))[0] / psteps * 1e-3
         ach = flops_conv / t_conv / 1e12 if t_conv > 0 else 0.0
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the largest of the 48 launches (stage-0 audio resampler,
+        # 290 GFLOP; algorithmic 215.5 MB = 18.9 MB weights + 70.8 MB tokens + 125.8 MB output) from the committed
+        # `ncu --set full` export profiles/r01_ncu_full_gemm_aud_s0_raw.csv (89.85 MB read + 84.13 MB written before the
+        # kernel ended; the rest of the output was still in L2)
         roof = {"kernel": "resample_conv (token resampler GEMM, 48 launches/step)", "bound": "tensor", "achieved": ach,
-                "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src,
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": 173.97e6,
+                "traffic_launch": "stage-0 audio resampler launch (M=4096 N=192 K=2304 x 80 frames), ncu --set full", "peak_source": peak_src,
                 "share_of_step": (t_conv * 1e3) / max(sum(v[0] for v in prof.values()) / psteps, 1e-9)}
         tot_bytes = sum(alg_bytes(*dims(k, s), BT) for k, _, _, s in layer_list())
         tot_flops = sum(alg_flops(*dims(k, s), BT) for k, _, _, s in layer_list())
@@ -579,7 +584,14 @@ def run_engine(args, rank, world, local_rank):
                                   "bytes_per_step": bucketer.total_bytes() if world > 1 else 0}
         print(json.dumps(line), flush=True)
     if dist is not None:
-        dist.destroy_process_group()
+        # Captured graphs hold NCCL kernels: tearing the communicator down underneath them can block (seen at N=2: the
+        # line above was printed and destroy_process_group never returned).  Drain, line up, and leave without it.
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def cpu_baseline(args):

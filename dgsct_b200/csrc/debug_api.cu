@@ -22,7 +22,7 @@ int dgsct_debug_gemm_bf16(const void* A, const void* B, float* D, int M, int N, 
     if (rc) return rc;
     // bn_hint bit 16: store D as bf16 into the same buffer (timing experiments); bits 20..21: epilogue ablation
     const int out_bf16 = (bn_hint >> 16) & 1;
-    p.debug_mode = (bn_hint >> 20) & 3;
+    p.debug_mode = (bn_hint >> 20) & 15;   // bits 0-1: epilogue ablation, bit 2: no MMAs, bit 3: no TMA loads
     cudaError_t err;
     if (out_bf16) {
       tc::EpiStore<true, ACT_NONE, false, false> e{};

@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           ok = mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, p.err_flag);
           if (!ok) break;
           const uint32_t fb = smem_u32(&full_bar[s]);
+          if (p.debug_mode & 8) { mbar_arrive(fb); continue; }   // bring-up: no loads, the stage is "full" at once
           mbar_expect_tx(fb, tx_bytes);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + p.a_stage_bytes;
@@ -366,6 +367,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)(nblk * num_k + kb) * p.b_stage_bytes) : sa + p.a_stage_bytes;
+          if (p.debug_mode & 4) { mbar_arrive(smem_u32(&empty_bar[s])); continue; }   // bring-up: no MMAs, software release
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, p.a_sw);
             const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, p.b_sw);
@@ -373,7 +375,10 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           }
           umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage once these MMAs have read it
         }
-        if (ok) umma_commit(smem_u32(&tmem_full_bar[acc]));   // accumulator complete
+        if (ok) {
+          if (p.debug_mode & 4) mbar_arrive(smem_u32(&tmem_full_bar[acc]));
+          else umma_commit(smem_u32(&tmem_full_bar[acc]));   // accumulator complete
+        }
       }
     }
   } else {
@@ -401,13 +406,13 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         if (row_ok) m -= bq * p.rows_per_frame;
       }
       const uint32_t lane_base = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(lane_grp * 32) << 16);
-      if (p.debug_mode < 2 && !(whole_row && half == 1)) {
+      if ((p.debug_mode & 3) < 2 && !(whole_row && half == 1)) {
         epi.begin(bq, m, row_ok);
         const int c_begin = whole_row ? 0 : half * 32, c_step = whole_row ? 32 : 64;
         for (int c = c_begin; c < BNI; c += c_step) {
           float v0[16], v1[16];
           const bool two = (c + 32 <= BNI);
-          if (p.debug_mode == 0) {
+          if ((p.debug_mode & 3) == 0) {
             if (two) tmem_ld32(lane_base + (uint32_t)c, v0, v1);
             else tmem_ld16(lane_base + (uint32_t)c, v0);
           } else {
