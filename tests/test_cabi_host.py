@@ -120,3 +120,20 @@ def test_cpu_tensors_are_rejected_not_emulated():
     with pytest.raises(ValueError):
         with torch.no_grad():
             ad(x.squeeze(-1), o)
+
+
+def test_keep_and_saved_workspace_sizes(lib):
+    """DGSCT_F_KEEP selects the non-aliasing forward plan (larger); a backward from saved activations needs no recompute
+    region (smaller than dgsct_bwd_workspace_bytes)."""
+    d = _desc()
+    plain = lib.dgsct_workspace_bytes(C.byref(d))
+    d.flags = L.F_KEEP
+    keep = lib.dgsct_workspace_bytes(C.byref(d))
+    assert keep > plain > 0
+    d.flags = 0
+    full = lib.dgsct_bwd_workspace_bytes(C.byref(d))
+    saved = lib.dgsct_bwd_saved_workspace_bytes(C.byref(d))
+    assert 0 < saved < full
+    assert full - saved >= keep - 4096          # the difference is the recompute region (the keep plan)
+    bad = _desc(C=191)
+    assert lib.dgsct_bwd_saved_workspace_bytes(C.byref(bad)) == 0
