@@ -285,7 +285,6 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
       // ===== TMA producer =====
       const int a_atom = p.a_sw / 2, b_atom = p.b_sw / 2;   // elements per swizzle row
       const uint32_t tx_bytes = (uint32_t)(p.a_boxes * p.a_box_bytes + (p.b_resident ? 0 : fpack * p.b_boxes * p.b_box_bytes));
-      int it = 0;   // running k-block counter across tiles (ring position)
       bool ok = true;
       if (p.b_resident) {                                   // the whole (shared) B operand, once
         const uint32_t rb = smem_u32(bres_bar);
@@ -301,37 +300,51 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
             }
           }
       }
+      // The single-thread role loops are on the critical path of every k-block (scripts/gemm_pipe_probe.py: with neither
+      // loads nor MMAs the barrier ping-pong alone cost 0.3-0.6 us per k-block): no run-time division / modulo per k-block,
+      // ring position and phase are counters, shared-memory addresses are base + stage * stride.
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const bool one_group = (num_tiles == tiles_per_batch);
+      int st_i = 0; uint32_t st_ph = 0;                      // ring slot and its phase
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x) {
-        const int grp = t / tiles_per_batch, r = t % tiles_per_batch;
+        int grp = 0, r = t;
+        if (!one_group) { grp = t / tiles_per_batch; r = t - grp * tiles_per_batch; }
+        int mi = r, ni = 0;
+        if (n_blocks > 1) { mi = r / n_blocks; ni = r - mi * n_blocks; }
         const int bfirst = kbf > 0 ? grp * kbf : grp * fpack;
         const int nfr = kbf > 0 ? min(kbf, p.batch - bfirst) : 1;
-        const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
-        for (int kk = 0; kk < nfr * num_k; ++kk, ++it) {
-          const int b = bfirst + kk / num_k, kb = kk % num_k;
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          ok = mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1, p.err_flag);
+        const int m0 = mi * BM, n0 = ni * p.BN;
+        int b = bfirst, k0 = 0;
+        const int total = nfr * num_k;
+        for (int kk = 0; kk < total; ++kk) {
+          ok = mbar_wait(empty0 + 8u * st_i, st_ph ^ 1, p.err_flag);
           if (!ok) break;
-          const uint32_t fb = smem_u32(&full_bar[s]);
-          if (p.debug_mode & 8) { mbar_arrive(fb); continue; }   // bring-up: no loads, the stage is "full" at once
-          mbar_expect_tx(fb, tx_bytes);
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + p.a_stage_bytes;
-          const int k0 = kb * p.BK;
-          if (p.a_mn_major) {
-            for (int j = 0; j < p.a_boxes; ++j)
-              tma_load_3d(sa + j * p.a_box_bytes, &p.mapA, m0 + j * a_atom, k0, p.a_batched ? b : 0, fb);
+          const uint32_t fb = full0 + 8u * st_i;
+          if (p.debug_mode & 8) {                          // bring-up: no loads, the stage is "full" at once
+            mbar_arrive(fb);
           } else {
-            tma_load_3d(sa, &p.mapA, k0, m0, p.a_batched ? b : 0, fb);
+            mbar_expect_tx(fb, tx_bytes);
+            const uint32_t sa = smem_base + (uint32_t)st_i * (uint32_t)stage_bytes;
+            const uint32_t sb = sa + p.a_stage_bytes;
+            if (p.a_mn_major) {
+              for (int q = 0; q < p.a_boxes; ++q)
+                tma_load_3d(sa + q * p.a_box_bytes, &p.mapA, m0 + q * a_atom, k0, p.a_batched ? b : 0, fb);
+            } else {
+              tma_load_3d(sa, &p.mapA, k0, m0, p.a_batched ? b : 0, fb);
+            }
+            if (p.b_resident) {
+            } else if (p.b_mn_major) {
+              for (int f = 0; f < fpack; ++f)       // a frame past the batch is out of bounds for TMA: zero fill
+                for (int q = 0; q < p.b_boxes; ++q)
+                  tma_load_3d(sb + (f * p.b_boxes + q) * p.b_box_bytes, &p.mapB, n0 + q * b_atom, k0, p.b_batched ? b + f : 0, fb);
+            } else {
+              tma_load_3d(sb, &p.mapB, k0, n0, p.b_batched ? b : 0, fb);
+            }
           }
-          if (p.b_resident) {
-          } else if (p.b_mn_major) {
-            for (int f = 0; f < fpack; ++f)       // a frame past the batch is out of bounds for TMA: zero fill
-              for (int j = 0; j < p.b_boxes; ++j)
-                tma_load_3d(sb + (f * p.b_boxes + j) * p.b_box_bytes, &p.mapB, n0 + j * b_atom, k0, p.b_batched ? b + f : 0, fb);
-          } else {
-            tma_load_3d(sb, &p.mapB, k0, n0, p.b_batched ? b : 0, fb);
-          }
+          if (++st_i == p.stages) { st_i = 0; st_ph ^= 1; }
+          k0 += p.BK;
+          if (k0 >= p.K) { k0 = 0; ++b; }                     // next frame of the group (weight gradients)
         }
       }
     }
@@ -346,38 +359,57 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
       const uint32_t b_sbo = 8u * (uint32_t)p.b_sw;
       const uint32_t b_kstep = p.b_mn_major ? 16u * (uint32_t)p.b_sw : 32u;
       const int ksteps = p.BK / 16;
-      int it = 0, ti = 0;
+      // descriptors: everything but the 14-bit start-address field is constant, and the field is linear in the byte
+      // address (>> 4; shared memory is < 256 KB so it never carries out), so a stage / k-step is one 64-bit add
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t adesc0 = make_smem_desc(smem_base, a_lbo, a_sbo, p.a_sw);
+      const uint64_t bdesc0 = make_smem_desc(p.b_resident ? smem_u32(bres) : smem_base + (uint32_t)p.a_stage_bytes, b_lbo, b_sbo, p.b_sw);
+      const uint64_t stage_step = (uint64_t)((uint32_t)stage_bytes >> 4);
+      const uint64_t a_kadd = (uint64_t)(a_kstep >> 4), b_kadd = (uint64_t)(b_kstep >> 4);
+      const uint64_t bres_step = (uint64_t)((uint32_t)p.b_stage_bytes >> 4);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+      const bool one_group = (num_tiles == tiles_per_batch);
+      int st_i = 0; uint32_t st_ph = 0;
+      int ti = 0;
       bool ok = true;
       if (p.b_resident) ok = mbar_wait(smem_u32(bres_bar), 0, p.err_flag);
       for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x, ++ti) {
         const int acc = acc_bufs == 2 ? (ti & 1) : 0;
         const uint32_t acc_ph = acc_bufs == 2 ? ((ti >> 1) & 1) : (ti & 1);
-        ok = mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_ph ^ 1, p.err_flag);   // epilogue drained this accumulator
+        ok = mbar_wait(tempty0 + 8u * acc, acc_ph ^ 1, p.err_flag);   // epilogue drained this accumulator
         if (!ok) break;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * acc_stride;
-        const int grp = t / tiles_per_batch;
-        const int nblk = (t % tiles_per_batch) % n_blocks;
+        int grp = 0, r = t;
+        if (!one_group) { grp = t / tiles_per_batch; r = t - grp * tiles_per_batch; }
+        int nblk = 0;
+        if (n_blocks > 1) nblk = r - (r / n_blocks) * n_blocks;
         const int nfr = kbf > 0 ? min(kbf, p.batch - grp * kbf) : 1;
-        for (int kb = 0; kb < nfr * num_k; ++kb, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          ok = mbar_wait(smem_u32(&full_bar[s]), ph, p.err_flag);
+        const int total = nfr * num_k;
+        int kb_in = 0;                                        // k-block inside the current frame (resident-B slot)
+        const uint64_t bres_tile = bdesc0 + (uint64_t)(nblk * num_k) * bres_step;
+        for (int kb = 0; kb < total; ++kb) {
+          ok = mbar_wait(full0 + 8u * st_i, st_ph, p.err_flag);
           if (!ok) break;
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = p.b_resident ? smem_u32(bres + (size_t)(nblk * num_k + kb) * p.b_stage_bytes) : sa + p.a_stage_bytes;
-          if (p.debug_mode & 4) { mbar_arrive(smem_u32(&empty_bar[s])); continue; }   // bring-up: no MMAs, software release
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, p.a_sw);
-            const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, p.b_sw);
-            umma_bf16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          if (p.debug_mode & 4) {                             // bring-up: no MMAs, software release
+            mbar_arrive(empty0 + 8u * st_i);
+          } else {
+            uint64_t ad = adesc0 + (uint64_t)st_i * stage_step;
+            uint64_t bd = p.b_resident ? bres_tile + (uint64_t)kb_in * bres_step : bdesc0 + (uint64_t)st_i * stage_step;
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16(tmem_d, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              ad += a_kadd; bd += b_kadd;
+            }
+            umma_commit(empty0 + 8u * st_i);   // frees the smem stage once these MMAs have read it
           }
-          umma_commit(smem_u32(&empty_bar[s]));   // frees the smem stage once these MMAs have read it
+          if (++st_i == p.stages) { st_i = 0; st_ph ^= 1; }
+          if (++kb_in == num_k) kb_in = 0;
         }
         if (ok) {
-          if (p.debug_mode & 4) mbar_arrive(smem_u32(&tmem_full_bar[acc]));
-          else umma_commit(smem_u32(&tmem_full_bar[acc]));   // accumulator complete
+          if (p.debug_mode & 4) mbar_arrive(tfull0 + 8u * acc);
+          else umma_commit(tfull0 + 8u * acc);   // accumulator complete
         }
       }
     }
@@ -391,8 +423,12 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
     int ti = 0;
     bool ok = true;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-      const int b0 = kbf > 0 ? (t / tiles_per_batch) : (t / tiles_per_batch) * fpack, r = t % tiles_per_batch;
-      const int m0 = (r / n_blocks) * BM, n0 = (r % n_blocks) * p.BN;
+      int grp = 0, r = t;
+      if (num_tiles != tiles_per_batch) { grp = t / tiles_per_batch; r = t - grp * tiles_per_batch; }
+      int mi = r, ni = 0;
+      if (n_blocks > 1) { mi = r / n_blocks; ni = r - mi * n_blocks; }
+      const int b0 = kbf > 0 ? grp : grp * fpack;
+      const int m0 = mi * BM, n0 = ni * p.BN;
       const int acc = acc_bufs == 2 ? (ti & 1) : 0;
       const uint32_t acc_ph = acc_bufs == 2 ? ((ti >> 1) & 1) : (ti & 1);
       if (ok) ok = mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_ph, p.err_flag);
