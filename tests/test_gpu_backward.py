@@ -166,7 +166,10 @@ def test_saved_activation_backward_equals_recompute(dtype):
     p2 = {k: (rm0[k].clone() if k in rm0 else v) for k, v in p.items()}
     out, smap, _ = adapter_forward_raw(cfg, p2, x, other, training=True, keep=keep)
     assert len(keep) == 1
-    assert rel_l2(out.float().cpu(), out_ref.float().cpu()) < 1e-6 and rel_l2(smap.float().cpu(), smap_ref.float().cpu()) < 1e-6
+    # same kernels, same math; only the order of the fp32 atomics (per-frame column sums) differs from run to run, and in
+    # bf16 a reordered sum can flip a rounding downstream
+    ftol = 1e-5 if dtype == torch.float32 else 5e-3
+    assert rel_l2(out.float().cpu(), out_ref.float().cpu()) < ftol and rel_l2(smap.float().cpu(), smap_ref.float().cpu()) < ftol
     dx, do, gr = adapter_backward_raw(cfg, p2, x, other, d_out, d_smap, None, training=True, saved=keep[0])
     torch.cuda.synchronize()
     # the two paths run the same kernels; fp32 atomics reorder sums, and in bf16 a reordered sum can flip a rounding
