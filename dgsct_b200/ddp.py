@@ -108,3 +108,90 @@ class GradBucketer:
 
     def total_bytes(self) -> int:
         return sum(b.flat.numel() * 4 for b in self.buckets)
+
+
+class AdapterDDP:
+    """Data-parallel wrapper for the trainable adapter modules of a model (what the reference's
+    single-GPU ``main()`` lacks, main_trans.py:178-302).  The frozen backbones need nothing; every listed module gets
+
+    * its parameters (and buffers) broadcast from rank 0 at construction, so replicas start identical;
+    * its gradients wired into the flat buckets of a :class:`GradBucketer` (registration = reverse forward order, the
+      order in which backward finishes);
+    * hooks that launch a bucket's all-reduce as soon as the backward of its last module has been enqueued:
+      engine adapters (``fused_grad_accumulation``: the kernels add into ``param.grad`` and autograd never sees the
+      gradient) use a module backward hook, ordinary modules use per-parameter post-accumulate hooks.
+
+    Usage::
+
+        ddp = AdapterDDP([m for m in model.modules() if isinstance(m, dgsct_b200.VisualAdapter)])
+        for batch in loader:
+            ddp.zero_grad(); loss = step(batch); loss.backward(); ddp.finish(); optimizer.step()
+
+    ``with ddp.no_sync():`` runs a micro-batch of gradient accumulation (``--accum_itr``, main_trans.py:135-136) without
+    collectives; gradients keep adding up in the buckets."""
+
+    def __init__(self, modules: Sequence[torch.nn.Module], bucket_bytes: int = 32 << 20, group=None, fused: bool = True,
+                 broadcast: bool = True):
+        self.modules = list(modules)
+        self.group = group
+        order = list(reversed(self.modules))
+        if broadcast and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            with torch.no_grad():
+                for m in self.modules:
+                    for t in list(m.parameters()) + list(m.buffers()):
+                        dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        groups = [[p for p in m.parameters() if p.requires_grad] for m in order]
+        self.bucketer = GradBucketer(groups, bucket_bytes=bucket_bytes, group=group)
+        self._sync = True
+        self._npar = [len(g) for g in groups]
+        self._pending = list(self._npar)
+        self._handles = []
+        for j, (m, g) in enumerate(zip(order, groups)):
+            engine = fused and hasattr(m, "_packed_weights")          # dgsct_b200.VisualAdapter
+            if engine:
+                m.fused_grad_accumulation = True
+                self._handles.append(m.register_full_backward_hook(self._module_hook(j)))
+            else:
+                for p in g:
+                    self._handles.append(p.register_post_accumulate_grad_hook(self._param_hook(j)))
+
+    def _module_hook(self, j):
+        def hook(module, grad_input, grad_output):
+            if self._sync:
+                self.bucketer.group_done(j)
+        return hook
+
+    def _param_hook(self, j):
+        def hook(param):
+            if not self._sync:
+                return
+            self._pending[j] -= 1
+            if self._pending[j] == 0:
+                self.bucketer.group_done(j)
+        return hook
+
+    def zero_grad(self) -> None:
+        self.bucketer.zero_grad()
+        self._pending = list(self._npar)
+
+    def no_sync(self):
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self._sync = self._sync, False
+            try:
+                yield
+            finally:
+                self._sync = prev
+        return ctx()
+
+    def finish(self) -> None:
+        """Wait for the outstanding all-reduces; ``param.grad`` then holds the mean over ranks."""
+        self.bucketer.finish()
+        self._pending = list(self._npar)
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []

@@ -71,3 +71,95 @@ def test_bucketed_allreduce_world2():
         assert p.exitcode == 0
     assert all(r[2] for r in res), res
     assert res[0][3] >= 2 and res[0][4] == (35 + 5 + 12000 + 11) * 4
+
+
+def _worker_ddp(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from dgsct_b200.ddp import AdapterDDP
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(10 + rank)                            # DIFFERENT initial replicas: construction must broadcast rank 0's
+    mods = [torch.nn.Linear(6, 6), torch.nn.Linear(6, 6), torch.nn.Linear(6, 3)]
+    mods[1].bias.requires_grad_(False)
+    ddp = AdapterDDP(mods, bucket_bytes=64)
+    w0 = [p.detach().clone() for m in mods for p in m.parameters()]
+    gathered = [torch.zeros_like(w0[0]) for _ in range(world)]
+    dist.all_gather(gathered, w0[0])
+    same_init = all(torch.equal(gathered[0], g) for g in gathered)
+
+    def loss_on(seed):
+        torch.manual_seed(seed)
+        x = torch.randn(4, 6)
+        h = x
+        for m in mods:
+            h = torch.tanh(m(h))
+        return (h ** 2).sum()
+
+    # one synchronised step
+    ddp.zero_grad()
+    loss_on(100 + rank).backward()
+    ddp.finish()
+    got = [p.grad.clone() for m in mods for p in m.parameters() if p.requires_grad]
+    # reference: plain autograd per rank, averaged with explicit all-reduces
+    ref_mods = [torch.nn.Linear(6, 6), torch.nn.Linear(6, 6), torch.nn.Linear(6, 3)]
+    for a, b in zip(ref_mods, mods):
+        a.load_state_dict(b.state_dict())
+    ref_mods[1].bias.requires_grad_(False)
+    torch.manual_seed(100 + rank)
+    h = torch.randn(4, 6)
+    for m in ref_mods:
+        h = torch.tanh(m(h))
+    (h ** 2).sum().backward()
+    ok = same_init
+    k = 0
+    for m in ref_mods:
+        for p in m.parameters():
+            if p.requires_grad:
+                g = p.grad.clone()
+                dist.all_reduce(g)
+                ok = ok and torch.allclose(got[k], g / world, atol=1e-6)
+                k += 1
+    # gradient accumulation: first micro-batch without collectives, second with
+    ddp.zero_grad()
+    with ddp.no_sync():
+        loss_on(200 + rank).backward()
+    loss_on(300 + rank).backward()
+    ddp.finish()
+    acc = [p.grad.clone() for m in mods for p in m.parameters() if p.requires_grad]
+    for m in ref_mods:
+        m.zero_grad()
+    for seed in (200 + rank, 300 + rank):
+        torch.manual_seed(seed)
+        h = torch.randn(4, 6)
+        for m in ref_mods:
+            h = torch.tanh(m(h))
+        (h ** 2).sum().backward()
+    k = 0
+    for m in ref_mods:
+        for p in m.parameters():
+            if p.requires_grad:
+                g = p.grad.clone()
+                dist.all_reduce(g)
+                ok = ok and torch.allclose(acc[k], g / world, atol=1e-6)
+                k += 1
+    q.put((rank, bool(ok), len(ddp.bucketer.buckets)))
+    dist.destroy_process_group()
+
+
+def test_adapter_ddp_hooks_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_ddp, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    assert res[0][2] >= 2
