@@ -47,6 +47,8 @@ struct Params {
   int rows_per_frame;           // > 0: A is (batch*rows_per_frame, K) contiguous and B is shared, so the frames are flattened
                                 // into one M extent (no per-frame tile padding); the epilogue recovers (b, m) per row
   int* err_flag;                // device int set to non-zero when a bounded wait expires
+  int early_release;            // experiment (DGSCT_EARLY_RELEASE=1, off by default, not yet measured on hardware): epilogue
+                                // warps release the accumulator as soon as their last block of the tile is in registers
   int debug_mode;               // bring-up only: 1 = epilogue skips the TMEM loads, 2 = skips loads and functor
 };
 
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         if (row_ok) m -= bq * p.rows_per_frame;
       }
       const uint32_t lane_base = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(lane_grp * 32) << 16);
+      bool released = false;
       if ((p.debug_mode & 3) < 2 && !(whole_row && half == 1)) {
         epi.begin(bq, m, row_ok);
         const int c_begin = whole_row ? 0 : half * 32, c_step = whole_row ? 32 : 64;
@@ -451,6 +454,14 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           if ((p.debug_mode & 3) == 0) {
             if (two) tmem_ld32(lane_base + (uint32_t)c, v0, v1);
             else tmem_ld16(lane_base + (uint32_t)c, v0);
+            if (p.early_release && c + c_step >= BNI) {
+              // this warp's last block of the tile is in registers: hand the accumulator back to the MMA issuer before
+              // the functor runs (bias / activation / reductions / stores then overlap the next tile's MMAs)
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+              released = true;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v0[j] = (float)(c + j); v1[j] = (float)(c + 16 + j); }
@@ -472,9 +483,11 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         }
         epi.end(bq, m, row_ok);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
     }
   }
   tc_fence_before();

@@ -203,6 +203,7 @@ int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B, int M,
   p.tmem_cols = cols;
   p.err_flag = tc_err_flag_device_ptr();
   p.debug_mode = 0;
+  p.early_release = getenv("DGSCT_EARLY_RELEASE") ? 1 : 0;
   int rc;
   if (A.mn_major) rc = encode(&p.mapA, A, batch, a_atom, p.BK, p.a_sw);
   else rc = encode(&p.mapA, A, batch, p.BK, BM, p.a_sw);
