@@ -181,7 +181,8 @@ static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const t
   EpiOut se2 = se;
   // skinny per-frame-vector products (M = BT rows): split the contraction over CTAs and add atomically.  The output is
   // fp32 and either accumulating (OUT_ADD) or zero-initialised by the caller (OUT_STORE targets live in the zero region).
-  if (split_k_ok && M <= 128 && K >= 256 && batch == 1 && !se.out_bf16 && !se.resid && se.mode != OUT_ATOMIC) {
+  // (additive epilogue terms -- residual, broadcast row -- would be applied once per split: such products never split)
+  if (split_k_ok && M <= 128 && K >= 256 && batch == 1 && !se.out_bf16 && !se.resid && !se.bcast && se.mode != OUT_ATOMIC) {
     const int ctas = ceil_div(N, SG_BN) * ceil_div(M, SG_BM);
     int ks = (2 * 148 + ctas - 1) / ctas;
     if (ks > K / 64) ks = K / 64;
