@@ -122,6 +122,59 @@ struct EpiOut {
     warp_store_block32<OUT_BF16>(out, off, n0, v0, v1, nv0 + nv1, row_ok, stage);
   }
 };
+// ---- fused backward epilogues (DGSCT_FUSE_BWD=1; compiled, NOT yet validated on hardware -> off by default) ------------
+// dXc = dz2 . Wv2 consumed in the epilogue instead of a store + bwd_xc_kernel's pass:
+//   gX1[b,m,n] += acc * (1 + mgate[b,n]) ;  dm[b,n] += sum_m acc * X1[b,m,n]
+struct EpiXcFused {
+  static constexpr bool kRowIndependent = true;
+  bf16* gx1; const bf16* x1; long long ld, sb; const float* mgate; float* dm; int C;
+  __device__ __forceinline__ void begin(int, int, bool) {}
+  __device__ __forceinline__ void end(int, int, bool) {}
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = 0.f;
+    if (row_ok && nvalid > 0) {
+      const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
+      float mg[16];
+      load16_guard(mgate + (long long)b * C + n0, mg, nvalid);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) {
+          const float xv = __bfloat162float(x1[idx + j]), gv = __bfloat162float(gx1[idx + j]);
+          w[j] = v[j] * xv;
+          v[j] = fmaf(v[j], 1.f + mg[j], gv);
+        }
+      store_row16<true>(gx1, idx, v, nvalid);
+    }
+    float* dmp = dm; const int Cc = C;
+    segmented_colsum16(w, b, row_ok, n0, N, [dmp, Cc](int bb, int col, float s_, bool owner) {
+      if (owner) atomicAdd(&dmp[(long long)bb * Cc + col], s_);
+    });
+  }
+};
+// z1 = X1 . Wv1^T consumed in the epilogue instead of a store + bwd_channel_mask_kernel's in-place pass:
+//   dz1[b,m,n] = dr1[b,n] * 1[acc + bias[n] > 0]  (bf16) ;  d_b1[n] += sum_{b,m} dz1
+struct EpiChannelMask {
+  static constexpr bool kRowIndependent = true;
+  bf16* out; long long ld, sb; const float* bias; const float* dr1; int dr_ld; float* d_b1;
+  __device__ __forceinline__ void begin(int, int, bool) {}
+  __device__ __forceinline__ void end(int, int, bool) {}
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    float bn[16], dr[16];
+    load16_guard(bias + n0, bn, nvalid);
+    load16_guard(dr1 + (long long)b * dr_ld + n0, dr, nvalid);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (row_ok && j < nvalid && v[j] + bn[j] > 0.f) ? dr[j] : 0.f;
+    if (row_ok && nvalid > 0) store_row16<true>(out, (size_t)((long long)b * sb + (long long)m * ld + n0), v, nvalid);
+    const float s_ = warp_colsum16(v);                      // one global column sum: frames need no separation
+    const int lane = threadIdx.x & 31;
+    const int col = n0 + colsum16_owner_col(lane);
+    if (((lane & 1) == 0) && col < N) atomicAdd(&d_b1[col], s_);
+  }
+};
 struct EpiNone {   // placeholder for products that never take the tensor-core kernel
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
@@ -189,6 +242,20 @@ static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const t
     if (ks > 1) { sh.ksplit = ks; se2.mode = OUT_ATOMIC; }
   }
   cudaError_t e = launch_gemm_simt(sh, simt_operand(A, a_bf16), simt_operand(B, b_bf16), ax, se2, g.st);
+  if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
+  return DGSCT_OK;
+}
+
+// tensor-core kernel or nothing: DGSCT_ERR_UNSUPPORTED tells the caller to take its unfused path
+template <typename TE>
+static int run_tc_only(const Gemm& g, const tc::OperandDesc& A, const tc::OperandDesc& B, int M, int N, int K, int batch, TE te) {
+  tc::Params p;
+  const int rc = tc::make_params(p, A, B, M, N, K, batch, 0, 0, false, tc::epi_row_independent<TE>::value,
+                                 tc::epi_stage_bytes<TE>::value);
+  if (rc != DGSCT_OK) return rc;
+  StageScope _sc(g.stage, g.st);
+  count_launch();
+  cudaError_t e = tc::launch(p, te, g.st);
   if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
   return DGSCT_OK;
 }
@@ -368,6 +435,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     ld_up = ldz; ld_dn = C; ld_v = C; ld_fc = Co; ld_res = No; ld_tok = C;
   }
   const int wbf = tcp ? 1 : 0;
+  const bool fuse_bwd = tcp && getenv("DGSCT_FUSE_BWD") != nullptr;   // experimental fused epilogues (see tc::EpiXcFused)
   const Gemm GB{ST_MISC, "bwd_gemm", st, tcp};
   const Gemm G_UD{ST_BWD_UPDOWN, "bwd_updown", st, tcp}, G_SP{ST_BWD_SPATIAL, "bwd_spatial", st, tcp}, G_CH{ST_BWD_CHANNEL, "bwd_channel", st, tcp},
       G_TK{ST_BWD_TOKEN, "bwd_token", st, tcp}, G_FC{ST_BWD_FC, "bwd_fc", st, tcp}, G_DW{ST_BWD_DWRES, "bwd_dwres", st, tcp},
@@ -516,13 +584,22 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       bwd_spatial_mask_kernel<<<dim3(ceil_div(H, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S2, bf, H, N, P.v2_b, ds, P.s_w, aq2, aq2_ld,
                                                                                         G.s_w, daq2, daq_ld, G.v2_b);
       KCHECK("bwd_spatial_mask"); }
-    // dXc = dz2 . Wv2 -> S1 ; dX1 += dXc (1+m) ; dm += sum_n dXc X1
-    EpiOut e2 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
-    RC(run_gemm(G_SP, K_(S2, N, H, H, (long long)N * H), bf, MN_(Wv2_op, H, C, ld_v, 0), wbf, N, C, H, BT,
-                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e2), e2, AxIdentity{}, true));
-    { StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
+    // dXc = dz2 . Wv2 ; dX1 += dXc (1+m) ; dm += sum_n dXc X1      (fused: in the product's epilogue; else via S1)
+    bool xc_fused = false;
+    if (fuse_bwd) {
+      tc::EpiXcFused te{(bf16*)gX1, (const bf16*)X1, C, (long long)N * C, mvec, dm, C};
+      const int rc = run_tc_only(G_SP, K_(S2, N, H, H, (long long)N * H), MN_(Wv2_op, H, C, ld_v, 0), N, C, H, BT, te);
+      if (rc == DGSCT_OK) xc_fused = true;
+      else if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
+    }
+    if (!xc_fused) {
+      EpiOut e2 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
+      RC(run_gemm(G_SP, K_(S2, N, H, H, (long long)N * H), bf, MN_(Wv2_op, H, C, ld_v, 0), wbf, N, C, H, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e2), e2, AxIdentity{}, true));
+      StageScope _sc(ST_SPATIAL_QUERY, st); count_launch();
       bwd_xc_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, gX1, X1, bf, C, N, mvec, dm);
-      KCHECK("bwd_xc"); }
+      KCHECK("bwd_xc");
+    }
     // opm = 1 + m
     { StageScope _sc(ST_MISC, st); count_launch();
       one_plus_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(mvec, opm, BT * C);
@@ -569,12 +646,21 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   }
   {
     // z1 = X1 . Wv1^T (pre-bias) -> S1 ; dz1 = dr1 * 1[z1+b>0] ; dX1 += dz1 . Wv1 ; dWv1 += dz1^T X1
-    EpiOut e1 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
-    RC(run_gemm(G_CH, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
-                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
-    { StageScope _sc(ST_CHANNEL_QUERY, st); count_launch();
+    bool mask_fused = false;
+    if (fuse_bwd) {
+      tc::EpiChannelMask te{(bf16*)S1, C, (long long)N * C, P.v1_b, dr1, C, G.v1_b};
+      const int rc = run_tc_only(G_CH, K_(X1, N, C, C, (long long)N * C), K_(Wv1_op, C, C, ld_v, 0), N, C, C, BT, te);
+      if (rc == DGSCT_OK) mask_fused = true;
+      else if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
+    }
+    if (!mask_fused) {
+      EpiOut e1 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
+      RC(run_gemm(G_CH, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+      StageScope _sc(ST_CHANNEL_QUERY, st); count_launch();
       bwd_channel_mask_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, bf, C, N, P.v1_b, dr1, G.v1_b);
-      KCHECK("bwd_channel_mask"); }
+      KCHECK("bwd_channel_mask");
+    }
     EpiOut e2 = eo(gX1, bf, C, (long long)N * C, OUT_ADD);
     RC(run_gemm(G_CH, K_(S1, N, C, C, (long long)N * C), bf, MN_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e2), e2, AxIdentity{}, true));

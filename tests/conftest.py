@@ -10,13 +10,19 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    config.addinivalue_line("markers", "gpu_experimental: default-off kernel experiments; run only when selected "
+                                       "explicitly with -m gpu_experimental on a B200")
 
 
 def pytest_collection_modifyitems(config, items):
     import torch
-    if torch.cuda.is_available():
-        return
-    skip = pytest.mark.skip(reason="no CUDA device")
+    have_cuda = torch.cuda.is_available()
+    want_experimental = "gpu_experimental" in (config.getoption("-m") or "")
+    skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    skip_exp = pytest.mark.skip(reason="experimental: select with -m gpu_experimental on a B200")
     for item in items:
-        if "gpu" in item.keywords:
-            item.add_marker(skip)
+        if "gpu_experimental" in item.keywords:
+            if not (have_cuda and want_experimental):
+                item.add_marker(skip_exp)
+        elif "gpu" in item.keywords and not have_cuda:
+            item.add_marker(skip_gpu)
