@@ -313,7 +313,7 @@ struct BwdPlan {
   size_t fwd;                        // keep-mode forward workspace
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
   size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, dWup_d, dWd_d, zero_end;
-  size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part;
+  size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
   size_t total;
 };
 
@@ -332,7 +332,9 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.S1 = take(BT * N * C * es);          // z1 -> dz1 ; later dXc
   p.S2 = take(BT * N * H * es);          // z2 -> dz2
   p.gV = take(BT * N * C * es);
-  p.gU = take(BT * N * Co * es);
+  { size_t gu = BT * N * Co;                           // dU (BT,N,Co), or dO' (BT,No,C) of the re-associated resampler
+    if (BT * (size_t)d.No * C > gu) gu = BT * (size_t)d.No * C;
+    p.gU = take(gu * es); }
   p.gQ = take(BT * N * K * es);          // dQraw -> dL2 ; later dL1
   p.gP = take(BT * N * K * 4);           // dP fp32
   p.dTp = take(BT * K * C * 4);
@@ -343,7 +345,9 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.colA = take(C * 4); p.colB = take(C * 4);
   p.dWup_d = take(C * ldz * 4); p.dWd_d = take(Cd * C * 4);
   p.vB = take(BT * C * 4); p.vC = take(BT * C * 4);     // split-K targets of the skinny products (added atomically)
+  p.fc_t = take(C * 4);                                 // sum_{b,n} dV b_res (re-associated resampler)
   p.zero_end = off;
+  p.fc_s = take(C * 4);
   p.vA = take(BT * C * 4); p.vD = take(BT * C * 4);
   p.coefA = take(C * 4); p.coefB = take(C * 4); p.coefC = take(C * 4);
   p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
@@ -745,7 +749,51 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
                 to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true, 0, true));
   }
   // ---- 8. token resampler ---------------------------------------------------------------------------------------------
-  {
+  const bool fc_first = tcp && use_fc_first(d);
+  if (fc_first) {
+    // forward was V = Wres . O' + b_res (x) s + b_fc with O' = other . Wfc^T kept in the U buffer, s = rowsum(Wfc)
+    const void* Op = U;
+    float* fcs = (float*)(ws + bp.fc_s); float* fct = (float*)(ws + bp.fc_t);
+    const bool has_bias = !(d.flags & DGSCT_F_NO_CONV_BIAS) && P.resample_b;
+    if (has_bias) {
+      StageScope _sc(ST_MISC, st); count_launch();
+      fc_rowsum_kernel<<<ceil_div(C, 8), 256, 0, st>>>((const bf16*)Wfc_op, C, Co, ld_fc, fcs);
+      KCHECK("fc_rowsum");
+    }
+    RC(fork_side());                                                  // gV is final
+    { StageScope _sc(ST_MISC, sst); count_launch();
+      col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
+      KCHECK("dfc_b"); }
+    // dO'[b] (No,C) = Wres^T . dV[b]  -> gU
+    EpiOut e1 = eo(gU, bf, C, (long long)No * C, OUT_STORE);
+    RC(run_gemm(G_DO, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gV, N, C, C, (long long)N * C), bf, No, C, N, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    // side: dWres += sum_b dV_b . O'_b^T ; d_bres[n] += sum dV s ; t[c] = sum dV b_res
+    if (G.resample_w) {
+      EpiOut e3 = eo(G.resample_w, 0, No, 0, OUT_ATOMIC);
+      RC(run_gemm(S_DW, K_(gV, N, C, C, (long long)N * C), bf, K_(Op, No, C, C, (long long)No * C), bf, N, No, C, BT,
+                  to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
+    }
+    if (has_bias && G.resample_b) {
+      StageScope _sc(ST_MISC, sst); count_launch(2);
+      rowsum_frames_weighted_kernel<<<N, 256, 0, sst>>>(gV, bf, BT, N, C, fcs, G.resample_b);
+      col_reduce_rowweight_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, R, N, C, P.resample_b, fct);
+      KCHECK("dres_b_reassoc");
+    }
+    // dother[b] (No,Co) = dO'[b] . Wfc ; side: dWfc += sum_b dO'_b^T . other_b (+ t broadcast over co)
+    RC(fork_side());                                                  // gU = dO' is final
+    EpiOut e4 = eo(dother, bf, Co, (long long)No * Co, OUT_STORE);
+    RC(run_gemm(G_FC, K_(gU, No, C, C, (long long)No * C), bf, MN_(Wfc_op, C, Co, ld_fc, 0), wbf, No, Co, C, BT,
+                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e4), e4, AxIdentity{}, true));
+    EpiOut e2 = eo(G.fc_w, 0, Co, 0, OUT_ATOMIC);
+    RC(run_gemm(S_FC, MN_(gU, No, C, C, (long long)No * C), bf, MN_(other, No, Co, Co, (long long)No * Co), bf, C, Co, No, BT,
+                to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e2), e2, AxIdentity{}, true, 0, true));
+    if (has_bias) {
+      StageScope _sc(ST_MISC, sst); count_launch();
+      add_col_broadcast_kernel<<<ceil_div(C * Co, 256), 256, 0, sst>>>(G.fc_w, fct, C, Co);
+      KCHECK("dfc_w_rank1");
+    }
+  } else {
     RC(fork_side());                                                  // gV is final
     { StageScope _sc(ST_MISC, sst); count_launch();
       col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);

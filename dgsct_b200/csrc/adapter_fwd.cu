@@ -3,6 +3,8 @@
 // substituted for the large products when io_dtype is bf16.
 #include "adapter_fwd.h"
 
+#include <stdlib.h>
+
 #include "epilogues.cuh"
 #include "pack.cuh"
 #include "profile.h"
@@ -21,13 +23,21 @@ int validate_desc(const dgsct_desc* d) {
   return DGSCT_OK;
 }
 
+bool use_fc_first(const dgsct_desc& d) {
+  return getenv("DGSCT_FC_FIRST") != nullptr && d.io_dtype == DGSCT_BF16 && !(d.flags & DGSCT_F_FORCE_SIMT) && d.C < d.Co &&
+         d.C % 8 == 0 && d.Co % 8 == 0;
+}
+
 FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
   FwdPlan p{};
   const size_t BT = d.BT, N = d.N, C = d.C, Co = d.Co, K = d.K, Cd = d.C / d.r, H = d.C / 2;
   const size_t es = d.io_dtype == DGSCT_BF16 ? 2 : 4;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  p.bufA = take(BT * N * (Co > C ? Co : C) * es);   // U (BT,N,Co) then up-sampler output (BT,N,C)
+  const size_t No = d.No;
+  size_t bufA_elems = BT * N * (Co > C ? Co : C);   // U (BT,N,Co) then up-sampler output (BT,N,C)
+  if (BT * No * C > bufA_elems) bufA_elems = BT * No * C;   // or O W_fc^T (BT,No,C) of the re-associated resampler
+  p.bufA = take(bufA_elems * es);
   p.bufV = take(BT * N * C * es);                   // V then Y
   p.bufX1 = take(BT * N * C * es);
   p.bufL = take(BT * N * K * 4);                    // token logits -> probabilities (P then Q), fp32
@@ -56,6 +66,7 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
   if (d.io_dtype == DGSCT_BF16) {
     p.Pb = take(BT * N * K * 2);
     p.csm_part = take(BT * (size_t)CSM_MAX_CHUNKS * 2 * K * 4);
+    p.fc_s = take(C * 4);
     p.TpB = take(BT * K * C * 2);
     p.Zr = take(BT * N * (size_t)pad8((int)Cd) * 2);
     p.Uo32 = take(BT * N * C * 4);                    // up-sampler output stays fp32 until ln_post
@@ -336,6 +347,21 @@ static int gemm_auto(int stage, const char* name, bool allow_tc, const tc::Opera
   return DGSCT_OK;
 }
 
+// tensor-core kernel or an error (no SIMT twin): for paths whose epilogue has no scalar counterpart
+template <typename TE>
+static int gemm_tc_only(int stage, const char* name, const tc::OperandDesc& A, const tc::OperandDesc& B, int M, int N, int K,
+                        int batch, TE te, cudaStream_t st) {
+  StageScope _sc(stage, st);
+  count_launch();
+  tc::Params p;
+  const int rc = tc::make_params(p, A, B, M, N, K, batch, 0, 0, false, tc::epi_row_independent<TE>::value,
+                                 tc::epi_stage_bytes<TE>::value);
+  if (rc != DGSCT_OK) return rc;
+  cudaError_t e = tc::launch(p, te, st);
+  if (e != cudaSuccess) { set_cuda_error(e, name); return DGSCT_ERR_CUDA; }
+  return DGSCT_OK;
+}
+
 static tc::OperandDesc kmaj(const void* p, int rows, int cols, long long ld, long long bs) {
   return tc::OperandDesc{p, 0, ld, bs, rows, cols};
 }
@@ -412,8 +438,31 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   { StageScope _sc(ST_MISC, st);
     DGSCT_CUDA_CHECK(cudaMemsetAsync(ws + pl.acc_begin, 0, pl.acc_end - pl.acc_begin, st)); }
 
+  const bool fc_first = use_fc_first(d);
+  if (fc_first) {
+    // (R1') O'[b] (No,C) = other[b] (No,Co) . Wfc^T          (frames flattened, Wfc resident)
+    // (R2') V[b] (N,C)  = Wres (N,No) . O'[b] + b_res[n] * s[c] + b_fc[c],  s = rowsum(Wfc) ; osum[b,c] = sum_n V
+    bf16* Op = U;
+    float* fcs = (float*)(ws + pl.fc_s);
+    { StageScope _sc(ST_RESAMPLE_FC, st); count_launch();
+      fc_rowsum_kernel<<<ceil_div(C, 8), 256, 0, st>>>(Wfc, C, Co, pp.ld_fc, fcs);
+      DGSCT_LAUNCH_CHECK("fc_rowsum"); }
+    {
+      auto te = tc_store<true>(Op, C, (long long)No * C);
+      DGSCT_RC(gemm_tc_only(ST_RESAMPLE_FC, "resample_fc_first", kmaj(other, No, Co, Co, (long long)No * Co),
+                            kmaj(Wfc, C, Co, pp.ld_fc, 0), No, C, Co, BT, te, st));
+    }
+    {
+      auto te = tc_store<true, true>(V, C, (long long)N * C);
+      te.bias_m = (d.flags & DGSCT_F_NO_CONV_BIAS) ? nullptr : P.resample_b;
+      te.bias_m_coln = te.bias_m ? fcs : nullptr;
+      te.bias_n = P.fc_b; te.colsum = osum; te.ncols_total = C;
+      DGSCT_RC(gemm_tc_only(ST_RESAMPLE_CONV, "resample_conv_reassoc", kmaj(Wres, N, No, pp.ld_res, 0),
+                            mnmaj(Op, No, C, C, (long long)No * C), N, C, No, BT, te, st));
+    }
+  }
   // (R1) U[b] (N,Co) = Wres (N,No) . other[b] (No,Co) + b_res[n]
-  {
+  if (!fc_first) {
     auto te = tc_store<true>(U, Co, (long long)N * Co);
     EpiBiasStore se = epi_store(U, 1, Co, (long long)N * Co);
     te.bias_m = se.bias_m = (d.flags & DGSCT_F_NO_CONV_BIAS) ? nullptr : P.resample_b;
@@ -421,7 +470,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
                        mnmaj(other, No, Co, Co, (long long)No * Co), N, Co, No, BT, te, se, st));
   }
   // (R2) V = U . Wfc^T + b_fc ; osum[b,c] = sum_n V
-  {
+  if (!fc_first) {
     auto te = tc_store<true, true>(V, C, (long long)N * C);
     EpiBiasStore se = epi_store(V, 1, C, (long long)N * C);
     te.bias_n = se.bias_n = P.fc_b; te.colsum = se.colsum = osum; te.ncols_total = se.ncols_total = C;

@@ -10,6 +10,7 @@ struct FwdPlan {
   size_t acc_begin, osum, qsum, ssum, bn1_sum, bn1_sq, bn2_sum, bn2_sq, acc_end;
   size_t aq1, aq2, h, m, tau, sig, bn1_scale, bn1_shift, bn2_scale, bn2_shift;
   size_t csm_part;                                // column-softmax partials (BT, chunks, 2, K) fp32
+  size_t fc_s;                                    // row sums of fc.weight (C) fp32 (re-associated resampler, DGSCT_FC_FIRST)
   size_t Pb, TpB, Zr, Uo32, packed, aq, vec_bf;   // tensor-core path: bf16 P, bf16 latent tokens, bf16 relu(bn1(Z)), fp32 up-sampler
                                                   // output, packed weights, [aq1 | aq2] fp32 (BT, C+H), bf16 per-frame vectors
   // Regions that alias others unless the plan is built with keep = true (training forward: everything the
@@ -21,6 +22,10 @@ struct FwdPlan {
 };
 
 int validate_desc(const dgsct_desc* d);
+// Re-associated token resampler V = W_res (O W_fc^T) + b_res (x) rowsum(W_fc) + b_fc instead of (W_res O + b_res) W_fc^T + b_fc:
+// when C < C' the N x N' contraction runs over C instead of C' columns (half the FLOPs of the forward product and of the
+// dother / dW_res products for the audio direction).  EXPERIMENT: DGSCT_FC_FIRST=1, tensor-core path only, default off.
+bool use_fc_first(const dgsct_desc& d);
 FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep = false);
 
 // bf16 tensor-core pipeline (tcgen05 GEMMs); `packed` = pre-packed bf16 weights or NULL (packed per call)

@@ -465,6 +465,41 @@ __global__ void rowsum_frames_kernel(const void* __restrict__ du, int bf, int BT
   if (threadIdx.x == 0) atomicAdd(&out[n], s);
 }
 
+// ---- re-associated resampler (DGSCT_FC_FIRST): the rank-1 bias term b_res[n] * s[c] of V --------------------------------
+// d_bres[n] += sum_{b,c} dV[b,n,c] * s[c]
+__global__ void rowsum_frames_weighted_kernel(const void* __restrict__ dv, int bf, int BT, int N, int C, const float* __restrict__ s,
+                                              float* __restrict__ out) {
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int b = warp; b < BT; b += warps)
+    for (int c = lane; c < C; c += 32) acc += ld_act(dv, ((size_t)b * N + n) * C + c, bf) * s[c];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(&out[n], acc);
+}
+// t[c] += sum_{b,n} dV[b,n,c] * w[n]          (grid (ceil(C/32), row splits), block 256 = 32 columns x 8 row lanes)
+__global__ void col_reduce_rowweight_kernel(const void* __restrict__ a, int bf, long long rows, int N, int C,
+                                            const float* __restrict__ w, float* __restrict__ t) {
+  __shared__ float r1[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float p1 = 0.f;
+  if (c < C)
+    for (long long r = (long long)blockIdx.y * 8 + ry; r < rows; r += (long long)gridDim.y * 8)
+      p1 += ld_act(a, (size_t)(r * C + c), bf) * w[(int)(r % N)];
+  r1[ry][cx] = p1;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int j = 1; j < 8; ++j) p1 += r1[j][cx];
+    atomicAdd(&t[c], p1);
+  }
+}
+// g[c, co] += t[c] for every co      (d fc.weight through s = rowsum(W_fc))
+__global__ void add_col_broadcast_kernel(float* __restrict__ g, const float* __restrict__ t, int C, int Co) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * Co) g[i] += t[i / Co];
+}
+
 // zr (rows, ldz) fp32 = relu(z*scale+shift)
 __global__ void bn_relu_f32_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                                    float* __restrict__ zr, long long rows, int Cd, int ldz) {

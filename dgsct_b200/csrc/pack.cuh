@@ -73,6 +73,17 @@ __global__ void channel_q_kernel(const float* __restrict__ aq1, int aq_ld, const
   if (q16) q16[i] = __float2bfloat16_rn(v);
 }
 
+// s[c] = sum_co W[c, co] over the bf16 operand copy of fc.weight (C, ld): the column factor of the rank-1 bias term
+// b_res[n] * s[c] when the resampler is re-associated as W_res (O W_fc^T) (DGSCT_FC_FIRST); one warp per row
+__global__ void fc_rowsum_kernel(const bf16* __restrict__ W, int C, int Co, int ld, float* __restrict__ s) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int j = lane; j < Co; j += 32) acc += __bfloat162float(W[(size_t)c * ld + j]);
+  acc = warp_sum(acc);
+  if (lane == 0) s[c] = acc;
+}
+
 __global__ void concat2_f32_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < na) dst[i] = a[i];

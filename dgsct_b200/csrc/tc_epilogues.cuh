@@ -207,10 +207,24 @@ struct EpiStore {
   float alpha;
   float* colsum; int ncols_total;
   double* stat_sum; double* stat_sq;
+  const float* bias_m_coln;   // non-NULL: the row bias enters as the rank-1 term bias_m[m] * bias_m_coln[n] (DGSCT_FC_FIRST)
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
   __device__ __forceinline__ void transform(int m, int n0, float (&v)[16], bool row_ok, int nvalid) const {
-    const float bm = (bias_m && row_ok) ? bias_m[m] : 0.f;
+    float bm = (bias_m && row_ok) ? bias_m[m] : 0.f;
+    if (bias_m_coln) {
+      float sn[16];
+      load16_guard(bias_m_coln + n0, sn, nvalid);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(bm, sn[j], alpha * v[j]);
+      bm = 0.f;
+      if (bias_n) {
+        float bn[16];
+        load16_guard(bias_n + n0, bn, nvalid);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += bn[j];
+      }
+    } else
     if (bias_n) {
       float bn[16];
       load16_guard(bias_n + n0, bn, nvalid);

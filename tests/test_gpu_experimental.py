@@ -48,3 +48,29 @@ def test_flag_reproduces_default_path(flag, shape):
     for k, v in ref[4].items():
         if float(v.abs().max()) > 1e-6 and k not in ("ln_before.bias",):
             assert rel_l2(got[4][k], v) < 5e-2, (k, rel_l2(got[4][k], v))
+
+
+# ---- DGSCT_FC_FIRST changes the association of the resampler, so it is checked against the ORACLE (same bars as the
+# default path: tests/test_gpu_parity.py, tests/test_gpu_backward.py), on the audio-direction shapes where it engages.
+@pytest.mark.parametrize("shape", ["aud_s0", "aud_s1", "aud_s2", "aud_s3"])
+def test_fc_first_forward_parity_bf16(shape, monkeypatch):
+    from tests import test_gpu_parity as P
+    monkeypatch.setenv("DGSCT_FC_FIRST", "1")
+    P.test_real_shapes_bf16(shape)
+    if shape in ("aud_s1", "aud_s3"):
+        P.test_bf16_tensor_core_taps(shape)
+
+
+@pytest.mark.parametrize("shape", ["aud_s1", "aud_s3"])
+def test_fc_first_gradients_bf16(shape, monkeypatch):
+    from tests import test_gpu_backward as B
+    monkeypatch.setenv("DGSCT_FC_FIRST", "1")
+    B.test_gradients_at_real_shapes(shape, torch.bfloat16)
+
+
+def test_fc_first_train_mode_and_saved_activations(monkeypatch):
+    from tests import test_gpu_parity as P
+    from tests import test_gpu_backward as B
+    monkeypatch.setenv("DGSCT_FC_FIRST", "1")
+    P.test_train_mode_batch_stats("aud_s2", torch.bfloat16)
+    B.test_saved_activation_backward_equals_recompute(torch.bfloat16)     # C=384 < Co=768: engages
