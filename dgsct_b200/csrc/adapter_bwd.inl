@@ -314,6 +314,7 @@ struct BwdPlan {
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
   size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, dWup_d, dWd_d, zero_end;
   size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
+  size_t PQ, TT;                      // DGSCT_FUSE_BWD: [P | dL1] (BT,N,2K) bf16 and [dT' ; tokens] (BT,2K,C) bf16
   size_t total;
 };
 
@@ -353,6 +354,10 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
   p.opm = take(BT * C * 4);
   p.csm_part = take(BT * (size_t)CSM_MAX_CHUNKS * K * 4);
+  if (d.io_dtype == DGSCT_BF16 && getenv("DGSCT_FUSE_BWD")) {
+    p.PQ = take(BT * N * 2 * K * 2);
+    p.TT = take(BT * 2 * K * C * 2);
+  }
   p.out_fwd = take(BT * N * C * es); p.smap_fwd = take(BT * N * es); p.tmap_fwd = take(BT * 4);
   p.total = off;
   return p;
@@ -718,14 +723,21 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
     // d tokens += sum_b dTp[b]
+    // fused variant (DGSCT_FUSE_BWD, K = 32 tensor-core path): dV = [P | dL1] . [dT' ; T] is one product over 2K
+    const bool fuse_dv = fuse_bwd && K == 32 && C % 8 == 0 && bp.PQ != 0;
+    bf16* PQ = (bf16*)(ws + bp.PQ); bf16* TT = (bf16*)(ws + bp.TT);
     const void* dTpOp = dTp;
+    long long dTp_bs = (long long)K * C;
     { StageScope _sc(ST_MISC, st); count_launch(2);
       sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, st>>>(dTp, BT, (size_t)K * C, G.tokens);
-      if (tcp) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
+      if (fuse_dv) {
+        build_tt_kernel<<<ew_grid, 256, 0, st>>>(dTp, (const bf16*)Tok_op, ld_tok, TT, BT, K, C);
+        dTpOp = TT; dTp_bs = 2LL * K * C;                               // first K rows of every frame's [dT' ; T]
+      } else if (tcp) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
       KCHECK("dtok_sum"); }
     // dP = V . dTp^T (fp32) ; dL1 = P (dP - sum_n dP P) -> gQ
     EpiOut e5 = eo(gP, 0, K, (long long)N * K, OUT_STORE);
-    RC(run_gemm(G_TK, K_(V, N, C, C, (long long)N * C), bf, K_(dTpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
+    RC(run_gemm(G_TK, K_(V, N, C, C, (long long)N * C), bf, K_(dTpOp, K, C, C, dTp_bs), wbf, N, K, C, BT,
                 to_tc_full<tc::EpiOut<false, OUT_STORE, false, false, false>>(e5), e5, AxIdentity{}, true));
     { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
       if (K > 256) return DGSCT_ERR_UNSUPPORTED;
@@ -733,19 +745,27 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
         float* part = (float*)(ws + bp.csm_part);
         count_launch();
         col_softmax_bwd_partial_kernel<<<grid, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, part, N, K);
-        col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
+        if (fuse_dv) col_softmax_bwd_apply_cat_kernel<<<grid, 256, 0, st>>>(gP, (const bf16*)Pm, part, PQ, N, K);
+        else col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
       KCHECK("col_softmax_bwd"); }
     // dV = P . dTp + dL1 . T + dobar / N
     EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
-    RC(run_gemm(G_TK, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
-                to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
-    EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
-    RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
-                to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
+    const void* dL1 = gQ; long long dL1_ld = K, dL1_bs = (long long)N * K;
+    if (fuse_dv) {
+      RC(run_gemm(G_TK, K_(PQ, N, 2 * K, 2 * K, 2LL * N * K), 1, MN_(TT, 2 * K, C, C, 2LL * K * C), 1, N, C, 2 * K, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
+      dL1 = PQ + K; dL1_ld = 2 * K; dL1_bs = 2LL * N * K;              // the dL1 half of [P | dL1]
+    } else {
+      RC(run_gemm(G_TK, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
+      EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
+      RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
+    }
     // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
-    RC(fork_side());                                                  // gQ = dL1 is final; sum_frames already added its share
+    RC(fork_side());                                                  // dL1 is final; sum_frames already added its share
     EpiOut e8 = eo(G.tokens, 0, C, 0, OUT_ATOMIC); e8.transposed = 1;
-    RC(run_gemm(S_TK, MN_(V, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
+    RC(run_gemm(S_TK, MN_(V, N, C, C, (long long)N * C), bf, MN_(dL1, N, K, dL1_ld, dL1_bs), bf, C, K, N, BT,
                 to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true, 0, true));
   }
   // ---- 8. token resampler ---------------------------------------------------------------------------------------------
