@@ -473,20 +473,28 @@ def run_engine(args, rank, world, local_rank):
         if not args.no_graph:
             for ns in (2, 1):
                 train_streams[0] = ns
+                g_train, captured = None, 1
                 try:
                     g_train, res_static = capture(step_train, "train")
-                    run_step = g_train.replay
-                    launch_mode = (f"cuda-graph replay of the whole train step (fwd + bwd + all-reduce + Adam), "
-                                   f"{ns} stream(s)")
-                    break
                 except Exception as e:                                # e.g. an op that cannot be captured
                     print(f"[bench] train-step graph capture with {ns} stream(s) failed ({type(e).__name__}: "
                           f"{str(e).splitlines()[0]})", file=sys.stderr)
                     torch.cuda.synchronize(dev)
-                    run_step = step_train
-                    res_static = None
-                    for k_ in range(nmod):
-                        outs[k_] = None
+                    captured = 0
+                if dist is not None:                                  # every rank must take the same path: the warm-up
+                    flag = torch.tensor([captured], device=dev)       # steps of an extra attempt run real collectives
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                    captured = int(flag.item())
+                if captured:
+                    run_step = g_train.replay
+                    launch_mode = (f"cuda-graph replay of the whole train step (fwd + bwd + all-reduce + Adam), "
+                                   f"{ns} stream(s)")
+                    break
+                run_step = step_train
+                res_static = None
+                g_train = None
+                for k_ in range(nmod):
+                    outs[k_] = None
         if res_static is None:
             train_streams[0] = 1                                      # eager: autograd stream syncs cost more than they hide
 
