@@ -24,7 +24,8 @@ class Desc(C.Structure):
 PARAM_FIELDS = ["resample_w", "resample_b", "fc_w", "fc_b", "a1_w", "a1_b", "v1_w", "v1_b", "bott_w", "bott_b",
                 "v2_w", "v2_b", "a2_w", "a2_b", "s_w", "s_b", "c_w", "c_b", "tokens", "gate_av", "gate",
                 "down_w", "up_w", "bn1_w", "bn1_b", "bn2_w", "bn2_b", "bn1_rm", "bn1_rv", "bn2_rm", "bn2_rv",
-                "lnb_w", "lnb_b", "lnp_w", "lnp_b", "t_w", "t_b"]
+                "lnb_w", "lnb_b", "lnp_w", "lnp_b", "t_w", "t_b",
+                "rs_rowptr", "rs_col", "rs_val", "rst_rowptr", "rst_col", "rst_val"]
 
 
 class Params(C.Structure):
@@ -52,7 +53,7 @@ EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgs
            "dgsct_bwd_saved_workspace_bytes", "dgsct_adapter_bwd_saved",
            "dgsct_adapter_fwd", "dgsct_bicubic_matrix", "dgsct_num_stages", "dgsct_stage_name",
            "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
-           "dgsct_tc_error_flag"]
+           "dgsct_tc_error_flag", "dgsct_bicubic_csr_capacity", "dgsct_bicubic_csr"]
 
 _lib = None
 
@@ -101,6 +102,10 @@ def lib() -> C.CDLL:
     L.dgsct_pack_params.argtypes = [C.POINTER(Desc), C.POINTER(Params), C.c_void_p, C.c_void_p]
     L.dgsct_bicubic_matrix.restype = C.c_int
     L.dgsct_bicubic_matrix.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.dgsct_bicubic_csr_capacity.restype = C.c_int
+    L.dgsct_bicubic_csr_capacity.argtypes = [C.c_int, C.c_int]
+    L.dgsct_bicubic_csr.restype = C.c_int
+    L.dgsct_bicubic_csr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dgsct_num_stages.restype = C.c_int
     L.dgsct_stage_name.restype = C.c_char_p
     L.dgsct_stage_name.argtypes = [C.c_int]

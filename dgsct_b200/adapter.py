@@ -50,14 +50,25 @@ _PARAM_MAP = {
 }
 
 _workspaces: Dict[tuple, torch.Tensor] = {}
+_captured_keys: set = set()          # workspaces a CUDA graph was captured against
+_retired: list = []                  # ... are never freed: graph replays keep writing into them
 
 
-def _workspace(device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
+def _workspace(device: torch.device, stream_ptr, nbytes: int) -> torch.Tensor:
+    """Scratch cached per (device, stream).  A workspace that was handed out while the stream was being captured into a
+    CUDA graph is pinned for the life of the process: when a later, larger call regrows the cache entry the old tensor
+    moves to ``_retired`` instead of being freed, so replays of the captured graph never write into recycled memory."""
     key = (device.index, stream_ptr)
     ws = _workspaces.get(key)
+    capturing = torch.cuda.is_current_stream_capturing()
     if ws is None or ws.numel() < nbytes:
+        if ws is not None and key in _captured_keys:
+            _retired.append(ws)
+            _captured_keys.discard(key)
         ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
+    if capturing:
+        _captured_keys.add(key)
     return ws
 
 
@@ -75,6 +86,32 @@ def bicubic_matrix(n_in_side: int, n_out_side: int, device) -> torch.Tensor:
         w = host.to(device)
         _bicubic_cache[key] = w
     return w
+
+
+_bicubic_csr_cache: Dict[tuple, tuple] = {}
+
+
+def bicubic_csr(n_in_side: int, n_out_side: int, device):
+    """CSR of the AVS-S4 bicubic resampler (PVT_AVSModel.py:190-197) and of its transpose, built by the engine's host
+    helper and cached per device: ((rowptr, col, val), (rowptr_T, col_T, val_T)) -- int32 / fp32 device tensors."""
+    key = (n_in_side, n_out_side, str(device))
+    hit = _bicubic_csr_cache.get(key)
+    if hit is None:
+        lib = L.lib()
+        cap = lib.dgsct_bicubic_csr_capacity(n_in_side, n_out_side)
+        out = []
+        for transpose, rows in ((0, n_out_side * n_out_side), (1, n_in_side * n_in_side)):
+            rp = torch.empty(rows + 1, dtype=torch.int32)
+            ci = torch.empty(cap, dtype=torch.int32)
+            va = torch.empty(cap, dtype=torch.float32)
+            nnz = lib.dgsct_bicubic_csr(n_in_side, n_out_side, transpose, C.c_void_p(rp.data_ptr()), C.c_void_p(ci.data_ptr()),
+                                        C.c_void_p(va.data_ptr()))
+            if nnz < 0:
+                L.check(nnz, "bicubic_csr")
+            out.append((rp.to(device), ci[:nnz].to(device), va[:nnz].to(device)))
+        hit = tuple(out)
+        _bicubic_csr_cache[key] = hit
+    return hit
 
 
 def _describe(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other: torch.Tensor, training: bool,
@@ -127,9 +164,15 @@ def _describe(cfg: dict, params: Dict[str, torch.Tensor], x: torch.Tensor, other
         s_in, s_out = int(math.isqrt(No)), int(math.isqrt(N))
         if s_in * s_in != No or s_out * s_out != N:
             raise ValueError("the bicubic resampler needs square token grids")
-        w = bicubic_matrix(s_in, s_out, dev)
-        P.resample_w = w.data_ptr()
         flags |= L.F_NO_CONV_BIAS
+        if cfg.get("dense_bicubic", False) or Co % 8 or Cc % 8:
+            # dense (N, No) interpolation matrix through the GEMM path (bf16 coefficients on the tensor-core path)
+            P.resample_w = bicubic_matrix(s_in, s_out, dev).data_ptr()
+        else:
+            # 16-tap stencil as CSR: one gather kernel, fp32 coefficients (forward) and its transpose (backward)
+            (rp, ci, va), (rpt, cit, vat) = bicubic_csr(s_in, s_out, dev)
+            P.rs_rowptr, P.rs_col, P.rs_val = rp.data_ptr(), ci.data_ptr(), va.data_ptr()
+            P.rst_rowptr, P.rst_col, P.rst_val = rpt.data_ptr(), cit.data_ptr(), vat.data_ptr()
     else:
         w = params.get("conv_adapter.weight")
         if w is None or w.numel() != N * No:
@@ -315,8 +358,8 @@ class _AdapterFn(torch.autograd.Function):
         targets = None
         if getattr(module, "fused_grad_accumulation", False):
             targets = {}
-            for n, p in module.named_parameters():
-                g = p.grad
+            for n, p in module._named_tensors():
+                g = p.grad if p.is_leaf else None
                 if n in ctx.names and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == xt.device:
                     targets[n] = g
         dx, dother, grads = adapter_backward_raw(cfg, params, xt, ot, d_out, d_smap, d_tmap, training=ctx.training,
@@ -327,6 +370,11 @@ class _AdapterFn(torch.autograd.Function):
             g = grads.get(n)
             p = params.get(n)
             flat.append(g.view_as(p) if (g is not None and p is not None) else None)
+        # AdapterDDP: every kernel that adds into this module's bucket views has now been enqueued on the current stream
+        # (a module full-backward hook would fire BEFORE this function when no input requires grad)
+        cb = getattr(module, "_ddp_done_cb", None)
+        if cb is not None:
+            cb()
         return (None, None, dx, dother, *flat)
 
 
@@ -400,10 +448,32 @@ class VisualAdapter(nn.Module):
                     gate_before_ln=v["gate_before_ln"], use_bn=bool(self.use_bn), use_gate=self.gate is not None,
                     temporal=v["temporal"], eps_ln=1e-5, eps_bn=1e-5, bn_momentum=0.1)
 
+    def _named_tensors(self):
+        """(state_dict name, tensor) for every engine parameter / buffer, resolved by ATTRIBUTE walk rather than through
+        ``named_parameters()``: ``nn.DataParallel`` replicas (S4 / MS3 / AVQA scripts, avs_s4/train.py:139) keep their
+        broadcast copies as plain attributes and have empty ``_parameters`` dicts."""
+        out = []
+        for name in _PARAM_MAP:
+            obj = self
+            for part in name.split("."):
+                if isinstance(obj, nn.Sequential) and part.isdigit():
+                    obj = obj[int(part)] if int(part) < len(obj) else None
+                else:
+                    obj = getattr(obj, part, None)
+                if obj is None:
+                    break
+            if isinstance(obj, torch.Tensor):
+                out.append((name, obj))
+        return out
+
     def _param_dict(self) -> Dict[str, torch.Tensor]:
-        sd = dict(self.named_parameters())
-        sd.update(dict(self.named_buffers()))
-        return {k: v.detach() for k, v in sd.items() if k in _PARAM_MAP}
+        return {k: v.detach() for k, v in self._named_tensors()}
+
+    def invalidate_packed(self) -> None:
+        """Drop the cached bf16 operand copies.  The cache is keyed on the parameters' ``_version``, which updates made
+        through ``.data`` (manual ``p.data.copy_``, EMA, ``dist.broadcast(p.data)``) do not bump: call this after them."""
+        self._packed_key = None
+        self._packed_buf = None
 
     _PACKED_SOURCES = ("conv_adapter.weight", "fc.weight", "my_tokens", "fc_affine_video_1.weight",
                        "fc_affine_video_2.weight", "down_sampler.weight", "up_sampler.weight")
@@ -430,10 +500,11 @@ class VisualAdapter(nn.Module):
         if xt.shape[1] != self.conv_dim_out or ot.shape[1] != self.conv_dim_in:
             raise RuntimeError(f"token counts ({xt.shape[1]}, {ot.shape[1]}) do not match conv_dim_out/conv_dim_in "
                                f"({self.conv_dim_out}, {self.conv_dim_in})")
+        tensors = self._named_tensors()
         need_grad = torch.is_grad_enabled() and (x.requires_grad or vis_token.requires_grad or
-                                                 any(p.requires_grad for p in self.parameters()))
+                                                 any(p.requires_grad for _, p in tensors))
         if need_grad:
-            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            named = [(n, p) for n, p in tensors if p.requires_grad and n in _GRAD_NAMES.values()]
             res = _AdapterFn.apply(self, tuple(n for n, _ in named), xt, ot, *[p for _, p in named])
         else:
             cfg, params = self._cfg(), self._param_dict()

@@ -122,59 +122,6 @@ struct EpiOut {
     warp_store_block32<OUT_BF16>(out, off, n0, v0, v1, nv0 + nv1, row_ok, stage);
   }
 };
-// ---- fused backward epilogues (DGSCT_FUSE_BWD=1; compiled, NOT yet validated on hardware -> off by default) ------------
-// dXc = dz2 . Wv2 consumed in the epilogue instead of a store + bwd_xc_kernel's pass:
-//   gX1[b,m,n] += acc * (1 + mgate[b,n]) ;  dm[b,n] += sum_m acc * X1[b,m,n]
-struct EpiXcFused {
-  static constexpr bool kRowIndependent = true;
-  bf16* gx1; const bf16* x1; long long ld, sb; const float* mgate; float* dm; int C;
-  __device__ __forceinline__ void begin(int, int, bool) {}
-  __device__ __forceinline__ void end(int, int, bool) {}
-  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
-    const int nvalid = nvalid16(n0, N);
-    float w[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) w[j] = 0.f;
-    if (row_ok && nvalid > 0) {
-      const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
-      float mg[16];
-      load16_guard(mgate + (long long)b * C + n0, mg, nvalid);
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nvalid) {
-          const float xv = __bfloat162float(x1[idx + j]), gv = __bfloat162float(gx1[idx + j]);
-          w[j] = v[j] * xv;
-          v[j] = fmaf(v[j], 1.f + mg[j], gv);
-        }
-      store_row16<true>(gx1, idx, v, nvalid);
-    }
-    float* dmp = dm; const int Cc = C;
-    segmented_colsum16(w, b, row_ok, n0, N, [dmp, Cc](int bb, int col, float s_, bool owner) {
-      if (owner) atomicAdd(&dmp[(long long)bb * Cc + col], s_);
-    });
-  }
-};
-// z1 = X1 . Wv1^T consumed in the epilogue instead of a store + bwd_channel_mask_kernel's in-place pass:
-//   dz1[b,m,n] = dr1[b,n] * 1[acc + bias[n] > 0]  (bf16) ;  d_b1[n] += sum_{b,m} dz1
-struct EpiChannelMask {
-  static constexpr bool kRowIndependent = true;
-  bf16* out; long long ld, sb; const float* bias; const float* dr1; int dr_ld; float* d_b1;
-  __device__ __forceinline__ void begin(int, int, bool) {}
-  __device__ __forceinline__ void end(int, int, bool) {}
-  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
-    const int nvalid = nvalid16(n0, N);
-    float bn[16], dr[16];
-    load16_guard(bias + n0, bn, nvalid);
-    load16_guard(dr1 + (long long)b * dr_ld + n0, dr, nvalid);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = (row_ok && j < nvalid && v[j] + bn[j] > 0.f) ? dr[j] : 0.f;
-    if (row_ok && nvalid > 0) store_row16<true>(out, (size_t)((long long)b * sb + (long long)m * ld + n0), v, nvalid);
-    const float s_ = warp_colsum16(v);                      // one global column sum: frames need no separation
-    const int lane = threadIdx.x & 31;
-    const int col = n0 + colsum16_owner_col(lane);
-    if (((lane & 1) == 0) && col < N) atomicAdd(&d_b1[col], s_);
-  }
-};
 struct EpiNone {   // placeholder for products that never take the tensor-core kernel
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
@@ -314,7 +261,6 @@ struct BwdPlan {
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
   size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, dWup_d, dWd_d, zero_end;
   size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
-  size_t PQ, TT;                      // DGSCT_FUSE_BWD: [P | dL1] (BT,N,2K) bf16 and [dT' ; tokens] (BT,2K,C) bf16
   size_t total;
 };
 
@@ -354,10 +300,6 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
   p.opm = take(BT * C * 4);
   p.csm_part = take(BT * (size_t)CSM_MAX_CHUNKS * K * 4);
-  if (d.io_dtype == DGSCT_BF16 && getenv("DGSCT_FUSE_BWD")) {
-    p.PQ = take(BT * N * 2 * K * 2);
-    p.TT = take(BT * 2 * K * C * 2);
-  }
   p.out_fwd = take(BT * N * C * es); p.smap_fwd = take(BT * N * es); p.tmap_fwd = take(BT * 4);
   p.total = off;
   return p;
@@ -444,7 +386,6 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     ld_up = ldz; ld_dn = C; ld_v = C; ld_fc = Co; ld_res = No; ld_tok = C;
   }
   const int wbf = tcp ? 1 : 0;
-  const bool fuse_bwd = tcp && getenv("DGSCT_FUSE_BWD") != nullptr;   // experimental fused epilogues (see tc::EpiXcFused)
   const Gemm GB{ST_MISC, "bwd_gemm", st, tcp};
   const Gemm G_UD{ST_BWD_UPDOWN, "bwd_updown", st, tcp}, G_SP{ST_BWD_SPATIAL, "bwd_spatial", st, tcp}, G_CH{ST_BWD_CHANNEL, "bwd_channel", st, tcp},
       G_TK{ST_BWD_TOKEN, "bwd_token", st, tcp}, G_FC{ST_BWD_FC, "bwd_fc", st, tcp}, G_DW{ST_BWD_DWRES, "bwd_dwres", st, tcp},
@@ -488,8 +429,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     a.eps = d.eps_ln; a.C = C; a.rows = R; a.db2 = gUo; a.db2_bf16 = bf;
     a.d_lnw = lnp ? G.lnp_w : nullptr; a.d_lnb = lnp ? G.lnp_b : nullptr; a.d_gate = a.gate ? G.gate : nullptr;
     const int wpb = C <= 768 ? 8 : 4;
-    static bool attr1 = false;
-    if (!attr1) { DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr1 = true; }
+    static PerDeviceOnce attr1;
+    if (attr1.first()) DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     StageScope _sc(ST_OUT_LN, st); count_launch();
     { cudaError_t pre = cudaGetLastError(); if (pre != cudaSuccess) { set_cuda_error(pre, "before bwd_out"); return DGSCT_ERR_CUDA; } }
     // vectorised kernel: also produces the bn2-backward column sums (colA = sum dB2, colB = sum dB2*Uo)
@@ -568,8 +509,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     a.dx1 = gX1; a.dx1_bf16 = bf; a.dm_acc = dm; a.dsig = dsig; a.dtau = use_tau ? dtau : nullptr;
     a.d_lnw = lnb ? G.lnb_w : nullptr; a.d_lnb = lnb ? G.lnb_b : nullptr;
     const int wpb = C <= 768 ? 8 : 4;
-    static bool attr2 = false;
-    if (!attr2) { DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_gate_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr2 = true; }
+    static PerDeviceOnce attr2;
+    if (attr2.first()) DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_gate_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     StageScope _sc(ST_BWD_GATE_LN, st); count_launch();
     if (!launch_bwd_gate_ln_vec(a, BT, st))
       bwd_gate_ln_kernel<<<rgrid, wpb * 32, (size_t)(2 + 2 * wpb) * C * 4, st>>>(a);
@@ -593,15 +534,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       bwd_spatial_mask_kernel<<<dim3(ceil_div(H, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S2, bf, H, N, P.v2_b, ds, P.s_w, aq2, aq2_ld,
                                                                                         G.s_w, daq2, daq_ld, G.v2_b);
       KCHECK("bwd_spatial_mask"); }
-    // dXc = dz2 . Wv2 ; dX1 += dXc (1+m) ; dm += sum_n dXc X1      (fused: in the product's epilogue; else via S1)
-    bool xc_fused = false;
-    if (fuse_bwd) {
-      tc::EpiXcFused te{(bf16*)gX1, (const bf16*)X1, C, (long long)N * C, mvec, dm, C};
-      const int rc = run_tc_only(G_SP, K_(S2, N, H, H, (long long)N * H), MN_(Wv2_op, H, C, ld_v, 0), N, C, H, BT, te);
-      if (rc == DGSCT_OK) xc_fused = true;
-      else if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
-    }
-    if (!xc_fused) {
+    // dXc = dz2 . Wv2 -> S1 ; dX1 += dXc (1+m) ; dm += sum_n dXc X1
+    {
       EpiOut e2 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
       RC(run_gemm(G_SP, K_(S2, N, H, H, (long long)N * H), bf, MN_(Wv2_op, H, C, ld_v, 0), wbf, N, C, H, BT,
                   to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e2), e2, AxIdentity{}, true));
@@ -655,14 +589,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   }
   {
     // z1 = X1 . Wv1^T (pre-bias) -> S1 ; dz1 = dr1 * 1[z1+b>0] ; dX1 += dz1 . Wv1 ; dWv1 += dz1^T X1
-    bool mask_fused = false;
-    if (fuse_bwd) {
-      tc::EpiChannelMask te{(bf16*)S1, C, (long long)N * C, P.v1_b, dr1, C, G.v1_b};
-      const int rc = run_tc_only(G_CH, K_(X1, N, C, C, (long long)N * C), K_(Wv1_op, C, C, ld_v, 0), N, C, C, BT, te);
-      if (rc == DGSCT_OK) mask_fused = true;
-      else if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
-    }
-    if (!mask_fused) {
+    {
       EpiOut e1 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
       RC(run_gemm(G_CH, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
                   to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
@@ -723,17 +650,11 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
     // d tokens += sum_b dTp[b]
-    // fused variant (DGSCT_FUSE_BWD, K = 32 tensor-core path): dV = [P | dL1] . [dT' ; T] is one product over 2K
-    const bool fuse_dv = fuse_bwd && K == 32 && C % 8 == 0 && bp.PQ != 0;
-    bf16* PQ = (bf16*)(ws + bp.PQ); bf16* TT = (bf16*)(ws + bp.TT);
     const void* dTpOp = dTp;
     long long dTp_bs = (long long)K * C;
     { StageScope _sc(ST_MISC, st); count_launch(2);
       sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, st>>>(dTp, BT, (size_t)K * C, G.tokens);
-      if (fuse_dv) {
-        build_tt_kernel<<<ew_grid, 256, 0, st>>>(dTp, (const bf16*)Tok_op, ld_tok, TT, BT, K, C);
-        dTpOp = TT; dTp_bs = 2LL * K * C;                               // first K rows of every frame's [dT' ; T]
-      } else if (tcp) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
+      if (tcp) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
       KCHECK("dtok_sum"); }
     // dP = V . dTp^T (fp32) ; dL1 = P (dP - sum_n dP P) -> gQ
     EpiOut e5 = eo(gP, 0, K, (long long)N * K, OUT_STORE);
@@ -745,17 +666,12 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
         float* part = (float*)(ws + bp.csm_part);
         count_launch();
         col_softmax_bwd_partial_kernel<<<grid, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, part, N, K);
-        if (fuse_dv) col_softmax_bwd_apply_cat_kernel<<<grid, 256, 0, st>>>(gP, (const bf16*)Pm, part, PQ, N, K);
-        else col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
+        col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
       KCHECK("col_softmax_bwd"); }
     // dV = P . dTp + dL1 . T + dobar / N
     EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
     const void* dL1 = gQ; long long dL1_ld = K, dL1_bs = (long long)N * K;
-    if (fuse_dv) {
-      RC(run_gemm(G_TK, K_(PQ, N, 2 * K, 2 * K, 2LL * N * K), 1, MN_(TT, 2 * K, C, C, 2LL * K * C), 1, N, C, 2 * K, BT,
-                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
-      dL1 = PQ + K; dL1_ld = 2 * K; dL1_bs = 2LL * N * K;              // the dL1 half of [P | dL1]
-    } else {
+    {
       RC(run_gemm(G_TK, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                   to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
       EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
@@ -769,7 +685,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
                 to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true, 0, true));
   }
   // ---- 8. token resampler ---------------------------------------------------------------------------------------------
-  const bool fc_first = tcp && use_fc_first(d);
+  const bool fc_first = tcp && use_fc_first(d, P);
   if (fc_first) {
     // forward was V = Wres . O' + b_res (x) s + b_fc with O' = other . Wfc^T kept in the U buffer, s = rowsum(Wfc)
     const void* Op = U;
@@ -837,9 +753,15 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       rowsum_frames_kernel<<<N, 256, 0, sst>>>(gU, bf, BT, N, Co, G.resample_b);
       KCHECK("dres_b");
     }
-    EpiOut e4 = eo(dother, bf, Co, (long long)No * Co, OUT_STORE);
-    RC(run_gemm(G_DO, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gU, N, Co, Co, (long long)N * Co), bf, No, Co, N, BT,
-                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e4), e4, AxIdentity{}, true));
+    if (P.rs_rowptr) {      // dother[b] = M^T . dU[b] from the transposed stencil
+      StageScope _sc(ST_BWD_DOTHER, st); count_launch();
+      if (!launch_spmm_frames(P.rst_rowptr, P.rst_col, P.rst_val, gU, dother, bf, BT, No, N, Co, st)) return DGSCT_ERR_UNSUPPORTED;
+      KCHECK("dother_spmm");
+    } else {
+      EpiOut e4 = eo(dother, bf, Co, (long long)No * Co, OUT_STORE);
+      RC(run_gemm(G_DO, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gU, N, Co, Co, (long long)N * Co), bf, No, Co, N, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e4), e4, AxIdentity{}, true));
+    }
   }
   RC(join_side());
   return DGSCT_OK;

@@ -23,8 +23,9 @@ int validate_desc(const dgsct_desc* d) {
   return DGSCT_OK;
 }
 
-bool use_fc_first(const dgsct_desc& d) {
-  return getenv("DGSCT_FC_FIRST") != nullptr && d.io_dtype == DGSCT_BF16 && !(d.flags & DGSCT_F_FORCE_SIMT) && d.C < d.Co &&
+bool use_fc_first(const dgsct_desc& d, const dgsct_params& P) {
+  if (P.rs_rowptr) return false;            // sparse (stencil) resampler: U = M . other is a gather, keep the reference order
+  return getenv("DGSCT_NO_FC_FIRST") == nullptr && d.io_dtype == DGSCT_BF16 && !(d.flags & DGSCT_F_FORCE_SIMT) && d.C < d.Co &&
          d.C % 8 == 0 && d.Co % 8 == 0;
 }
 
@@ -130,7 +131,11 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
   DGSCT_CUDA_CHECK(cudaMemsetAsync(ws + pl.acc_begin, 0, pl.acc_end - pl.acc_begin, st)); }
 
   // (R1) U[b] = Wres (N,No) . other[b] (No,Co) + b_res[n]                       net_trans.py:553
-  {
+  if (P.rs_rowptr) {      // sparse resampling matrix (bicubic stencil, PVT_AVSModel.py:190-197)
+    StageScope _sc(ST_RESAMPLE_CONV, st); count_launch();
+    if (!launch_spmm_frames(P.rs_rowptr, P.rs_col, P.rs_val, other, U, bf, BT, N, No, Co, st)) return DGSCT_ERR_UNSUPPORTED;
+    DGSCT_LAUNCH_CHECK("resample_spmm");
+  } else {
     GemmShape sh{N, Co, No, BT, 1};
     EpiBiasStore e = epi_store(U, bf, Co, (long long)N * Co);
     e.bias_m = (d.flags & DGSCT_F_NO_CONV_BIAS) ? nullptr : P.resample_b;
@@ -305,7 +310,7 @@ int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaSt
     count_launch();
     pack_rows_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(src, r, c, (bf16*)(packed + off), ld);
   };
-  rows(P.resample_w, N, No, pp.res, pp.ld_res);
+  if (P.resample_w) rows(P.resample_w, N, No, pp.res, pp.ld_res);
   rows(P.fc_w, C, Co, pp.fc, pp.ld_fc);
   rows(P.tokens, K, C, pp.tok, pp.ld_c);
   rows(P.v1_w, C, C, pp.v1, pp.ld_c);
@@ -438,7 +443,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
   { StageScope _sc(ST_MISC, st);
     DGSCT_CUDA_CHECK(cudaMemsetAsync(ws + pl.acc_begin, 0, pl.acc_end - pl.acc_begin, st)); }
 
-  const bool fc_first = use_fc_first(d);
+  const bool fc_first = use_fc_first(d, P);
   if (fc_first) {
     // (R1') O'[b] (No,C) = other[b] (No,Co) . Wfc^T          (frames flattened, Wfc resident)
     // (R2') V[b] (N,C)  = Wres (N,No) . O'[b] + b_res[n] * s[c] + b_fc[c],  s = rowsum(Wfc) ; osum[b,c] = sum_n V
@@ -462,7 +467,11 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     }
   }
   // (R1) U[b] (N,Co) = Wres (N,No) . other[b] (No,Co) + b_res[n]
-  if (!fc_first) {
+  if (!fc_first && P.rs_rowptr) {   // sparse resampling matrix (bicubic stencil): gather with fp32 coefficients
+    StageScope _sc(ST_RESAMPLE_CONV, st); count_launch();
+    if (!launch_spmm_frames(P.rs_rowptr, P.rs_col, P.rs_val, other, U, 1, BT, N, No, Co, st)) return DGSCT_ERR_UNSUPPORTED;
+    DGSCT_LAUNCH_CHECK("resample_spmm");
+  } else if (!fc_first) {
     auto te = tc_store<true>(U, Co, (long long)N * Co);
     EpiBiasStore se = epi_store(U, 1, Co, (long long)N * Co);
     te.bias_m = se.bias_m = (d.flags & DGSCT_F_NO_CONV_BIAS) ? nullptr : P.resample_b;

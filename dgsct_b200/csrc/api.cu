@@ -2,12 +2,54 @@
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "adapter_fwd.h"
 
 namespace dgsct {
 static thread_local char g_err[512] = "";
 void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int check_arch() {
+  static int cached[kMaxDevices] = {};      // 0 unknown, 1 ok, 2 wrong architecture
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return DGSCT_ERR_CUDA;
+  if (dev >= 0 && dev < kMaxDevices && cached[dev]) return cached[dev] == 1 ? DGSCT_OK : DGSCT_ERR_ARCH;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return DGSCT_ERR_CUDA;
+  const int ok = (major == 10);             // the library holds sm_100a code only
+  if (dev >= 0 && dev < kMaxDevices) cached[dev] = ok ? 1 : 2;
+  return ok ? DGSCT_OK : DGSCT_ERR_ARCH;
+}
+
+static int* g_flag_host = nullptr;
+static std::once_flag g_flag_once;
+int* timeout_flag_device_ptr() {
+  std::call_once(g_flag_once, [] {
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      g_flag_host = reinterpret_cast<int*>(h);
+      *g_flag_host = 0;
+    }
+  });
+  return g_flag_host;      // unified addressing: portable mapped host memory has the same address on every device
+}
+int timeout_flag_host_value(int reset) {
+  if (!g_flag_host) return 0;
+  const int v = *reinterpret_cast<volatile int*>(g_flag_host);
+  if (reset) *reinterpret_cast<volatile int*>(g_flag_host) = 0;
+  return v;
+}
+// common prologue of the compute entry points
+static int entry_checks() {
+  const int rc = check_arch();
+  if (rc != DGSCT_OK) return rc;
+  if (timeout_flag_host_value(0)) return DGSCT_ERR_TIMEOUT;
+  return DGSCT_OK;
 }
 }  // namespace dgsct
 
@@ -26,6 +68,7 @@ const char* dgsct_status_string(int s) {
     case DGSCT_ERR_CUDA: return "CUDA error";
     case DGSCT_ERR_UNSUPPORTED: return "unsupported";
     case DGSCT_ERR_ARCH: return "device is not sm_100";
+    case DGSCT_ERR_TIMEOUT: return "a tcgen05 pipeline wait timed out in an earlier call (results since then are invalid)";
     default: return "unknown status";
   }
 }
@@ -47,8 +90,9 @@ int dgsct_pack_params(const dgsct_desc* desc, const dgsct_params* params, void* 
   if (rc != DGSCT_OK) return rc;
   if (!params || !packed) return DGSCT_ERR_NULL;
   const dgsct_params& P = *params;
-  if (!P.resample_w || !P.fc_w || !P.tokens || !P.v1_w || !P.v2_w || !P.down_w || !P.up_w) return DGSCT_ERR_NULL;
+  if ((!P.resample_w && !P.rs_rowptr) || !P.fc_w || !P.tokens || !P.v1_w || !P.v2_w || !P.down_w || !P.up_w) return DGSCT_ERR_NULL;
   if ((uintptr_t)packed & 255) return DGSCT_ERR_WORKSPACE;
+  if ((rc = entry_checks()) != DGSCT_OK) return rc;
   return pack_params(*desc, P, (char*)packed, (cudaStream_t)stream);
 }
 
@@ -58,13 +102,15 @@ int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const 
   int rc = validate_desc(desc);
   if (rc != DGSCT_OK) return rc;
   if (!params || !x || !other || !out || !spatial_map || !workspace) return DGSCT_ERR_NULL;
+  if ((rc = entry_checks()) != DGSCT_OK) return rc;
   const dgsct_desc& d = *desc;
   const dgsct_params& P = *params;
-  if (!P.resample_w || !P.fc_w || !P.fc_b || !P.a1_w || !P.a1_b || !P.v1_w || !P.v1_b || !P.bott_w || !P.bott_b ||
+  if ((!P.resample_w && !P.rs_rowptr) || !P.fc_w || !P.fc_b || !P.a1_w || !P.a1_b || !P.v1_w || !P.v1_b || !P.bott_w || !P.bott_b ||
       !P.v2_w || !P.v2_b || !P.a2_w || !P.a2_b || !P.s_w || !P.s_b || !P.c_w || !P.c_b || !P.tokens || !P.gate_av ||
       !P.down_w || !P.up_w)
     return DGSCT_ERR_NULL;
   if (!(d.flags & DGSCT_F_NO_CONV_BIAS) && !P.resample_b) return DGSCT_ERR_NULL;
+  if (P.rs_rowptr && (!P.rs_col || !P.rs_val || !(d.flags & DGSCT_F_NO_CONV_BIAS))) return DGSCT_ERR_NULL;
   if ((d.flags & DGSCT_F_USE_GATE) && !P.gate) return DGSCT_ERR_NULL;
   if ((d.flags & DGSCT_F_USE_BN) &&
       (!P.bn1_w || !P.bn1_b || !P.bn2_w || !P.bn2_b || !P.bn1_rm || !P.bn1_rv || !P.bn2_rm || !P.bn2_rv))
@@ -92,8 +138,10 @@ static int bwd_entry(const dgsct_desc* desc, const dgsct_params* params, const v
   if (rc != DGSCT_OK) return rc;
   if (!params || !x || !other || !d_out || !dx || !dother || !grads || !workspace) return DGSCT_ERR_NULL;
   if (need_saved && !saved) return DGSCT_ERR_NULL;
+  if ((rc = entry_checks()) != DGSCT_OK) return rc;
   const dgsct_desc& d = *desc;
   const dgsct_grads& G = *grads;
+  if (params->rs_rowptr && (!params->rst_rowptr || !params->rst_col || !params->rst_val)) return DGSCT_ERR_NULL;
   if (!G.fc_w || !G.fc_b || !G.a1_w || !G.a1_b || !G.v1_w || !G.v1_b || !G.bott_w || !G.bott_b || !G.v2_w || !G.v2_b ||
       !G.a2_w || !G.a2_b || !G.s_w || !G.s_b || !G.c_w || !G.c_b || !G.tokens || !G.gate_av || !G.down_w || !G.up_w)
     return DGSCT_ERR_NULL;
@@ -161,6 +209,58 @@ int dgsct_bicubic_matrix(int n_in, int n_out, float* w) {
     }
   }
   return DGSCT_OK;
+}
+
+int dgsct_bicubic_csr_capacity(int n_in, int n_out) {
+  if (n_in <= 0 || n_out <= 0) return DGSCT_ERR_BAD_DESC;
+  return 16 * n_out * n_out;
+}
+
+int dgsct_bicubic_csr(int n_in, int n_out, int transpose, int32_t* rowptr, int32_t* col, float* val) {
+  if (n_in <= 0 || n_out <= 0 || !rowptr || !col || !val) return DGSCT_ERR_BAD_DESC;
+  const int rows_out = n_out * n_out, rows_in = n_in * n_in;
+  // taps of every output pixel (border-clamped duplicates merged), in fp64
+  std::vector<std::vector<std::pair<int, double>>> taps(rows_out);
+  const double scale = (double)n_in / (double)n_out;   // align_corners = False
+  for (int oy = 0; oy < n_out; ++oy) {
+    const double sy = scale * (oy + 0.5) - 0.5;
+    const int iy = (int)floor(sy);
+    double wy[4]; cubic_coeffs(sy - iy, wy);
+    for (int ox = 0; ox < n_out; ++ox) {
+      const double sx = scale * (ox + 0.5) - 0.5;
+      const int ix = (int)floor(sx);
+      double wx[4]; cubic_coeffs(sx - ix, wx);
+      auto& t = taps[(size_t)oy * n_out + ox];
+      for (int a = 0; a < 4; ++a) {
+        int yy = iy - 1 + a; yy = yy < 0 ? 0 : (yy >= n_in ? n_in - 1 : yy);
+        for (int b = 0; b < 4; ++b) {
+          int xx = ix - 1 + b; xx = xx < 0 ? 0 : (xx >= n_in ? n_in - 1 : xx);
+          const int c = yy * n_in + xx;
+          bool merged = false;
+          for (auto& e : t) if (e.first == c) { e.second += wy[a] * wx[b]; merged = true; break; }
+          if (!merged) t.emplace_back(c, wy[a] * wx[b]);
+        }
+      }
+    }
+  }
+  int nnz = 0;
+  if (!transpose) {
+    for (int r = 0; r < rows_out; ++r) {
+      rowptr[r] = nnz;
+      for (auto& e : taps[r]) { col[nnz] = e.first; val[nnz] = (float)e.second; ++nnz; }
+    }
+    rowptr[rows_out] = nnz;
+  } else {
+    std::vector<int> cnt(rows_in + 1, 0);
+    for (int r = 0; r < rows_out; ++r) for (auto& e : taps[r]) ++cnt[e.first + 1];
+    for (int i = 0; i < rows_in; ++i) cnt[i + 1] += cnt[i];
+    for (int i = 0; i <= rows_in; ++i) rowptr[i] = cnt[i];
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int r = 0; r < rows_out; ++r)
+      for (auto& e : taps[r]) { const int q = fill[e.first]++; col[q] = r; val[q] = (float)e.second; }
+    nnz = cnt[rows_in];
+  }
+  return nnz;
 }
 
 }  // extern "C"

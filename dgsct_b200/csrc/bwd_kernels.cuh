@@ -417,39 +417,6 @@ __global__ void __launch_bounds__(256) col_softmax_bwd_apply_kernel(const float*
   }
 }
 
-// DGSCT_FUSE_BWD: same as col_softmax_bwd_apply_kernel, but writes the K-concatenated operand [P | dL1] (N, 2K) bf16 so that
-// dV = P dT' + dL1 T is ONE product over 2K instead of a store followed by a read-modify-write of the (N, C) gradient
-__global__ void __launch_bounds__(256) col_softmax_bwd_apply_cat_kernel(const float* __restrict__ dP, const bf16* __restrict__ P,
-                                                                        const float* __restrict__ part, bf16* __restrict__ PQ,
-                                                                        int N, int K) {
-  const int s_ = blockIdx.x, b = blockIdx.y, S = gridDim.x;
-  const int groups = blockDim.x / K;
-  const int k = threadIdx.x % K, g = threadIdx.x / K;
-  if (g >= groups) return;
-  float t = 0.f;
-  for (int j = 0; j < S; ++j) t += part[((size_t)b * S + j) * K + k];
-  const int rows = csm_chunk_rows(N);
-  const int n0 = s_ * rows, n1 = min(N, n0 + rows);
-  const size_t base = (size_t)b * N * K;
-  bf16* out = PQ + (size_t)b * N * 2 * K;
-  for (int n = n0 + g; n < n1; n += groups) {
-    const size_t i = base + (size_t)n * K + k;
-    const bf16 pv = P[i];
-    out[(size_t)n * 2 * K + k] = pv;
-    out[(size_t)n * 2 * K + K + k] = __float2bfloat16_rn(__bfloat162float(pv) * (dP[i] - t));
-  }
-}
-// TT[b] (2K, C) bf16 = [dT'[b] (fp32 -> bf16) ; tokens (bf16 operand copy, pitch ld_tok)]
-__global__ void build_tt_kernel(const float* __restrict__ dTp, const bf16* __restrict__ tok, int ld_tok, bf16* __restrict__ TT,
-                                int BT, int K, int C) {
-  const size_t total = (size_t)BT * 2 * K * C;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const size_t r = i / C;
-    const int k2 = (int)(r % (2 * K)), b = (int)(r / (2 * K));
-    TT[i] = k2 < K ? __float2bfloat16_rn(dTp[((size_t)b * K + k2) * C + c]) : tok[(size_t)(k2 - K) * ld_tok + c];
-  }
-}
 
 // vectorised in-place g = A[c]*g + B[c]*x + Cc[c] for bf16 g (pitch g_ld) and fp32 x (pitch x_ld); C % 8 == 0, 16-byte rows
 __global__ void __launch_bounds__(256) affine_combine_vec_kernel(bf16* __restrict__ g, long long g_ld, const float* __restrict__ x,

@@ -32,6 +32,25 @@ void set_cuda_error(cudaError_t e, const char* where);
     }                                                            \
   } while (0)
 
+// cudaFuncSetAttribute is per DEVICE: one flag per device ordinal (nn.DataParallel drives several devices from one process).
+// Returns true the first time it is called for the current device with this flag array.
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;   // unknown: set it again (harmless)
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+// DGSCT_OK when the current device is sm_100 (compute capability 10.x), DGSCT_ERR_ARCH otherwise (cached per device)
+int check_arch();
+// sticky pipeline-timeout flag in host-mapped memory: kernels raise it, every entry point reads it without synchronising
+int* timeout_flag_device_ptr();
+int timeout_flag_host_value(int reset);
+
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -48,14 +48,11 @@ int dgsct_debug_gemm_bf16(const void* A, const void* B, float* D, int M, int N, 
   return DGSCT_OK;
 }
 
-// reads (and optionally clears) the device flag set when a bounded mbarrier wait expired; synchronises
+// value of the sticky pipeline-timeout flag (0 = healthy); synchronises the current device first so that every kernel
+// launched so far has had the chance to raise it; `reset` clears it
 int dgsct_tc_error_flag(int reset) {
-  int* p = tc::tc_err_flag_device_ptr();
-  if (!p) return -1;
-  int v = 0;
-  if (cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (reset) { int z = 0; cudaMemcpy(p, &z, sizeof(int), cudaMemcpyHostToDevice); }
-  return v;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  return timeout_flag_host_value(reset);
 }
 
 }  // extern "C"

@@ -47,8 +47,6 @@ struct Params {
   int rows_per_frame;           // > 0: A is (batch*rows_per_frame, K) contiguous and B is shared, so the frames are flattened
                                 // into one M extent (no per-frame tile padding); the epilogue recovers (b, m) per row
   int* err_flag;                // device int set to non-zero when a bounded wait expires
-  int early_release;            // experiment (DGSCT_EARLY_RELEASE=1, off by default, not yet measured on hardware): epilogue
-                                // warps release the accumulator as soon as their last block of the tile is in registers
   int debug_mode;               // bring-up only: 1 = epilogue skips the TMEM loads, 2 = skips loads and functor
 };
 
@@ -79,7 +77,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      if (err_flag) atomicExch(err_flag, 1);
+      if (err_flag) { *reinterpret_cast<volatile int*>(err_flag) = 1; __threadfence_system(); }
       return false;
     }
   }
@@ -444,7 +442,6 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         if (row_ok) m -= bq * p.rows_per_frame;
       }
       const uint32_t lane_base = tmem_base + (uint32_t)acc * acc_stride + ((uint32_t)(lane_grp * 32) << 16);
-      bool released = false;
       if ((p.debug_mode & 3) < 2 && !(whole_row && half == 1)) {
         epi.begin(bq, m, row_ok);
         const int c_begin = whole_row ? 0 : half * 32, c_step = whole_row ? 32 : 64;
@@ -454,14 +451,6 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           if ((p.debug_mode & 3) == 0) {
             if (two) tmem_ld32(lane_base + (uint32_t)c, v0, v1);
             else tmem_ld16(lane_base + (uint32_t)c, v0);
-            if (p.early_release && c + c_step >= BNI) {
-              // this warp's last block of the tile is in registers: hand the accumulator back to the MMA issuer before
-              // the functor runs (bias / activation / reductions / stores then overlap the next tile's MMAs)
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-              released = true;
-            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { v0[j] = (float)(c + j); v1[j] = (float)(c + 16 + j); }
@@ -483,11 +472,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         }
         epi.end(bq, m, row_ok);
       }
-      if (!released) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
     }
   }
   tc_fence_before();
@@ -520,12 +507,11 @@ bool operands_ok(const OperandDesc& A, const OperandDesc& B, int K);
 
 template <typename EPI>
 inline cudaError_t launch(const Params& p, EPI epi, cudaStream_t st) {
-  static bool attr_set = false;
+  static PerDeviceOnce attr;                 // the > 48 KB dynamic shared-memory opt-in is a per-device function attribute
   const size_t smem = smem_bytes(p);
-  if (!attr_set) {
+  if (attr.first()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) *
                           (p.kb_frames > 0 ? ceil_div(p.batch, p.kb_frames) : ceil_div(p.batch, p.fpack));

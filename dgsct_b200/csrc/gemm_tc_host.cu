@@ -21,21 +21,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-__device__ int g_tc_err_flag = 0;
-
-int* tc_err_flag_device_ptr() {
-  static thread_local int* ptr = nullptr;
-  static thread_local int dev = -1;
-  int cur = 0;
-  cudaGetDevice(&cur);
-  if (!ptr || cur != dev) {
-    void* p = nullptr;
-    if (cudaGetSymbolAddress(&p, g_tc_err_flag) != cudaSuccess) return nullptr;
-    ptr = reinterpret_cast<int*>(p);
-    dev = cur;
-  }
-  return ptr;
-}
+// The bounded mbarrier waits of the GEMM raise this flag instead of hanging.  It lives in host-mapped (zero-copy, portable)
+// memory so that every entry point of the library can test it WITHOUT synchronising: a pipeline timeout in an earlier call
+// turns into DGSCT_ERR_TIMEOUT on the next call (sticky, like a CUDA error) instead of DGSCT_OK with garbage.
+int* tc_err_flag_device_ptr() { return timeout_flag_device_ptr(); }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -203,7 +192,6 @@ int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B, int M,
   p.tmem_cols = cols;
   p.err_flag = tc_err_flag_device_ptr();
   p.debug_mode = 0;
-  p.early_release = getenv("DGSCT_EARLY_RELEASE") ? 1 : 0;
   int rc;
   if (A.mn_major) rc = encode(&p.mapA, A, batch, a_atom, p.BK, p.a_sw);
   else rc = encode(&p.mapA, A, batch, p.BK, BM, p.a_sw);

@@ -414,4 +414,67 @@ inline bool launch_out_ln_vec(const OutLnArgs& a, cudaStream_t st) {
   return dispatch_row_geometry(a.C / 8, OutLnLaunch{a, st});
 }
 
+// ---- sparse token resampler (AVS-S4 bicubic stencil, PVT_AVSModel.py:190-197) --------------------------------------------
+// out[b, r, :] = sum_j val[j] * in[b, col[j], :]  for the CSR row r (<= 16 taps): one thread per 16-byte vector of an output
+// row, fp32 coefficients and accumulation.  HBM-bound: reads <= 16 (L2-resident) input rows per output row, writes once.
+template <bool BF16>
+__global__ void __launch_bounds__(256) spmm_frames_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                          const float* __restrict__ val, const void* __restrict__ in,
+                                                          void* __restrict__ out, int rows_out, int rows_in, int Cc, int nvec) {
+  constexpr int VE = BF16 ? 8 : 4;               // elements per 16-byte vector
+  const int b = blockIdx.y;
+  const long long total = (long long)rows_out * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / nvec), v = (int)(i - (long long)r * nvec);
+    float acc[VE];
+#pragma unroll
+    for (int e = 0; e < VE; ++e) acc[e] = 0.f;
+    const int j0 = rowptr[r], j1 = rowptr[r + 1];
+    for (int j = j0; j < j1; ++j) {
+      const float w = val[j];
+      const size_t off = ((size_t)b * rows_in + col[j]) * Cc + (size_t)v * VE;
+      if (BF16) {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(in) + off);
+        const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&q[e]);
+          acc[2 * e] = fmaf(w, __bfloat162float(t.x), acc[2 * e]);
+          acc[2 * e + 1] = fmaf(w, __bfloat162float(t.y), acc[2 * e + 1]);
+        }
+      } else {
+        const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + off);
+        acc[0] = fmaf(w, u.x, acc[0]); acc[1] = fmaf(w, u.y, acc[1]); acc[2] = fmaf(w, u.z, acc[2]); acc[3] = fmaf(w, u.w, acc[3]);
+      }
+    }
+    const size_t o = ((size_t)b * rows_out + r) * Cc + (size_t)v * VE;
+    if (BF16) {
+      uint4 u;
+      __nv_bfloat162 t;
+      t = __floats2bfloat162_rn(acc[0], acc[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(acc[2], acc[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(acc[4], acc[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2bfloat162_rn(acc[6], acc[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + o) = u;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+  }
+}
+
+// Cc must be a multiple of 8 (bf16) / 4 (fp32): every width of the reference geometries is.  Returns false otherwise.
+inline bool launch_spmm_frames(const int32_t* rowptr, const int32_t* col, const float* val, const void* in, void* out, int is_bf16,
+                               int BT, int rows_out, int rows_in, int Cc, cudaStream_t st) {
+  const int ve = is_bf16 ? 8 : 4;
+  if (Cc % ve) return false;
+  const int nvec = Cc / ve;
+  const long long total = (long long)rows_out * nvec;
+  int gx = (int)((total + 255) / 256);
+  const int cap = (148 * 8 + BT - 1) / BT;        // ~8 CTAs per SM over the whole (gx, BT) grid
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  if (is_bf16) spmm_frames_kernel<true><<<dim3(gx, BT), 256, 0, st>>>(rowptr, col, val, in, out, rows_out, rows_in, Cc, nvec);
+  else spmm_frames_kernel<false><<<dim3(gx, BT), 256, 0, st>>>(rowptr, col, val, in, out, rows_out, rows_in, Cc, nvec);
+  return true;
+}
+
 }  // namespace dgsct

@@ -21,20 +21,41 @@ class GradBucket:
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             if p.dtype != torch.float32:
                 raise TypeError("gradient buckets hold fp32 master gradients")
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            p.grad = self.views[-1]
             off += p.numel()
         self.work: Optional[dist.Work] = None
+        self.launched = False
+
+    def reattach(self) -> None:
+        """Make every ``param.grad`` alias its bucket view again.  ``optimizer.zero_grad()`` defaults to
+        ``set_to_none=True`` (the reference loop calls it, main_trans.py:134), which drops the views: autograd would then
+        allocate fresh gradients and the bucket would reduce stale zeros.  A foreign gradient tensor found here (produced
+        after such a reset) is folded into the bucket before the view is restored."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                v.add_(g.detach().to(v.dtype).view_as(v))
+                p.grad = v
 
     def zero(self) -> None:
         self.flat.zero_()
+        self.launched = False
+        for p, v in zip(self.params, self.views):
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
 
     def all_reduce(self, group=None, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Launch the averaging all-reduce of this bucket (asynchronously).  On CUDA the collective runs on ``stream``
         after the work already queued on the current stream, so later kernels of the backward overlap it."""
+        self.launched = True
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
         if stream is not None and self.flat.is_cuda:
@@ -93,11 +114,24 @@ class GradBucketer:
         bi = self.owner[group_index]
         self._left[bi] -= 1
         if self._left[bi] == 0:
-            self.buckets[bi].all_reduce(self.group, self.comm_stream)
-            self._comm_used = self._comm_used or self.buckets[bi].work is not None
+            self._launch(bi)
+
+    def _launch(self, bi: int) -> None:
+        b = self.buckets[bi]
+        if b.launched:
+            raise RuntimeError(f"gradient bucket {bi} was already reduced in this step (a module ran its backward more often "
+                               "than announced; call zero_grad() once per step)")
+        b.reattach()
+        b.all_reduce(self.group, self.comm_stream)
+        self._comm_used = self._comm_used or b.work is not None
 
     def finish(self) -> None:
-        """Wait for every outstanding all-reduce and turn sums into means (call before optimizer.step())."""
+        """Reduce every bucket that has not been reduced yet (an adapter that was not used in this step, or a parameter
+        that received no gradient, never reports: its bucket would otherwise keep per-rank gradients), wait for every
+        outstanding all-reduce and turn sums into means (call before optimizer.step())."""
+        for bi, b in enumerate(self.buckets):
+            if not b.launched:
+                self._launch(bi)
         for b in self.buckets:
             b.wait(self.group)
         # join the communication stream only if a collective was launched on it this step: with one rank nothing was,
@@ -140,26 +174,45 @@ class AdapterDDP:
                 for m in self.modules:
                     for t in list(m.parameters()) + list(m.buffers()):
                         dist.broadcast(t.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                    if hasattr(m, "invalidate_packed"):
+                        m.invalidate_packed()        # .data writes do not bump _version (packed bf16 weight cache key)
         groups = [[p for p in m.parameters() if p.requires_grad] for m in order]
         self.bucketer = GradBucketer(groups, bucket_bytes=bucket_bytes, group=group)
         self._sync = True
         self._npar = [len(g) for g in groups]
         self._pending = list(self._npar)
         self._handles = []
+        self._engine = []
+        self._fwd_calls = [0] * len(order)       # engine adapters: forward calls of this step that will run a backward
+        self._bwd_calls = [0] * len(order)
         for j, (m, g) in enumerate(zip(order, groups)):
             engine = fused and hasattr(m, "_packed_weights")          # dgsct_b200.VisualAdapter
+            self._engine.append(engine)
             if engine:
+                # The engine's kernels add into the bucket views from inside _AdapterFn.backward, so "this module's
+                # gradients are complete" is signalled from the END of that function (module._ddp_done_cb).  A module
+                # full-backward hook is NOT usable: when no module input requires grad (layer-0 adapters fed by the frozen
+                # patch_embed, net_trans.py:877,891) PyTorch fires it before the backward function has run.
                 m.fused_grad_accumulation = True
-                self._handles.append(m.register_full_backward_hook(self._module_hook(j)))
+                m._ddp_done_cb = self._engine_done(j)
+                self._handles.append(m.register_forward_pre_hook(self._count_forward(j)))
             else:
                 for p in g:
                     self._handles.append(p.register_post_accumulate_grad_hook(self._param_hook(j)))
 
-    def _module_hook(self, j):
-        def hook(module, grad_input, grad_output):
-            if self._sync:
-                self.bucketer.group_done(j)
+    def _count_forward(self, j):
+        def hook(module, args):
+            if torch.is_grad_enabled():
+                self._fwd_calls[j] += 1
         return hook
+
+    def _engine_done(self, j):
+        def done():
+            self._bwd_calls[j] += 1
+            # a module called several times per step reports once, after the backward of its last call
+            if self._sync and self._bwd_calls[j] >= max(self._fwd_calls[j], 1):
+                self.bucketer.group_done(j)
+        return done
 
     def _param_hook(self, j):
         def hook(param):
@@ -173,6 +226,8 @@ class AdapterDDP:
     def zero_grad(self) -> None:
         self.bucketer.zero_grad()
         self._pending = list(self._npar)
+        self._fwd_calls = [0] * len(self._fwd_calls)
+        self._bwd_calls = [0] * len(self._bwd_calls)
 
     def no_sync(self):
         import contextlib
@@ -190,8 +245,13 @@ class AdapterDDP:
         """Wait for the outstanding all-reduces; ``param.grad`` then holds the mean over ranks."""
         self.bucketer.finish()
         self._pending = list(self._npar)
+        self._fwd_calls = [0] * len(self._fwd_calls)
+        self._bwd_calls = [0] * len(self._bwd_calls)
 
     def remove(self) -> None:
         for h in self._handles:
             h.remove()
         self._handles = []
+        for m in self.modules:
+            if hasattr(m, "_ddp_done_cb"):
+                m._ddp_done_cb = None

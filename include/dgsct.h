@@ -33,7 +33,9 @@ typedef enum dgsct_status {
   DGSCT_ERR_WORKSPACE = -3,     /* workspace too small or misaligned (256 B)                        */
   DGSCT_ERR_CUDA = -4,          /* a CUDA runtime/driver call failed (see dgsct_last_cuda_error)    */
   DGSCT_ERR_UNSUPPORTED = -5,   /* valid request the engine does not implement (yet)                */
-  DGSCT_ERR_ARCH = -6           /* device is not sm_100                                             */
+  DGSCT_ERR_ARCH = -6,          /* device is not sm_100 (checked on every compute entry point)      */
+  DGSCT_ERR_TIMEOUT = -7        /* a bounded tcgen05 pipeline wait expired in an EARLIER call: sticky until
+                                   dgsct_tc_error_flag(1); everything computed since is invalid      */
 } dgsct_status;
 
 typedef enum dgsct_dtype { DGSCT_F32 = 0, DGSCT_BF16 = 1 } dgsct_dtype;
@@ -87,6 +89,14 @@ typedef struct dgsct_params {
   float *bn1_rm, *bn1_rv, *bn2_rm, *bn2_rv;    /* running stats, updated in place when TRAIN     */
   const float *lnb_w, *lnb_b, *lnp_w, *lnp_b;  /* (C) each or NULL                               */
   const float *t_w, *t_b;                      /* (1,C), (1)  temporal_gated.0 or NULL           */
+  /* Optional SPARSE resampling matrix (CSR, fp32 values): the AVS-S4 bicubic interpolation is a 16-tap stencil
+   * (PVT_AVSModel.py:190-197), not a dense (N,No) matrix.  When rs_rowptr != NULL the engine computes
+   * U[b] = M . other[b] with one gather kernel (fp32 coefficients, no bf16 rounding of the stencil) and
+   * dother[b] = M^T . dU[b] from the transposed CSR; resample_w may then be NULL.  Build both with dgsct_bicubic_csr. */
+  const int32_t *rs_rowptr, *rs_col;           /* (N+1), (nnz)   CSR of M   (N x No)             */
+  const float *rs_val;                         /* (nnz)                                          */
+  const int32_t *rst_rowptr, *rst_col;         /* (No+1), (nnz)  CSR of M^T (No x N)             */
+  const float *rst_val;                        /* (nnz)                                          */
 } dgsct_params;
 
 /* fp32 gradient buffers, one per entry of dgsct_params (same shapes).  dgsct_adapter_bwd ADDS into them, so the
@@ -169,13 +179,20 @@ long long dgsct_launch_count(void);
 int dgsct_debug_gemm_bf16(const void *A, const void *B, float *D, int M, int N, int K, int batch, int a_mn_major,
                           int b_mn_major, long long lda, long long ldb, long long a_batch_stride,
                           long long b_batch_stride, int use_tc, int bn_hint, int stages_hint, void *stream);
-/* value of the device flag raised when a bounded pipeline wait expired (0 = healthy); synchronises */
+/* value of the sticky flag (host-mapped memory) raised when a bounded pipeline wait expired (0 = healthy); synchronises
+ * the current device first; reset != 0 clears it.  The compute entry points test the same flag WITHOUT synchronising and
+ * return DGSCT_ERR_TIMEOUT once it is set. */
 int dgsct_tc_error_flag(int reset);
 
 /* Host helper: dense (n_out^2, n_in^2) matrix of bicubic (A=-0.75, align_corners=False) interpolation
  * on a square token grid, written to HOST memory `w` (row-major).  Used for the AVS-S4 resampler
  * (PVT_AVSModel.py:190-197). */
 int dgsct_bicubic_matrix(int n_in_side, int n_out_side, float *w_host);
+/* Host helper: the same interpolation as CSR (transpose = 0: rows = n_out^2 outputs, <= 16 taps each; transpose = 1: rows =
+ * n_in^2 inputs).  rowptr_host has rows+1 entries; col_host / val_host hold up to dgsct_bicubic_csr_capacity() entries
+ * (taps that clamp onto the same border pixel are merged).  Returns the number of stored entries, or a negative status. */
+int dgsct_bicubic_csr_capacity(int n_in_side, int n_out_side);
+int dgsct_bicubic_csr(int n_in_side, int n_out_side, int transpose, int32_t *rowptr_host, int32_t *col_host, float *val_host);
 
 #ifdef __cplusplus
 }

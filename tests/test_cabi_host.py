@@ -38,7 +38,7 @@ def test_struct_layouts_match_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = []
     for decl in body.split(";"):
-        decl = decl.replace("const", "").replace("float", "").replace("typedef struct dgsct_params {", "")
+        decl = decl.replace("const", "").replace("float", "").replace("int32_t", "").replace("typedef struct dgsct_params {", "")
         names += [n.strip().lstrip("*") for n in decl.split(",") if n.strip()]
     assert names == L.PARAM_FIELDS
     body = hdr[hdr.index("typedef struct dgsct_taps {"):hdr.index("} dgsct_taps;")]
@@ -68,6 +68,28 @@ def test_workspace_bytes_and_validation(lib):
     # null pointers are reported, not dereferenced
     rc = lib.dgsct_adapter_fwd(C.byref(_desc()), None, None, None, None, None, None, None, None, None, 0, None)
     assert rc == -2 and lib.dgsct_status_string(rc) == b"null pointer"
+
+
+@pytest.mark.parametrize("n_in,n_out", [(6, 4), (4, 6), (8, 8), (16, 12), (64, 48)])
+def test_bicubic_csr_matches_torch_interpolate(lib, n_in, n_out):
+    """The 16-tap stencil (CSR) and its transpose equal the dense matrix of torch's F.interpolate(mode='bicubic')."""
+    ref = O.bicubic_matrix(n_in, n_out)
+    cap = lib.dgsct_bicubic_csr_capacity(n_in, n_out)
+    assert cap == 16 * n_out * n_out
+    for tr, rows, cols in ((0, n_out * n_out, n_in * n_in), (1, n_in * n_in, n_out * n_out)):
+        rp = torch.empty(rows + 1, dtype=torch.int32)
+        ci = torch.empty(cap, dtype=torch.int32)
+        va = torch.empty(cap, dtype=torch.float32)
+        nnz = lib.dgsct_bicubic_csr(n_in, n_out, tr, C.c_void_p(rp.data_ptr()), C.c_void_p(ci.data_ptr()), C.c_void_p(va.data_ptr()))
+        assert 0 < nnz <= cap and int(rp[0]) == 0 and int(rp[-1]) == nnz
+        dense = torch.zeros(rows, cols, dtype=torch.float64)
+        for r in range(rows):
+            for j in range(int(rp[r]), int(rp[r + 1])):
+                dense[r, int(ci[j])] += float(va[j])
+        assert float((dense - (ref.t() if tr else ref)).abs().max()) < 2e-6
+        if not tr:
+            assert int((rp[1:] - rp[:-1]).max()) <= 16
+    assert lib.dgsct_bicubic_csr(0, 4, 0, None, None, None) == -1
 
 
 @pytest.mark.parametrize("n_in,n_out", [(6, 4), (4, 6), (8, 8), (16, 12), (12, 48)])
