@@ -31,8 +31,35 @@ ADAPTER_CFG = dict(K=32, r=8, g=2, T=10, alpha=0.3, beta=0.05, gamma=0.0, resamp
                    ln_post=True, gate_before_ln=False, use_bn=True, use_gate=True, temporal=False)
 
 
-METRIC = {"train": "AVE clips/sec (B=8,T=10): adapter-stack train step (fwd+bwd+all-reduce+Adam over the 48 DG-SCT adapters)",
-          "fwd": "AVE clips/sec (B=8,T=10): adapter-stack forward (48 VisualAdapter.forward calls)"}
+# Workloads = BASELINE.json configs: "ave" is the metric's own (configs 1-3, Swin-V2-L/192 token shapes: the geometry the
+# reference really runs); "b224" is BASELINE.json's Swin-V2-B/224 wording; "s4" is config 4 (AVS-S4: bicubic
+# resampler, no ln_before, gate before ln_post, BN / gate off, B=4 clips x 5 frames, PVT_AVSModel.py:90-316, avs_s4/train.sh);
+# "avqa_t60" is config 5 (AVQA copy: K=2 latent tokens, g=4, BN / gate off, net_avst.py:27-218, T=60 frames per clip).
+VIS_B224 = [(128, 3136), (256, 784), (512, 196), (1024, 49)]
+WORKLOADS = {
+    "ave": dict(variant="ave", vis=VIS, B=8, T=10, cfg=ADAPTER_CFG, what="AVE", module_kw=dict(use_bn=True, use_gate=True, num_tk=32),
+                opt=dict(num_conv_group=2)),
+    "b224": dict(variant="ave", vis=VIS_B224, B=8, T=10, cfg=ADAPTER_CFG, what="AVE, Swin-V2-B/224 token shapes",
+                 module_kw=dict(use_bn=True, use_gate=True, num_tk=32), opt=dict(num_conv_group=2)),
+    "s4": dict(variant="s4", vis=VIS, B=4, T=5, what="AVS-S4",
+               cfg=dict(ADAPTER_CFG, T=5, resampler="bicubic", ln_before=False, gate_before_ln=True, use_bn=False, use_gate=False),
+               module_kw=dict(use_bn=False, use_gate=False), opt=dict(num_conv_group=2, num_tokens=32)),
+    "avqa_t60": dict(variant="avqa", vis=VIS, B=8, T=60, what="AVQA long-temporal",
+                     cfg=dict(ADAPTER_CFG, T=60, K=2, g=4, use_bn=False, use_gate=False),
+                     module_kw=dict(use_bn=False, use_gate=False), opt=dict(num_conv_group=4, num_tokens=2)),
+}
+_WL = {"name": "ave"}
+
+
+def wl():
+    return WORKLOADS[_WL["name"]]
+
+
+def metric_name(args):
+    w = wl()
+    what = ("adapter-stack train step (fwd+bwd+all-reduce+Adam over the 48 DG-SCT adapters)" if args.mode == "train"
+            else "adapter-stack forward (48 VisualAdapter.forward calls)")
+    return f"{w['what']} clips/sec (B={args.B},T={args.T}): {what}"
 
 
 def layer_list():
@@ -45,7 +72,8 @@ def layer_list():
 
 
 def dims(kind, s):
-    (C, N), (Co, No) = (VIS[s], AUD[s]) if kind == "vis" else (AUD[s], VIS[s])
+    vis = wl()["vis"]
+    (C, N), (Co, No) = (vis[s], AUD[s]) if kind == "vis" else (AUD[s], vis[s])
     return C, N, Co, No
 
 
@@ -77,8 +105,10 @@ def init_param(shape, fan_in, gen, kind):
     return (torch.rand(shape, generator=gen) * 2 - 1) * b
 
 
-def make_params(C, N, Co, No, gen, K=32, r=8, g=2):
+def make_params(C, N, Co, No, gen, K=None, r=8, g=None):
     """Reference initialisers with gates / BN buffers randomised (SURVEY.md §8d 'Synthetic inputs')."""
+    K = wl()["cfg"]["K"] if K is None else K
+    g = wl()["cfg"]["g"] if g is None else g
     H, Cd = C // 2, C // r
     spec = {
         "conv_adapter.weight": ((N, No, 1, 1), No, "w"), "conv_adapter.bias": ((N,), No, "w"),
@@ -103,7 +133,7 @@ def make_params(C, N, Co, No, gen, K=32, r=8, g=2):
 
 def make_tokens(B, T, gen, dtype):
     BT = B * T
-    vis = [torch.randn(BT, N, C, generator=gen).to(dtype) for (C, N) in VIS]
+    vis = [torch.randn(BT, N, C, generator=gen).to(dtype) for (C, N) in wl()["vis"]]
     aud = [torch.randn(BT, N, C, generator=gen).to(dtype) for (C, N) in AUD]
     return vis, aud
 
@@ -148,19 +178,32 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def make_cpu_step(args):
-    """One CPU step of the same workload on ONE clip (B=1): the oracle restatement of the reference path; in train mode
-    forward + backward (torch autograd of the oracle) + Adam, with train-mode BatchNorm."""
+def oracle_cfg(O, C, N, Co, No):
+    """Oracle AdapterConfig of the current workload (variant presets + the workload's overrides)."""
+    c = wl()["cfg"]
+    return O.make_config(wl()["variant"], C, N, Co, No, K=c["K"], r=c["r"], g=c["g"], T=c["T"], use_bn=c["use_bn"], use_gate=c["use_gate"])
+
+
+def make_cpu_step(args, B, device="cpu", autocast=False):
+    """One step of the same workload on B clips with the ORACLE (the restatement of the reference path pinned to the
+    reference's own classes by tests/golden): in train mode forward + backward (torch autograd of the oracle) + Adam, with
+    train-mode BatchNorm.  device='cpu' is the reference arm / cpu_baseline; device='cuda' (+ bf16 autocast) is the
+    PyTorch-eager-on-B200 comparator.  Baselines only: the engine path never calls this."""
     from oracle import dgsct_oracle as O
     gen = torch.Generator().manual_seed(43)
-    vis, aud = make_tokens(1, args.T, gen, torch.float32)
+    vis, aud = make_tokens(B, args.T, gen, torch.float32)
+    vis = [t.to(device) for t in vis]
+    aud = [t.to(device) for t in aud]
     stack = []
     for kind, li, pos, s in layer_list():
         C, N, Co, No = dims(kind, s)
-        stack.append((kind, s, O.make_config("ave", C, N, Co, No), make_params(C, N, Co, No, gen)))
+        cfg = oracle_cfg(O, C, N, Co, No)
+        names = set(O.param_shapes(cfg))
+        stack.append((kind, s, cfg, {k: v.to(device) for k, v in make_params(C, N, Co, No, gen).items() if k in names}))
+    ac = (lambda: torch.autocast(device, dtype=torch.bfloat16)) if autocast else (lambda: torch.autocast(device, enabled=False))
     if args.mode != "train":
         def step():
-            with torch.no_grad():
+            with torch.no_grad(), ac():
                 for kind, s, cfg, p in stack:
                     x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
                     O.adapter_forward(cfg, p, x, o, training=False)
@@ -172,30 +215,37 @@ def make_cpu_step(args):
                 v.requires_grad_(True)
                 leaves.append(v)
     opt = torch.optim.Adam(leaves, lr=1e-5)
-    d_vis = [torch.randn(t.shape, generator=gen) * 1e-2 for t in vis]
-    d_aud = [torch.randn(t.shape, generator=gen) * 1e-2 for t in aud]
+    d_vis = [(torch.randn(t.shape, generator=gen) * 1e-2).to(device) for t in vis]
+    d_aud = [(torch.randn(t.shape, generator=gen) * 1e-2).to(device) for t in aud]
 
     def step():
         opt.zero_grad(set_to_none=True)
         for kind, s, cfg, p in stack:
             x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
-            out, smap, _, stats = O.adapter_forward(cfg, p, x, o, training=True)
-            ((out * (d_vis[s] if kind == "vis" else d_aud[s])).sum() + smap.sum()).backward()
+            with ac():
+                out, smap, _, stats = O.adapter_forward(cfg, p, x, o, training=True)
+            ((out.float() * (d_vis[s] if kind == "vis" else d_aud[s])).sum() + smap.float().sum()).backward()
             for k, v in stats.items():
                 p[k] = v
         opt.step()
     return step
 
 
+REF_CLIPS = {"ave": None, "b224": None, "s4": None, "avqa_t60": 1}      # None: the engine's own B (same config)
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path (the oracle restatement pinned to the reference's
-    classes by tests/golden), all host threads, one clip (B=1, T=10 -> BT=10) per step."""
+    """The reference's own CPU implementation of the path (the oracle restatement pinned to the reference's classes by
+    tests/golden), all host threads, on the engine arm's config: B clips x T frames per step (the AVQA T=60 workload is
+    bounded to 1 clip = 60 frames per step and says so)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = 1
-    step = make_cpu_step(args)
+    Bs = REF_CLIPS[_WL["name"]] or args.B
+    if args.ref_clips:
+        Bs = args.ref_clips
+    step = make_cpu_step(args, Bs)
 
     for _ in range(args.warmup):
         step()
@@ -204,24 +254,27 @@ def run_reference(args, rank, world):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = Bs / dt
-    line = {"metric": METRIC[args.mode], "value": v, "unit": "clips/s",
+    sample = (f"B={Bs} clips (BT={Bs * args.T}) per step" + ("" if Bs == args.B else f" -- bounded sample of the B={args.B} config")
+              + f", 48 adapters, fp32, {args.mode}, torch CPU ({cores} threads)")
+    line = {"metric": metric_name(args), "value": v, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
             "config": workload_config(args, "cpu"),
-            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port",
-                             "sample": f"B={Bs} clip (BT={Bs * args.T}) per step, 48 adapters, fp32, {args.mode}, torch CPU ({cores} threads)"},
+            "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "clips_per_step": Bs, "sample": sample},
             "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, where, launch=None):
-    what = ("train step (forward + backward + grad all-reduce + fused Adam), train-mode BatchNorm" if args.mode == "train"
-            else "forward, eval-mode BN")
-    return {"workload": f"AVE adapter stack {what}: 48 VisualAdapter calls, Swin-V2-L/192 + HTS-AT/256 token shapes, "
-                        f"B={args.B} clips x T={args.T} frames per GPU, K=32 r=8 g=2",
-            "B_per_gpu": args.B, "T": args.T, "adapters": 48, "adapter_params": 188.5e6, "mode": args.mode,
-            "l2": "per-step working set (377 MB packed bf16 weights + 250 MB tokens + intermediates) exceeds the 126 MB L2; no explicit flush",
+    what = ("train step (forward + backward + grad all-reduce + fused Adam)" + (", train-mode BatchNorm" if wl()["cfg"]["use_bn"] else "")
+            if args.mode == "train" else "forward, eval mode")
+    c = wl()["cfg"]
+    geom = "Swin-V2-B/224" if _WL["name"] == "b224" else "Swin-V2-L/192"
+    return {"workload": f"{_WL['name']}: {wl()['what']} adapter stack {what}: 48 VisualAdapter calls, {geom} + HTS-AT/256 token shapes, "
+                        f"B={args.B} clips x T={args.T} frames per GPU, K={c['K']} r={c['r']} g={c['g']}, resampler={c['resampler']}",
+            "B_per_gpu": args.B, "T": args.T, "adapters": 48, "mode": args.mode,
+            "l2": "per-step working set (packed bf16 weights + tokens + intermediates, > 600 MB) exceeds the 126 MB L2; no explicit flush",
             "launch": launch or "host loop",
             "device": where}
 
@@ -235,6 +288,10 @@ def run_engine(args, rank, world, local_rank):
     assert torch.cuda.is_available(), "the engine arm needs a B200; there is no CPU fallback"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    CFG = wl()["cfg"]
+    # CPU baseline first, on rank 0, BEFORE the process group exists: the other ranks then wait inside the rendezvous
+    # (blocking socket reads) instead of spinning in an NCCL barrier on the same host cores (round 1: 0.012 clips/s at N=8).
+    cpu_base = cpu_baseline(args) if (rank == 0 and not args.no_cpu_baseline) else None
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -250,16 +307,16 @@ def run_engine(args, rank, world, local_rank):
     pgen = torch.Generator().manual_seed(1234)          # identical (replicated) parameters on every rank
     stack = []
     import types
-    opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=2, is_before_layernorm=1, is_post_layernorm=1)
+    opt = types.SimpleNamespace(is_multimodal=1, is_before_layernorm=1, is_post_layernorm=1, **wl()["opt"])
     modules = []
     for kind, li, pos, s in layer_list():
         C, N, Co, No = dims(kind, s)
         p = {k: v.to(dev) for k, v in make_params(C, N, Co, No, pgen).items()}
         x0, o0 = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
-        pk = adapter_forward_raw(ADAPTER_CFG, p, x0, o0, pack_only=True) if dtype == torch.bfloat16 else None
+        pk = adapter_forward_raw(CFG, p, x0, o0, pack_only=True) if dtype == torch.bfloat16 else None
         stack.append((kind, s, p, pk))
-        m = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, use_bn=True, use_gate=True, num_tk=32,
-                                     conv_dim_in=No, conv_dim_out=N, linear_in=Co, linear_out=C)
+        m = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, conv_dim_in=No, conv_dim_out=N,
+                                     linear_in=Co, linear_out=C, variant=wl()["variant"], **wl()["module_kw"])
         m.load_state_dict(p, strict=False)
         modules.append(m.to(dev).eval())
     BT = args.B * args.T
@@ -277,7 +334,7 @@ def run_engine(args, rank, world, local_rank):
             for (kind, s, p, pk), strm in ((stack[i], s_aud), (stack[i + 1], s_vis)):
                 x, o = (vis[s], aud[s]) if kind == "vis" else (aud[s], vis[s])
                 with torch.cuda.stream(strm):
-                    adapter_forward_raw(ADAPTER_CFG, p, x, o, training=False, packed=pk)
+                    adapter_forward_raw(CFG, p, x, o, training=False, packed=pk)
             cur.wait_stream(s_aud)
             cur.wait_stream(s_vis)
 
@@ -374,28 +431,37 @@ def run_engine(args, rank, world, local_rank):
         if not args.no_graph:
             g_api, res_static = capture(api_forward, "api fwd")
 
-            def step_e2e():
-                h2d_copy()
+            def step_e2e(skip_h2d=False):
+                if not skip_h2d:
+                    h2d_copy()
                 g_api.replay()
                 d2h_buf[:res_static.numel()].copy_(res_static, non_blocking=True)
                 return res_static.numel() * 4
         else:
-            def step_e2e():
-                h2d_copy()
+            def step_e2e(skip_h2d=False):
+                if not skip_h2d:
+                    h2d_copy()
                 res = api_forward()
                 d2h_buf[:res.numel()].copy_(res, non_blocking=True)
                 return res.numel() * 4
     else:
-        from dgsct_b200.ddp import GradBucketer
+        from dgsct_b200.ddp import FlatAdam, GradBucketer
         fwd_ms = timed(run_step, max(3, args.steps // 2), 3)            # forward-only reference point (same stack)
         for m in modules:
             m.train()
-            if hasattr(m, "gate_tk"):
-                m.gate_tk.requires_grad_(False)                        # declared, never used (net_trans.py:487)
+            for n_, p_ in m.named_parameters():                        # declared, never used: gate_tk (net_trans.py:487), the dead
+                if n_ == "gate_tk" or n_.startswith(("fc_caption", "temporal_gated")) or \
+                        (CFG["resampler"] == "bicubic" and n_.startswith("conv_adapter")):     # caption / temporal heads, S4's conv_adapter
+                    p_.requires_grad_(False)
         groups = [[p for p in m.parameters() if p.requires_grad] for m in reversed(modules)]   # backward completion order
-        bucketer = GradBucketer(groups, bucket_bytes=32 << 20)
-        opt_adam = torch.optim.Adam([p for m in modules for p in m.parameters() if p.requires_grad], lr=1e-5, fused=True,
-                                    capturable=not args.no_graph)
+        comm_dtype = torch.bfloat16 if (args.comm_dtype == "bf16" and world > 1) else torch.float32
+        if args.torch_adam:     # round-1 configuration: torch's fused multi-tensor Adam over ~1400 parameter tensors
+            bucketer = GradBucketer(groups, bucket_bytes=32 << 20, comm_dtype=comm_dtype)
+            opt_adam = torch.optim.Adam([p for m in modules for p in m.parameters() if p.requires_grad], lr=1e-5, fused=True,
+                                        capturable=not args.no_graph)
+        else:                   # the engine's Adam: one kernel per flat bucket, reads the (bf16) reduced gradient in place
+            bucketer = GradBucketer(groups, bucket_bytes=32 << 20, flatten_params=True, comm_dtype=comm_dtype)
+            opt_adam = FlatAdam(bucketer, lr=1e-5, modules=modules)
         for t in vis_in + aud_in:
             t.requires_grad_(True)
         h2d_copy_nograd = h2d_copy
@@ -498,8 +564,9 @@ def run_engine(args, rank, world, local_rank):
         if res_static is None:
             train_streams[0] = 1                                      # eager: autograd stream syncs cost more than they hide
 
-        def step_e2e():      # noqa: F811  (host tokens in, fwd+bwd+all-reduce+Adam, two gradient checksums out)
-            h2d_copy()
+        def step_e2e(skip_h2d=False):      # noqa: F811  (host tokens in, fwd+bwd+all-reduce+Adam, two gradient checksums out)
+            if not skip_h2d:
+                h2d_copy()
             res = res_static
             if res_static is not None:
                 run_step()
@@ -524,25 +591,56 @@ def run_engine(args, rank, world, local_rank):
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "clips_per_s": world * args.B / (ms_step * 1e-3)}), flush=True)
         return
-    d2h = step_e2e()
-    ms_e2e = timed(step_e2e, max(3, args.steps // 2), 3)
+    # ---- end to end through the public API: host tokens in (pinned -> device, every step), result out.  The copy of step
+    # i+1's inputs is issued on a copy stream while step i computes (what a data loader with prefetch does): H2D lands in a
+    # staging set, and the step starts with a device-to-device copy into the graph's static inputs.
+    copy_stream = torch.cuda.Stream(dev)
+    stage_in = [torch.empty_like(t) for t in vis_in + aud_in]
+    static_in = vis_in + aud_in
+    host_in = vis_h + aud_h
+    prefetched = [False]
 
-    # per-stage device time (CUDA events inside the library, on the launching stream) for the roofline
+    def prefetch():
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))     # staging is free once the previous D2D copy was queued
+        with torch.cuda.stream(copy_stream), torch.no_grad():
+            for d_, h_ in zip(stage_in, host_in):
+                d_.copy_(h_, non_blocking=True)
+        prefetched[0] = True
+
+    def step_e2e_prefetch():
+        if not prefetched[0]:
+            prefetch()
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+        with torch.no_grad():
+            for d_, s_ in zip(static_in, stage_in):
+                d_.copy_(s_, non_blocking=True)
+        prefetch()                                                   # next step's inputs travel under this step's compute
+        return step_e2e(skip_h2d=True)
+
+    d2h = step_e2e()
+    ms_e2e_serial = timed(step_e2e, max(3, args.steps // 2), 3)
+    ms_e2e = timed(step_e2e_prefetch, max(3, args.steps // 2), 3)
+
+    # ---- per-stage device time (CUDA events inside the library, on the launching stream; one stream, side stream off)
     roof = None
-    cpu_base = None
     stage_ms = None
+    eager_gpu = None
     if rank == 0:
         def step_sequential():                # one stream, so per-stage event times do not overlap
             for kind, s_, p_, pk_ in stack:
                 x_, o_ = (vis[s_], aud[s_]) if kind == "vis" else (aud[s_], vis[s_])
-                adapter_forward_raw(ADAPTER_CFG, p_, x_, o_, training=False, packed=pk_)
+                adapter_forward_raw(CFG, p_, x_, o_, training=False, packed=pk_)
 
-        step_sequential()
+        prof_fn = step_sequential
+        if args.mode == "train":
+            train_streams[0] = 1
+            prof_fn = step_train
+        prof_fn()
         torch.cuda.synchronize(dev)
         L.profile_enable(True)
-        psteps = 3
+        psteps = 2
         for _ in range(psteps):
-            step_sequential()
+            prof_fn()
         torch.cuda.synchronize(dev)
         prof = L.profile_collect()
         L.profile_enable(False)
@@ -554,42 +652,64 @@ def run_engine(args, rank, world, local_rank):
             pass
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured" if peaks else "fallback"
-        # dominant kernel: the token-resampler contraction (conv_adapter as a GEMM), 48 launches per step
-        flops_conv = sum(2 * BT * dims(k, s)[1] * dims(k, s)[3] * dims(k, s)[2] for k, _, _, s in layer_list())
-        t_conv = prof.get("resample_conv", (0.0, 0))[0] / psteps * 1e-3
-        ach = flops_conv / t_conv / 1e12 if t_conv > 0 else 0.0
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the largest of the 48 launches (stage-0 audio resampler,
-        # 290 GFLOP; algorithmic 215.5 MB = 18.9 MB weights + 70.8 MB tokens + 125.8 MB output) from the committed
-        # `ncu --set full` export profiles/r01_ncu_full_gemm_aud_s0_raw.csv (89.85 MB read + 84.13 MB written before the
-        # kernel ended; the rest of the output was still in L2)
-        roof = {"kernel": "resample_conv (token resampler GEMM, 48 launches/step)", "bound": "tensor", "achieved": ach,
-                "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": 173.97e6,
-                "traffic_launch": "stage-0 audio resampler launch (M=4096 N=192 K=2304 x 80 frames), ncu --set full", "peak_source": peak_src,
-                "share_of_step": (t_conv * 1e3) / max(sum(v[0] for v in prof.values()) / psteps, 1e-9)}
-        tot_bytes = sum(alg_bytes(*dims(k, s), BT) for k, _, _, s in layer_list())
-        tot_flops = sum(alg_flops(*dims(k, s), BT) for k, _, _, s in layer_list())
+        peak_src = "measured (MEASURED_PEAKS.json: sustained bf16, copy bandwidth)" if peaks else "fallback"
+        work = stage_work(BT, CFG)
+        prof_total = max(sum(v[0] for v in prof.values()) / psteps, 1e-9)
+        entries = {}
+        for st_name, (amount, bound, what) in work.items():
+            t_ms = prof.get(st_name, (0.0, 0))[0] / psteps
+            if t_ms <= 0:
+                continue
+            peak = tf_peak if bound == "tensor" else hbm_peak
+            ach = amount / (t_ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+            entries[st_name] = {"kernel": what, "bound": bound, "achieved": ach, "peak": peak,
+                                "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": ach / peak, "ms_per_step": t_ms,
+                                "launches_per_step": prof[st_name][1] // psteps, "share_of_step": t_ms / prof_total}
+        # the dominant kernel of THIS timed step = the modelled stage with the largest device time
+        dom = max(entries, key=lambda k: entries[k]["ms_per_step"]) if entries else None
+        roof = dict(entries[dom]) if dom else {"kernel": None, "bound": "tensor", "achieved": 0.0, "peak": tf_peak, "unit": "TFLOP/s", "frac": 0.0}
+        roof["stage"] = dom
+        roof["peak_source"] = peak_src
+        tr = load_traffic(dom)
+        roof["traffic"] = tr["bytes"] if tr else None     # dram bytes per launch from a committed `ncu --set full` capture, else null
+        if tr:
+            roof["traffic_source"] = tr["source"]
+        roof["stages"] = entries
+        tot_bytes = sum(alg_bytes(*dims(k, s), BT, K=CFG["K"], r=CFG["r"], g=CFG["g"]) for k, _, _, s in layer_list())
+        tot_flops = sum(alg_flops(*dims(k, s), BT, K=CFG["K"], r=CFG["r"], g=CFG["g"]) for k, _, _, s in layer_list())
         t_fwd = (fwd_ms if fwd_ms is not None else ms_step) * 1e-3      # adapter-forward time (the metric's second half)
         roof["stack"] = {"what": "whole adapter-forward stack (48 calls), algorithmic bytes / flops of SURVEY.md 8(d)",
                          "algorithmic_GB": tot_bytes / 1e9, "algorithmic_TFLOP": tot_flops / 1e12, "fwd_ms": t_fwd * 1e3,
                          "hbm_GBps": tot_bytes / t_fwd / 1e9, "hbm_frac": tot_bytes / t_fwd / 1e9 / hbm_peak,
                          "tensor_TFLOPs": tot_flops / t_fwd / 1e12, "tensor_frac": tot_flops / t_fwd / 1e12 / tf_peak}
-        cpu_base = cpu_baseline(args)
+        if args.mode == "train":     # whole train step: forward + activation gradients + weight gradients ~ 3x forward flops
+            roof["step"] = {"what": "whole train step, 3 x the forward's algorithmic flops", "algorithmic_TFLOP": 3 * tot_flops / 1e12,
+                            "ms": ms_step, "tensor_TFLOPs": 3 * tot_flops / (ms_step * 1e-3) / 1e12,
+                            "tensor_frac": 3 * tot_flops / (ms_step * 1e-3) / 1e12 / tf_peak}
+        if world == 1 and not args.no_eager:
+            eager_gpu = eager_gpu_comparator(args)
 
     if rank == 0:
         value = world * args.B / (ms_step * 1e-3)
-        line = {"metric": METRIC[args.mode], "value": value,
+        line = {"metric": metric_name(args), "value": value,
                 "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "impl": "engine", "config": workload_config(args, torch.cuda.get_device_name(dev), launch_mode),
                 "e2e": {"value": world * args.B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
-                "stage_ms_per_step": stage_ms}
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                        "how": "public nn.Module API; every step copies its pinned host tokens to the device (prefetched on a copy "
+                               "stream under the previous step's compute, then one device-to-device copy) and reads the result back",
+                        "serial_copy": {"value": world * args.B / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial,
+                                        "how": "same, with the H2D copy serialised in front of the step"}},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+                "cpu_baseline": cpu_base if cpu_base is not None else {"value": None, "unit": "clips/s", "note": "skipped (--no-cpu-baseline)"},
+                "gpu_eager_baseline": eager_gpu, "stage_ms_per_step": stage_ms}
         if fwd_ms is not None:
             line["forward_only"] = {"ms_per_step": fwd_ms, "clips_per_s": world * args.B / (fwd_ms * 1e-3)}
-            line["collective"] = {"op": "all-reduce (mean) of adapter gradients, fp32, bucketed 32 MB, NCCL" if world > 1 else "none (1 GPU)",
+            line["collective"] = {"op": f"all-reduce (mean) of adapter gradients, {args.comm_dtype if world > 1 else 'fp32'} on the wire, "
+                                        "fp32 master buckets of 32 MB, NCCL" if world > 1 else "none (1 GPU)",
                                   "bytes_per_step": bucketer.total_bytes() if world > 1 else 0}
+            line["optimizer"] = "torch.optim.Adam(fused=True)" if args.torch_adam else "dgsct FlatAdam (one fused kernel per flat bucket)"
         print(json.dumps(line), flush=True)
     if dist is not None:
         # Captured graphs hold NCCL kernels: tearing the communicator down underneath them can block (seen at N=2: the
@@ -603,10 +723,11 @@ def run_engine(args, rank, world, local_rank):
 
 
 def cpu_baseline(args):
-    """Oracle on the host cores, bounded sample: one clip (BT=T) through the 48 adapters (same mode), best of 3."""
+    """Oracle on the host cores, bounded sample: ONE clip (BT=T) through the 48 adapters (same mode), best of 2-3 -- the same
+    code the reference arm (--impl reference) times at the full B clips per step."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = make_cpu_step(args)
+    step = make_cpu_step(args, 1)
     best = 1e30
     for it in range(4 if args.mode != "train" else 3):
         t0 = time.perf_counter()
@@ -614,8 +735,73 @@ def cpu_baseline(args):
         dt = time.perf_counter() - t0
         if it:
             best = min(best, dt)
-    return {"value": 1.0 / best, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"1 clip (BT={args.T}) through the 48 adapters, fp32, {args.mode}, torch CPU {cores} threads, best of {3 if args.mode != 'train' else 2}"}
+    return {"value": 1.0 / best, "unit": "clips/s", "cores": cores, "kind": "port", "clips_per_step": 1,
+            "sample": f"1 clip (BT={args.T}) through the 48 adapters, fp32, {args.mode}, torch CPU {cores} threads, best of "
+                      f"{3 if args.mode != 'train' else 2}; measured on rank 0 before the process group is created"}
+
+
+def eager_gpu_comparator(args):
+    """PyTorch eager on the same B200 ('the bar a hand-written kernel must beat'): the oracle's torch ops on
+    cuda:0 under bf16 autocast, same workload, B clips per step.  A baseline leg like cpu_baseline (the oracle is never on
+    the engine path); bounded to a few steps."""
+    try:
+        step = make_cpu_step(args, args.B, device="cuda", autocast=True)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 3
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        return {"value": args.B / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms, "kind": "pytorch-eager (oracle ops on cuda:0, bf16 autocast, "
+                f"torch.optim.Adam), {args.mode}, B={args.B}", "steps": n}
+    except Exception as e:       # informative only
+        return {"value": None, "error": f"{type(e).__name__}: {str(e).splitlines()[0][:200]}"}
+
+
+def stage_work(BT, cfg):
+    """Algorithmic work per step of the library stages with a clean model: {stage: (flops or bytes, bound, description)}.
+    Tensor-bound stages count EXECUTED flops (the re-associated resampler contracts over min(C, C') columns); HBM-bound row
+    kernels count the bytes they must move (bf16 activations, fp32 up-sampler output)."""
+    conv = dw = dwres = 0
+    gate_ln = out_ln = bwd_out = bwd_gate_ln = 0
+    K, r = cfg["K"], cfg["r"]
+    sparse = cfg["resampler"] == "bicubic"
+    for kind, _, _, s in layer_list():
+        C, N, Co, No = dims(kind, s)
+        Cd, H = C // r, C // 2
+        cc = min(C, Co) if not sparse else Co
+        conv += (2 * BT * N * No * cc) if not sparse else 0
+        dwres += (2 * BT * N * No * cc) if not sparse else 0
+        dw += 2 * BT * N * (2 * C * Cd + H * C + C * C + K * C) + 2 * BT * (No if (C < Co and not sparse) else N) * C * Co
+        gate_ln += BT * N * C * 4
+        out_ln += BT * N * C * 6
+        bwd_out += BT * N * C * 8
+        bwd_gate_ln += BT * N * C * 6
+    w = {"gate_ln": (gate_ln, "hbm", "gate combine + ln_before row kernel (read X', write Y)"),
+         "out_ln": (out_ln, "hbm", "bn2 + ln_post + gate row kernel (read fp32 up-sampler output, write out)"),
+         "bwd_out": (bwd_out, "hbm", "backward of gate / ln_post / bn2 sums (read d_out + Uo, write dUo)"),
+         "bwd_gate_ln": (bwd_gate_ln, "hbm", "backward of ln_before + gate combine (read dY + X', write dX')"),
+         "bwd_dw": (dw, "tensor", "weight-gradient products sum_b A_b^T B_b of the small matrices (tcgen05 GEMM, split over frames)")}
+    if not sparse:
+        w["resample_conv"] = (conv, "tensor", "token-resampler contraction (tcgen05 GEMM, 48 launches/step)")
+        w["bwd_dother"] = (conv, "tensor", "d other = W_res^T . dU (tcgen05 GEMM)")
+        w["bwd_dwres"] = (dwres, "tensor", "d W_res = sum_b dU_b . other_b^T (tcgen05 GEMM, K extended over frames)")
+    return w
+
+
+def load_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel from the committed `ncu --set full`
+    capture (profiles/r02_traffic.json: {stage: {"bytes": ..., "source": ...}}); None when no capture covers the stage."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return t.get(stage)
+    except Exception:
+        return None
 
 
 def main():
@@ -624,15 +810,28 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--B", type=int, default=8)
-    ap.add_argument("--T", type=int, default=10)
+    ap.add_argument("--B", type=int, default=0, help="clips per GPU (default: the workload's)")
+    ap.add_argument("--T", type=int, default=0, help="frames per clip (default: the workload's)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--mode", default="train", choices=["fwd", "train"],
                     help="train: fwd + bwd + gradient all-reduce + Adam over the 48 adapters (BASELINE config 2/3); fwd: forward only")
     ap.add_argument("--no-graph", action="store_true", help="time the eager Python loop instead of CUDA-graph replay")
+    ap.add_argument("--workload", default="ave", choices=sorted(WORKLOADS),
+                    help="ave: BASELINE.json configs 1-3 (default, the metric's own); b224: Swin-V2-B/224 token shapes; "
+                         "s4: config 4 (AVS-S4, B=4 x 5 frames); avqa_t60: config 5 (AVQA, T=60)")
+    ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "f32"], help="dtype of the gradient all-reduce (N > 1)")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam(fused=True) instead of the engine's flat-bucket Adam")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-on-GPU comparator (rank 0, N=1)")
+    ap.add_argument("--ref-clips", type=int, default=0, help="reference arm: clips per step (default: the engine's B)")
     ap.add_argument("--recompute", action="store_true",
                     help="train: keep no activations, the backward recomputes the forward (default: saved activations)")
     args = ap.parse_args()
+    _WL["name"] = args.workload
+    args.B = args.B or wl()["B"]
+    args.T = args.T or wl()["T"]
+    if args.T != wl()["cfg"]["T"]:
+        wl()["cfg"] = dict(wl()["cfg"], T=args.T)
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

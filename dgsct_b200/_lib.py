@@ -53,7 +53,8 @@ EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgs
            "dgsct_bwd_saved_workspace_bytes", "dgsct_adapter_bwd_saved",
            "dgsct_adapter_fwd", "dgsct_bicubic_matrix", "dgsct_num_stages", "dgsct_stage_name",
            "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
-           "dgsct_tc_error_flag", "dgsct_bicubic_csr_capacity", "dgsct_bicubic_csr"]
+           "dgsct_tc_error_flag", "dgsct_bicubic_csr_capacity", "dgsct_bicubic_csr",
+           "dgsct_adam_tick", "dgsct_adam_flat", "dgsct_cast_bucket_bf16"]
 
 _lib = None
 
@@ -106,6 +107,12 @@ def lib() -> C.CDLL:
     L.dgsct_bicubic_csr_capacity.argtypes = [C.c_int, C.c_int]
     L.dgsct_bicubic_csr.restype = C.c_int
     L.dgsct_bicubic_csr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dgsct_adam_tick.restype = C.c_int
+    L.dgsct_adam_tick.argtypes = [C.c_void_p, C.c_void_p]
+    L.dgsct_adam_flat.restype = C.c_int
+    L.dgsct_adam_flat.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_float] * 6 + [C.c_void_p, C.c_void_p]
+    L.dgsct_cast_bucket_bf16.restype = C.c_int
+    L.dgsct_cast_bucket_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]
     L.dgsct_num_stages.restype = C.c_int
     L.dgsct_stage_name.restype = C.c_char_p
     L.dgsct_stage_name.argtypes = [C.c_int]

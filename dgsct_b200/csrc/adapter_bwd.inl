@@ -47,7 +47,10 @@ struct EpiOut {
 
 namespace tc {
 // tensor-core twin (row-major output only; transposed outputs use EpiOutT)
-template <bool OUT_BF16, int MODE, bool RESID, bool BCAST, bool CSCALE>
+// GCOLSUM: gcolsum[n] += sum over all rows (every frame) of the fp32 value this product contributes, BEFORE it is rounded to
+// the output dtype -- bias gradients of a bf16 tensor summed over ~10^4 rows lose small coherent terms (the dobar / N
+// broadcast in dV) when they are re-read from the rounded tensor (fc.bias sat at 0.6-0.8 rel-L2 in round 1).
+template <bool OUT_BF16, int MODE, bool RESID, bool BCAST, bool CSCALE, bool GCOLSUM = false>
 struct EpiOut {
   // staged (row-contiguous) I/O only for pure stores: staging a residual / accumulate LOAD measured slower than the direct
   // per-row access (see EpiResidual)
@@ -56,8 +59,19 @@ struct EpiOut {
   static constexpr bool kRowIndependent = true;
   void* out; long long ld, sb; float alpha; const float* alpha_ptr; float al;
   const float* colscale; int cs_ld; const bf16* resid; const float* bcast; int bc_ld; float bc_scale;
+  float* gcolsum;
   __device__ __forceinline__ void begin(int, int, bool) { al = alpha * (alpha_ptr ? alpha_ptr[0] : 1.f); }
   __device__ __forceinline__ void end(int, int, bool) {}
+  // all 32 lanes must call this (shuffles); v is left untouched
+  __device__ __forceinline__ void global_colsum(const float (&v)[16], int n0, int nvalid, bool row_ok, int N) const {
+    float w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = (row_ok && j < nvalid) ? v[j] : 0.f;
+    const float s_ = warp_colsum16(w);
+    const int lane = threadIdx.x & 31;
+    const int col = n0 + colsum16_owner_col(lane);
+    if (((lane & 1) == 0) && col < N) atomicAdd(&gcolsum[col], s_);
+  }
   __device__ __forceinline__ void transform(int b, int n0, float (&v)[16], int nvalid) const {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] *= al;
@@ -76,9 +90,13 @@ struct EpiOut {
   }
   __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
     const int nvalid = nvalid16(n0, N);
+    if (GCOLSUM) {
+      transform(row_ok ? b : 0, n0, v, nvalid);
+      global_colsum(v, n0, nvalid, row_ok, N);
+    }
     if (!row_ok || nvalid <= 0) return;
     const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
-    transform(b, n0, v, nvalid);
+    if (!GCOLSUM) transform(b, n0, v, nvalid);
     if (RESID) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
@@ -107,6 +125,10 @@ struct EpiOut {
     const int bs = row_ok ? b : 0;                       // rows past M still execute (warp-cooperative I/O): keep loads in range
     transform(bs, n0, v0, nv0);
     if (two) transform(bs, n0 + 16, v1, nv1);
+    if (GCOLSUM) {
+      global_colsum(v0, n0, nv0, row_ok, N);
+      if (two) global_colsum(v1, n0 + 16, nv1, row_ok, N);
+    }
     if (RESID) {
       float r0[16], r1[16];
       warp_load_block32_bf16(resid, off, n0, nv0 + nv1, row_ok, stage, r0, r1);
@@ -163,9 +185,10 @@ static GemmOperand simt_operand(const tc::OperandDesc& o, int is_bf16) {
 template <typename TE, typename AX>
 static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const tc::OperandDesc& B, int b_bf16, int M, int N, int K,
                     int batch, TE te, const EpiOut& se, AX ax, bool ax_identity, int bn_hint = 0, bool sum_b = false,
-                    bool split_k_ok = false) {
+                    bool split_k_ok = false, bool* used_tc = nullptr) {
   StageScope _sc(g.stage, g.st);
   count_launch();
+  if (used_tc) *used_tc = false;
   if (g.allow_tc && a_bf16 && b_bf16 && ax_identity) {
     tc::Params p;
     const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint, 0, sum_b, tc::epi_row_independent<TE>::value,
@@ -173,6 +196,7 @@ static int run_gemm(const Gemm& g, const tc::OperandDesc& A, int a_bf16, const t
     if (rc == DGSCT_OK) {
       cudaError_t e = tc::launch(p, te, g.st);
       if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
+      if (used_tc) *used_tc = true;
       return DGSCT_OK;
     }
     if (rc != DGSCT_ERR_UNSUPPORTED) return rc;
@@ -410,9 +434,10 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     side_used = false;
     return DGSCT_OK;
   };
-  const Gemm S_UD{ST_BWD_UPDOWN, "bwd_updown_dw", sst, tcp}, S_SP{ST_BWD_SPATIAL, "bwd_spatial_dw", sst, tcp},
-      S_CH{ST_BWD_CHANNEL, "bwd_channel_dw", sst, tcp}, S_TK{ST_BWD_TOKEN, "bwd_token_dw", sst, tcp},
-      S_FC{ST_BWD_FC, "bwd_fc_dw", sst, tcp}, S_DW{ST_BWD_DWRES, "bwd_dwres", sst, tcp};
+  // (stage "bwd_dw" = the weight-gradient products sum_b A_b^T B_b of the small matrices; "bwd_dwres" = the resampler's)
+  const Gemm S_UD{ST_BWD_DW, "bwd_updown_dw", sst, tcp}, S_SP{ST_BWD_DW, "bwd_spatial_dw", sst, tcp},
+      S_CH{ST_BWD_DW, "bwd_channel_dw", sst, tcp}, S_TK{ST_BWD_DW, "bwd_token_dw", sst, tcp},
+      S_FC{ST_BWD_DW, "bwd_fc_dw", sst, tcp}, S_DW{ST_BWD_DWRES, "bwd_dwres", sst, tcp};
   (void)G_DW;
   const int rgrid = (int)((R + 7) / 8 < 148 * 4 ? (R + 7) / 8 : 148 * 4);
   const int ew_grid = 148 * 8;
@@ -630,6 +655,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     }
   }
   // ---- 7. latent-token attention -----------------------------------------------------------------------------------
+  bool fcb_summed = false;            // d fc_b already accumulated by the dV products (tensor-core epilogues)
   {
     // dQraw = G . Tp^T -> gQ ; dL2 (in place) ; d_gate_av
     EpiOut e1 = eo(gQ, bf, K, (long long)N * K, OUT_STORE);
@@ -669,14 +695,20 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
         col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
       KCHECK("col_softmax_bwd"); }
     // dV = P . dTp + dL1 . T + dobar / N
+    // (tensor-core path: d fc_b = column sums of dV are taken here from the fp32 accumulators, see tc::EpiOut GCOLSUM)
     EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
     const void* dL1 = gQ; long long dL1_ld = K, dL1_bs = (long long)N * K;
+    bool fcb_tc6 = false, fcb_tc7 = false;
     {
+      auto t6 = to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false, true>>(e6); t6.gcolsum = G.fc_b;
       RC(run_gemm(G_TK, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
-                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
+                  t6, e6, AxIdentity{}, true, 0, false, false, &fcb_tc6));
       EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
+      auto t7 = to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false, true>>(e7); t7.gcolsum = G.fc_b;
       RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
-                  to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
+                  t7, e7, AxIdentity{}, true, 0, false, false, &fcb_tc7));
+      if (tcp && fcb_tc6 != fcb_tc7) return DGSCT_ERR_UNSUPPORTED;      // (same operand geometry: both or neither)
+      fcb_summed = fcb_tc6 && fcb_tc7;
     }
     // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
     RC(fork_side());                                                  // dL1 is final; sum_frames already added its share
@@ -697,7 +729,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("fc_rowsum");
     }
     RC(fork_side());                                                  // gV is final
-    { StageScope _sc(ST_MISC, sst); count_launch();
+    if (!fcb_summed) { StageScope _sc(ST_MISC, sst); count_launch();
       col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
       KCHECK("dfc_b"); }
     // dO'[b] (No,C) = Wres^T . dV[b]  -> gU
@@ -731,7 +763,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     }
   } else {
     RC(fork_side());                                                  // gV is final
-    { StageScope _sc(ST_MISC, sst); count_launch();
+    if (!fcb_summed) { StageScope _sc(ST_MISC, sst); count_launch();   // (else: summed by the dV products' epilogues)
       col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
       KCHECK("dfc_b"); }
     // dU = dV . Wfc ; dWfc += dV^T . U

@@ -13,7 +13,7 @@ static const char* kNames[ST_COUNT] = {
     "small_linear", "channel_query", "spatial_query", "spatial_map", "gate_ln", "down_sampler", "bn_finalize",
     "up_sampler", "out_ln", "misc",
     "bwd_out", "bwd_updown", "bwd_gate_ln", "bwd_spatial", "bwd_channel", "bwd_small", "bwd_token", "bwd_fc", "bwd_dwres",
-    "bwd_dother"};
+    "bwd_dother", "bwd_dw", "adam"};
 
 const char* stage_name(int s) { return (s >= 0 && s < ST_COUNT) ? kNames[s] : "?"; }
 

@@ -11,7 +11,7 @@ enum Stage {
   ST_X_UPDATE, ST_SMALL_LINEAR, ST_CHANNEL_QUERY, ST_SPATIAL_QUERY, ST_SPATIAL_MAP, ST_GATE_LN, ST_DOWN, ST_BN_FINALIZE,
   ST_UP, ST_OUT_LN, ST_MISC,
   ST_BWD_OUT, ST_BWD_UPDOWN, ST_BWD_GATE_LN, ST_BWD_SPATIAL, ST_BWD_CHANNEL, ST_BWD_SMALL, ST_BWD_TOKEN, ST_BWD_FC, ST_BWD_DWRES,
-  ST_BWD_DOTHER, ST_COUNT
+  ST_BWD_DOTHER, ST_BWD_DW, ST_ADAM, ST_COUNT
 };
 
 const char* stage_name(int s);

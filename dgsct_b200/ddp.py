@@ -15,20 +15,46 @@ import torch
 import torch.distributed as dist
 
 
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
 class GradBucket:
-    def __init__(self, params: Sequence[torch.nn.Parameter]):
+    """One flat fp32 gradient buffer; every ``param.grad`` is a view into it (16-byte aligned offsets).
+    ``flatten_params``: the parameters themselves become views of a second flat buffer with the same layout, so an
+    optimizer can update the whole bucket with one elementwise kernel (:class:`FlatAdam`).
+    ``comm_dtype=torch.bfloat16``: the all-reduce runs on a bf16 copy of the bucket (half the NVLink bytes)."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], flatten_params: bool = False, comm_dtype: torch.dtype = torch.float32):
         self.params = list(params)
-        n = sum(p.numel() for p in self.params)
+        self.offsets: List[int] = []
+        n = 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += _pad4(p.numel())
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views: List[torch.Tensor] = []
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             if p.dtype != torch.float32:
                 raise TypeError("gradient buckets hold fp32 master gradients")
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             p.grad = self.views[-1]
-            off += p.numel()
+        self.pflat: Optional[torch.Tensor] = None
+        if flatten_params:
+            self.pflat = torch.zeros(n, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for p, off in zip(self.params, self.offsets):
+                    dst = self.pflat[off:off + p.numel()].view_as(p)
+                    dst.copy_(p.data)
+                    p.data = dst                      # same Parameter object, storage now inside the flat buffer
+        self.comm_dtype = comm_dtype
+        self.comm: Optional[torch.Tensor] = None      # bf16 communication copy (filled when the bucket is reduced)
+        if comm_dtype == torch.bfloat16:
+            self.comm = torch.zeros(n, dtype=torch.bfloat16, device=dev)
+        elif comm_dtype != torch.float32:
+            raise TypeError("comm_dtype must be float32 or bfloat16")
+        self.reduced_in_comm = False                  # this step's reduced SUM lives in `comm` (bf16), not in `flat`
         self.work: Optional[dist.Work] = None
         self.launched = False
 
@@ -48,6 +74,7 @@ class GradBucket:
     def zero(self) -> None:
         self.flat.zero_()
         self.launched = False
+        self.reduced_in_comm = False
         for p, v in zip(self.params, self.views):
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
@@ -58,18 +85,47 @@ class GradBucket:
         self.launched = True
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return
+
+        def reduce_():
+            buf = self.flat
+            if self.comm is not None:
+                self._to_comm()
+                buf = self.comm
+                self.reduced_in_comm = True
+            self.work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
         if stream is not None and self.flat.is_cuda:
             stream.wait_stream(torch.cuda.current_stream(self.flat.device))
             with torch.cuda.stream(stream):
-                self.work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+                reduce_()
         else:
-            self.work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+            reduce_()
 
-    def wait(self, group=None) -> None:
+    def _to_comm(self) -> None:
+        if self.flat.is_cuda:
+            import ctypes as C
+            from . import _lib as L
+            st = torch.cuda.current_stream(self.flat.device).cuda_stream
+            with torch.cuda.device(self.flat.device):
+                L.check(L.lib().dgsct_cast_bucket_bf16(C.c_void_p(self.flat.data_ptr()), C.c_void_p(self.comm.data_ptr()),
+                                                       C.c_size_t(self.flat.numel()), C.c_float(1.0), C.c_void_p(st)), "cast_bucket")
+        else:
+            self.comm.copy_(self.flat)
+
+    def wait(self, group=None, keep_in_comm: bool = False) -> None:
+        """Wait for the all-reduce and turn the sum into the mean in ``flat``.  ``keep_in_comm`` (FlatAdam): leave a bf16
+        reduced SUM in ``comm`` -- the optimizer kernel reads it directly with grad_scale = 1/world, saving one pass."""
         if self.work is not None:
             self.work.wait()
             self.work = None
-            self.flat.div_(dist.get_world_size(group))
+            w = dist.get_world_size(group)
+            if self.reduced_in_comm:
+                if not keep_in_comm:
+                    self.flat.copy_(self.comm)
+                    self.flat.div_(w)
+                    self.reduced_in_comm = False
+            else:
+                self.flat.div_(w)
 
 
 class GradBucketer:
@@ -78,8 +134,11 @@ class GradBucketer:
     Parameters that never receive a gradient (``gate_tk``, dead ``fc_caption`` / ``temporal_gated`` heads) must be left
     out -- the all-reduce would still be correct (zeros), just wasteful."""
 
-    def __init__(self, param_groups: Iterable[Sequence[torch.nn.Parameter]], bucket_bytes: int = 32 << 20, group=None):
+    def __init__(self, param_groups: Iterable[Sequence[torch.nn.Parameter]], bucket_bytes: int = 32 << 20, group=None,
+                 flatten_params: bool = False, comm_dtype: torch.dtype = torch.float32):
         self.group = group
+        self.keep_in_comm = False             # set by FlatAdam: bf16-reduced sums stay in the communication buffers
+        mk = lambda ps: GradBucket(ps, flatten_params=flatten_params, comm_dtype=comm_dtype)
         self.buckets: List[GradBucket] = []
         self.owner: List[int] = []            # bucket index of every registered group, in order
         cur: List[torch.nn.Parameter] = []
@@ -91,11 +150,11 @@ class GradBucketer:
             cur_bytes += sum(p.numel() for p in g) * 4
             pending_groups += 1
             if cur_bytes >= bucket_bytes:
-                self.buckets.append(GradBucket(cur))
+                self.buckets.append(mk(cur))
                 self.owner += [len(self.buckets) - 1] * pending_groups
                 cur, cur_bytes, pending_groups = [], 0, 0
         if cur:
-            self.buckets.append(GradBucket(cur))
+            self.buckets.append(mk(cur))
             self.owner += [len(self.buckets) - 1] * pending_groups
         self._remaining = [self.owner.count(i) for i in range(len(self.buckets))]
         self._left = list(self._remaining)
@@ -133,7 +192,7 @@ class GradBucketer:
             if not b.launched:
                 self._launch(bi)
         for b in self.buckets:
-            b.wait(self.group)
+            b.wait(self.group, keep_in_comm=self.keep_in_comm)
         # join the communication stream only if a collective was launched on it this step: with one rank nothing was,
         # and waiting on a stream that is not part of an ongoing CUDA-graph capture would invalidate the capture
         if self.comm_stream is not None and self._comm_used:
@@ -141,7 +200,55 @@ class GradBucketer:
         self._comm_used = False
 
     def total_bytes(self) -> int:
-        return sum(b.flat.numel() * 4 for b in self.buckets)
+        return sum(b.flat.numel() * (2 if b.comm is not None else 4) for b in self.buckets)
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (the reference's optimizer, main_trans.py:276) over the flat buckets of a
+    :class:`GradBucketer` built with ``flatten_params=True``: ONE fused kernel per bucket (dgsct_adam_flat) instead of a
+    multi-tensor apply over ~1400 parameter tensors, reading the (possibly bf16, all-reduced-SUM) gradient in place.
+    The step counter lives on the device, so ``step()`` is CUDA-graph capturable.  After a step the engine adapters'
+    packed bf16 weight copies are stale: pass the modules so they are invalidated (their next forward re-packs)."""
+
+    def __init__(self, bucketer: GradBucketer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 modules: Sequence[torch.nn.Module] = ()):
+        self.bucketer = bucketer
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.modules = list(modules)
+        for b in bucketer.buckets:
+            if b.pflat is None:
+                raise ValueError("FlatAdam needs GradBucketer(..., flatten_params=True)")
+            if not b.flat.is_cuda:
+                raise RuntimeError("FlatAdam runs on CUDA buckets only (no CPU fallback)")
+        dev = bucketer.buckets[0].flat.device
+        self.m = [torch.zeros_like(b.flat) for b in bucketer.buckets]
+        self.v = [torch.zeros_like(b.flat) for b in bucketer.buckets]
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        bucketer.keep_in_comm = True
+
+    def step(self) -> None:
+        import ctypes as C
+        from . import _lib as L
+        lib = L.lib()
+        world = dist.get_world_size(self.bucketer.group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = self.step_dev.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            L.check(lib.dgsct_adam_tick(C.c_void_p(self.step_dev.data_ptr()), st), "adam_tick")
+            for b, m, v in zip(self.bucketer.buckets, self.m, self.v):
+                if b.reduced_in_comm:       # bf16 SUM over ranks, still in the communication buffer
+                    g, g_bf16, scale = b.comm, 1, 1.0 / world
+                    b.reduced_in_comm = False
+                else:                       # fp32 mean (or a single rank's gradient)
+                    g, g_bf16, scale = b.flat, 0, 1.0
+                L.check(lib.dgsct_adam_flat(C.c_void_p(b.pflat.data_ptr()), C.c_void_p(g.data_ptr()), g_bf16, C.c_void_p(m.data_ptr()),
+                                            C.c_void_p(v.data_ptr()), C.c_size_t(b.flat.numel()), C.c_float(self.lr),
+                                            C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                            C.c_float(self.weight_decay), C.c_float(scale), C.c_void_p(self.step_dev.data_ptr()), st),
+                        "adam_flat")
+        for mod in self.modules:
+            if hasattr(mod, "invalidate_packed"):
+                mod.invalidate_packed()
 
 
 class AdapterDDP:
@@ -165,7 +272,7 @@ class AdapterDDP:
     collectives; gradients keep adding up in the buckets."""
 
     def __init__(self, modules: Sequence[torch.nn.Module], bucket_bytes: int = 32 << 20, group=None, fused: bool = True,
-                 broadcast: bool = True):
+                 broadcast: bool = True, flatten_params: bool = False, comm_dtype: torch.dtype = torch.float32):
         self.modules = list(modules)
         self.group = group
         order = list(reversed(self.modules))
@@ -177,7 +284,8 @@ class AdapterDDP:
                     if hasattr(m, "invalidate_packed"):
                         m.invalidate_packed()        # .data writes do not bump _version (packed bf16 weight cache key)
         groups = [[p for p in m.parameters() if p.requires_grad] for m in order]
-        self.bucketer = GradBucketer(groups, bucket_bytes=bucket_bytes, group=group)
+        self.bucketer = GradBucketer(groups, bucket_bytes=bucket_bytes, group=group, flatten_params=flatten_params,
+                                     comm_dtype=comm_dtype)
         self._sync = True
         self._npar = [len(g) for g in groups]
         self._pending = list(self._npar)

@@ -163,6 +163,17 @@ int dgsct_adapter_bwd_saved(const dgsct_desc *desc, const dgsct_params *params, 
                             const void *d_spatial_map, const float *d_temporal_map, void *dx, void *dother,
                             const dgsct_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Optimizer over FLAT buffers (the gradient buckets of the data-parallel wrapper): torch.optim.Adam semantics
+ * (DG-SCT/AVE/main_trans.py:276: Adam over the trainable adapter parameters), one fused kernel per bucket.
+ *   dgsct_adam_tick   increments the device-resident step counter (once per optimizer step; graph-capturable)
+ *   dgsct_adam_flat   p, m, v fp32 (n elements, 16-B aligned); g fp32 or bf16 (g_is_bf16); grad_scale multiplies g first
+ *                     (1/world after a SUM all-reduce); bias corrections use *step_dev
+ *   dgsct_cast_bucket_bf16   dst = bf16(scale * src): communication copy of an fp32 bucket for a bf16 all-reduce */
+int dgsct_adam_tick(int *step_dev, void *stream);
+int dgsct_adam_flat(float *p, const void *g, int g_is_bf16, float *m, float *v, size_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, float grad_scale, const int *step_dev, void *stream);
+int dgsct_cast_bucket_bf16(const float *src, void *dst_bf16, size_t n, float scale, void *stream);
+
 /* Stage profiler (used by bench.py for the per-kernel roofline).  When enabled every pipeline stage is
  * bracketed by CUDA events on the launching stream; collect() synchronises on them, writes accumulated
  * milliseconds and call counts per stage (arrays of >= dgsct_num_stages() entries) and clears the log. */

@@ -1,0 +1,248 @@
+"""Round-2 GPU tests: BASELINE configs 4 / 5 at their real frame counts, the sparse S4 resampler, the data-parallel wrapper
+driving real engine adapters, the flat-bucket Adam, nn.DataParallel replicas and the boundary's error reporting."""
+import copy
+import dataclasses
+import types
+
+import pytest
+import torch
+
+import dgsct_b200
+from dgsct_b200 import _lib as L
+from dgsct_b200.adapter import adapter_backward_raw, adapter_forward_raw
+from oracle import dgsct_oracle as O
+from tests.golden_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+S4 = dict(use_bn=False, use_gate=False)                          # avs_s4/train.sh defaults
+AVQA = dict(K=2, g=4, use_bn=False, use_gate=False)              # AVQA/train.sh, base_options.py:67-87
+
+
+def _dev(params):
+    return {k: v.float().cuda().contiguous() for k, v in params.items()}
+
+
+def _oracle_grads(cfg, params, x, other, R_out, R_smap, training):
+    p = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in params.items()}
+    xs, os_ = x.clone().requires_grad_(True), other.clone().requires_grad_(True)
+    out, smap, _, _ = O.adapter_forward(cfg, p, xs, os_, training=training)
+    ((out * R_out).sum() + (smap.reshape(R_smap.shape) * R_smap).sum()).backward()
+    return out.detach(), smap.detach(), xs.grad, os_.grad, {k: v.grad for k, v in p.items() if v.grad is not None}
+
+
+# ---- config 4: AVS-S4, B=4 clips x 5 frames = 20 frames per call, bicubic resampler as a 16-tap stencil --------------------
+@pytest.mark.parametrize("shape", [(768, 144, 384, 256), (384, 256, 768, 144), (192, 2304, 96, 4096), (96, 4096, 192, 2304), (1536, 36, 768, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_s4_bt20_forward_backward(shape, dtype):
+    C, N, Co, No = shape
+    BT = 20
+    cfg = O.make_config("s4", C, N, Co, No, **S4)
+    params = O.random_params(cfg, seed=51)
+    x, other = O.random_inputs(cfg, BT, seed=52)
+    g = torch.Generator().manual_seed(53)
+    R_out = torch.randn(BT, N, C, generator=g).to(dtype).float()
+    R_smap = torch.randn(BT, N, generator=g).to(dtype).float()
+    xq, oq = x.to(dtype), other.to(dtype)
+    p = _dev(params)
+    cd = dataclasses.asdict(cfg)
+    out, smap, _ = adapter_forward_raw(cd, p, xq.cuda(), oq.cuda(), training=True)
+    dx, do, grads = adapter_backward_raw(cd, p, xq.cuda(), oq.cuda(), R_out.to(dtype).cuda(), R_smap.to(dtype).cuda(), None, training=True)
+    torch.cuda.synchronize()
+    assert L.lib().dgsct_tc_error_flag(1) == 0
+    ro, rs, gx, go, gp = _oracle_grads(cfg, params, xq.float(), oq.float(), R_out, R_smap, True)
+    ftol = 1e-3 if dtype == torch.float32 else 1e-2                  # north_star: 1e-3 rel fp32 / 1e-2 bf16
+    assert rel_l2(out.float().cpu(), ro) < ftol, rel_l2(out.float().cpu(), ro)
+    assert rel_l2(smap.float().cpu(), rs.reshape(smap.shape)) < ftol
+    gtol = 3e-3 if dtype == torch.float32 else 6e-2
+    errs = {"x": rel_l2(dx.float().cpu(), gx), "other": rel_l2(do.float().cpu(), go)}
+    for k, v in gp.items():
+        if k in grads and float(v.abs().max()) > 1e-6:
+            errs[k] = rel_l2(grads[k].cpu(), v.reshape(grads[k].shape))
+    errs.pop("gate", None)
+    assert "conv_adapter.weight" not in grads            # the stencil has no trainable matrix
+    bad = {k: f"{v:.2e}" for k, v in errs.items() if v > gtol}
+    assert not bad, bad
+
+
+def test_s4_sparse_stencil_equals_dense_matrix_path():
+    C, N, Co, No = 384, 576, 192, 1024
+    cfg = O.make_config("s4", C, N, Co, No, **S4)
+    p = _dev(O.random_params(cfg, seed=61))
+    x, other = O.random_inputs(cfg, 5, seed=62)
+    cd = dataclasses.asdict(cfg)
+    o1, s1, _ = adapter_forward_raw(cd, p, x.cuda(), other.cuda())
+    o2, s2, _ = adapter_forward_raw(dict(cd, dense_bicubic=True), p, x.cuda(), other.cuda())
+    torch.cuda.synchronize()
+    assert rel_l2(o1.cpu(), o2.cpu()) < 1e-5 and rel_l2(s1.cpu(), s2.cpu()) < 1e-5
+
+
+# ---- config 5: AVQA, T=60 -> 480 frames per call, K=2 latent tokens, g=4 ---------------------------------------------------
+@pytest.mark.parametrize("shape", [(768, 144, 384, 256), (384, 256, 768, 144)])
+def test_avqa_bt480_against_oracle(shape):
+    """deep-stage shapes: the oracle finishes 480 frames in seconds, so the whole call is checked directly (fwd + bwd)."""
+    C, N, Co, No = shape
+    BT = 480
+    cfg = O.make_config("avqa", C, N, Co, No, T=60, **AVQA)
+    params = O.random_params(cfg, seed=71)
+    x, other = O.random_inputs(cfg, BT, seed=72)
+    g = torch.Generator().manual_seed(73)
+    R_out = torch.randn(BT, N, C, generator=g).bfloat16().float()
+    R_smap = torch.randn(BT, N, generator=g).bfloat16().float()
+    xq, oq = x.bfloat16(), other.bfloat16()
+    p = _dev(params)
+    cd = dataclasses.asdict(cfg)
+    out, smap, _ = adapter_forward_raw(cd, p, xq.cuda(), oq.cuda(), training=True)
+    dx, do, grads = adapter_backward_raw(cd, p, xq.cuda(), oq.cuda(), R_out.bfloat16().cuda(), R_smap.bfloat16().cuda(), None, training=True)
+    torch.cuda.synchronize()
+    assert L.lib().dgsct_tc_error_flag(1) == 0
+    ro, rs, gx, go, gp = _oracle_grads(cfg, params, xq.float(), oq.float(), R_out, R_smap, True)
+    assert rel_l2(out.float().cpu(), ro) < 1e-2 and rel_l2(smap.float().cpu(), rs.reshape(smap.shape)) < 1e-2
+    assert rel_l2(dx.float().cpu(), gx) < 6e-2 and rel_l2(do.float().cpu(), go) < 6e-2
+    for k in ("fc_affine_video_1.weight", "fc.weight", "down_sampler.weight", "ln_post.weight"):
+        assert rel_l2(grads[k].cpu(), gp[k].reshape(grads[k].shape)) < 6e-2, k
+
+
+def test_avqa_bt480_stage0_reproduces_10_frame_calls():
+    """stage-0 shape at 480 frames: BN is off in AVQA, so frames are independent and every 10-frame slice of the big call
+    must reproduce the 10-frame call on that slice (which test_variants_at_real_shape pins to the oracle)."""
+    C, N, Co, No = 96, 4096, 192, 2304
+    BT = 480
+    cfg = O.make_config("avqa", C, N, Co, No, T=60, **AVQA)
+    p = _dev(O.random_params(cfg, seed=81))
+    g = torch.Generator().manual_seed(82)
+    x = torch.randn(BT, N, C, generator=g).bfloat16().cuda()
+    other = torch.randn(BT, No, Co, generator=g).bfloat16().cuda()
+    cd = dataclasses.asdict(cfg)
+    out, smap, _ = adapter_forward_raw(cd, p, x, other)
+    for lo in (0, 230, 470):
+        o10, s10, _ = adapter_forward_raw(cd, p, x[lo:lo + 10].contiguous(), other[lo:lo + 10].contiguous())
+        assert rel_l2(out[lo:lo + 10].float().cpu(), o10.float().cpu()) < 2e-3
+        assert rel_l2(smap[lo:lo + 10].float().cpu(), s10.float().cpu()) < 2e-3
+    ro, rs, _, _ = O.adapter_forward(cfg, {k: v.cpu() for k, v in p.items()}, x[:2].float().cpu(), other[:2].float().cpu())
+    assert rel_l2(out[:2].float().cpu(), ro) < 1e-2
+    assert float((smap.float().sum(-1) - 1).abs().max()) < 2e-2
+    assert L.lib().dgsct_tc_error_flag(1) == 0
+
+
+# ---- the data-parallel wrapper driving real engine adapters (single process: no collective, same hooks) ---------------------
+def _make_adapter(C, N, Co, No, seed):
+    opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=2, is_before_layernorm=1, is_post_layernorm=1)
+    ad = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, num_tk=32, conv_dim_in=No, conv_dim_out=N,
+                                  linear_in=Co, linear_out=C).cuda().train()
+    ad.load_state_dict(O.random_params(O.make_config("ave", C, N, Co, No), seed=seed), strict=False)
+    ad.gate_tk.requires_grad_(False)
+    return ad
+
+
+def _two_layer_loss(a1, a2, f_v, f_a):
+    o1, _ = a1(f_v.permute(0, 2, 1).unsqueeze(-1), f_a.permute(0, 2, 1).unsqueeze(-1))            # inputs do NOT require grad
+    f_v2 = f_v + o1.squeeze(-1).permute(0, 2, 1)
+    o2, m2 = a2(f_v2.permute(0, 2, 1).unsqueeze(-1), f_a.permute(0, 2, 1).unsqueeze(-1))
+    return (o2.float() ** 2).sum() * 1e-2 + m2.float()[:, 0, ::5].sum()
+
+
+def test_adapter_ddp_with_engine_adapters_and_flat_adam():
+    C, N, Co, No = 384, 256, 768, 144
+    g = torch.Generator().manual_seed(91)
+    f_v = torch.randn(10, N, C, generator=g).cuda()
+    f_a = torch.randn(10, No, Co, generator=g).cuda()
+    # reference run: plain autograd + torch.optim.Adam
+    r1, r2 = _make_adapter(C, N, Co, No, 1), _make_adapter(C, N, Co, No, 2)
+    ref_opt = torch.optim.Adam([q for m in (r1, r2) for q in m.parameters() if q.requires_grad], lr=1e-3)
+    # engine run: AdapterDDP (fused accumulation into flat buckets, completion signalled from inside the backward) + FlatAdam
+    e1, e2 = copy.deepcopy(r1), copy.deepcopy(r2)
+    ddp = dgsct_b200.AdapterDDP([e1, e2], bucket_bytes=1 << 20, flatten_params=True)
+    opt = dgsct_b200.FlatAdam(ddp.bucketer, lr=1e-3, modules=[e1, e2])
+    assert e1.fused_grad_accumulation and e1._ddp_done_cb is not None
+    for step in range(3):
+        ref_opt.zero_grad(set_to_none=True)
+        _two_layer_loss(r1, r2, f_v, f_a).backward()
+        ddp.zero_grad()
+        for q in e1.parameters():                     # the reference loop's zero_grad(set_to_none=True) drops the views ...
+            q.grad = None
+        ddp.zero_grad()                               # ... and the wrapper re-attaches them
+        _two_layer_loss(e1, e2, f_v, f_a).backward()
+        assert all(b.launched for b in ddp.bucketer.buckets)          # both adapters reported from inside their backward
+        ddp.finish()
+        if step == 0:
+            for (n, qa), (_, qb) in zip(r1.named_parameters(), e1.named_parameters()):
+                if qa.grad is not None and float(qa.grad.abs().max()) > 1e-7:
+                    assert rel_l2(qb.grad.cpu(), qa.grad.cpu()) < 2e-3, n
+        ref_opt.step()
+        opt.step()
+    torch.cuda.synchronize()
+    for (n, qa), (_, qb) in zip(list(r1.named_parameters()) + list(r2.named_parameters()),
+                                list(e1.named_parameters()) + list(e2.named_parameters())):
+        if qa.requires_grad:
+            # three Adam steps of lr 1e-3 move every element by <= 3e-3; elements whose gradient is numerically zero may
+            # take opposite signs in the two runs (fp32 atomics reorder sums), everything else must agree closely
+            assert float((qa - qb).abs().max()) < 6.5e-3, n
+            assert rel_l2(qb.detach().cpu(), qa.detach().cpu()) < 2e-3, n
+
+
+def test_flat_adam_matches_torch_adam_elementwise():
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in ((257, 33), (5,), (1024, 96))]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.Adam(qs, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
+    bk = dgsct_b200.GradBucketer([ps], bucket_bytes=1 << 30, flatten_params=True)
+    opt = dgsct_b200.FlatAdam(bk, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
+    for step in range(5):
+        bk.zero_grad()
+        for p, q in zip(ps, qs):
+            gr = torch.randn_like(p)
+            p.grad.add_(gr)
+            q.grad = gr.clone()
+        bk.finish()
+        opt.step()
+        ref.step()
+    torch.cuda.synchronize()
+    for p, q in zip(ps, qs):
+        assert float((p - q).abs().max()) < 1e-5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (nn.DataParallel replicas)")
+def test_data_parallel_replicas_match_single_device():
+    """The S4 / MS3 / AVQA scripts wrap the model in nn.DataParallel (avs_s4/train.py:139): replicas are driven from one
+    Python thread per GPU in one process, hold broadcast copies as plain attributes, and reduce gradients to device 0."""
+    C, N, Co, No = 768, 144, 384, 256
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ad = _make_adapter(C, N, Co, No, 3)
+
+        def forward(self, f_v, f_a):
+            o, m = self.ad(f_v.permute(0, 2, 1).unsqueeze(-1), f_a.permute(0, 2, 1).unsqueeze(-1))
+            return o.squeeze(-1).permute(0, 2, 1), m
+
+    net = Net().cuda(0).eval()                      # eval: BN uses running stats, so replicas and the single device agree
+    g = torch.Generator().manual_seed(5)
+    f_v = torch.randn(8, N, C, generator=g).cuda(0).requires_grad_(True)
+    f_a = torch.randn(8, No, Co, generator=g).cuda(0)
+    o1, m1 = net(f_v, f_a)
+    (o1 ** 2).sum().backward()
+    g1 = {n: q.grad.clone() for n, q in net.named_parameters() if q.grad is not None}
+    gx1 = f_v.grad.clone()
+    net.zero_grad()
+    f_v.grad = None
+    dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+    o2, m2 = dp(f_v, f_a)
+    (o2 ** 2).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_l2(o2.cpu(), o1.detach().cpu()) < 1e-4 and rel_l2(m2.cpu(), m1.detach().cpu()) < 1e-4
+    assert rel_l2(f_v.grad.cpu(), gx1.cpu()) < 1e-3
+    for n, q in net.named_parameters():
+        if n in g1 and float(g1[n].abs().max()) > 1e-7:
+            assert rel_l2(q.grad.cpu(), g1[n].cpu()) < 2e-3, n
+
+
+def test_boundary_reports_errors():
+    lib = L.lib()
+    assert lib.dgsct_tc_error_flag(0) == 0
+    assert lib.dgsct_status_string(-6) == b"device is not sm_100"
+    assert b"timed out" in lib.dgsct_status_string(-7)
+    cfg = O.make_config("ave", 768, 36, 384, 64)
+    p = _dev(O.random_params(cfg, seed=1))
+    with pytest.raises(RuntimeError):
+        adapter_forward_raw(dataclasses.asdict(cfg), p, torch.randn(2, 36, 768), torch.randn(2, 64, 384))      # CPU tensors
