@@ -47,31 +47,18 @@ struct EpiOut {
 
 namespace tc {
 // tensor-core twin (row-major output only; transposed outputs use EpiOutT)
-// GCOLSUM: gcolsum[n] += sum over all rows (every frame) of the fp32 value this product contributes, BEFORE it is rounded to
-// the output dtype -- bias gradients of a bf16 tensor summed over ~10^4 rows lose small coherent terms (the dobar / N
-// broadcast in dV) when they are re-read from the rounded tensor (fc.bias sat at 0.6-0.8 rel-L2 in round 1).
-template <bool OUT_BF16, int MODE, bool RESID, bool BCAST, bool CSCALE, bool GCOLSUM = false>
+template <bool OUT_BF16, int MODE, bool RESID, bool BCAST, bool CSCALE>
 struct EpiOut {
   // staged (row-contiguous) I/O only for pure stores: staging a residual / accumulate LOAD measured slower than the direct
   // per-row access (see EpiResidual)
   static constexpr bool kHasChunk32 = (MODE == OUT_STORE) && !RESID;
+  static constexpr bool kHasPair = OUT_BF16 && (RESID || MODE == OUT_ADD);
   static constexpr int kStageBytes = OUT_BF16 ? 2048 : 4096;
   static constexpr bool kRowIndependent = true;
   void* out; long long ld, sb; float alpha; const float* alpha_ptr; float al;
   const float* colscale; int cs_ld; const bf16* resid; const float* bcast; int bc_ld; float bc_scale;
-  float* gcolsum;
   __device__ __forceinline__ void begin(int, int, bool) { al = alpha * (alpha_ptr ? alpha_ptr[0] : 1.f); }
   __device__ __forceinline__ void end(int, int, bool) {}
-  // all 32 lanes must call this (shuffles); v is left untouched
-  __device__ __forceinline__ void global_colsum(const float (&v)[16], int n0, int nvalid, bool row_ok, int N) const {
-    float w[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) w[j] = (row_ok && j < nvalid) ? v[j] : 0.f;
-    const float s_ = warp_colsum16(w);
-    const int lane = threadIdx.x & 31;
-    const int col = n0 + colsum16_owner_col(lane);
-    if (((lane & 1) == 0) && col < N) atomicAdd(&gcolsum[col], s_);
-  }
   __device__ __forceinline__ void transform(int b, int n0, float (&v)[16], int nvalid) const {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] *= al;
@@ -90,23 +77,16 @@ struct EpiOut {
   }
   __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
     const int nvalid = nvalid16(n0, N);
-    if (GCOLSUM) {
-      transform(row_ok ? b : 0, n0, v, nvalid);
-      global_colsum(v, n0, nvalid, row_ok, N);
-    }
     if (!row_ok || nvalid <= 0) return;
     const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
-    if (!GCOLSUM) transform(b, n0, v, nvalid);
+    transform(b, n0, v, nvalid);
     if (RESID) {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j < nvalid) v[j] += __bfloat162float(resid[idx + j]);
     }
     if (MODE == OUT_ATOMIC) {
-      float* o = reinterpret_cast<float*>(out) + idx;
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nvalid) atomicAdd(o + j, v[j]);
+      red_add16(reinterpret_cast<float*>(out) + idx, v, nvalid);
     } else {
       if (MODE == OUT_ADD) {
 #pragma unroll
@@ -117,6 +97,31 @@ struct EpiOut {
       store_row16<OUT_BF16>(out, idx, v, nvalid);
     }
   }
+  // read-modify-write blocks (bf16 residual and / or accumulate into a bf16 output): both 16-column halves at once, every
+  // 128-bit load of the block issued before the first dependent use
+  __device__ __forceinline__ void pair(int b, int m, int n0, float (&v0)[16], float (&v1)[16], bool two, bool row_ok, int N) {
+    const int nv0 = nvalid16(n0, N), nv1 = two ? nvalid16(n0 + 16, N) : 0;
+    const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
+    const bool fast = row_ok && nv0 == 16 && nv1 == 16 && ((idx * 2) & 15) == 0;
+    if (!__all_sync(FULL, fast || !row_ok) || !__any_sync(FULL, fast)) {      // ragged / misaligned block somewhere in the warp
+      chunk(b, m, n0, v0, row_ok, N);
+      if (two) chunk(b, m, n0 + 16, v1, row_ok, N);
+      return;
+    }
+    Raw16 r0{}, r1{}, a0{}, a1{};
+    if (fast) {
+      if (RESID) { r0 = ldg_raw16(resid + idx); r1 = ldg_raw16(resid + idx + 16); }
+      if (MODE == OUT_ADD) { a0 = ldg_raw16(reinterpret_cast<const bf16*>(out) + idx); a1 = ldg_raw16(reinterpret_cast<const bf16*>(out) + idx + 16); }
+    }
+    const int bs = row_ok ? b : 0;
+    transform(bs, n0, v0, 16);
+    transform(bs, n0 + 16, v1, 16);
+    if (!fast) return;
+    if (RESID) { add_raw16(r0, v0); add_raw16(r1, v1); }
+    if (MODE == OUT_ADD) { add_raw16(a0, v0); add_raw16(a1, v1); }
+    store_row16<true>(out, idx, v0, 16);
+    store_row16<true>(out, idx + 16, v1, 16);
+  }
   // 32 columns through the warp's staging buffer: residual / accumulate loads and the store are row-contiguous
   __device__ __forceinline__ void chunk32(int b, int m, int n0, float (&v0)[16], float (&v1)[16], bool two, bool row_ok,
                                           int N, uint8_t* stage) {
@@ -125,10 +130,6 @@ struct EpiOut {
     const int bs = row_ok ? b : 0;                       // rows past M still execute (warp-cooperative I/O): keep loads in range
     transform(bs, n0, v0, nv0);
     if (two) transform(bs, n0 + 16, v1, nv1);
-    if (GCOLSUM) {
-      global_colsum(v0, n0, nv0, row_ok, N);
-      if (two) global_colsum(v1, n0 + 16, nv1, row_ok, N);
-    }
     if (RESID) {
       float r0[16], r1[16];
       warp_load_block32_bf16(resid, off, n0, nv0 + nv1, row_ok, stage, r0, r1);
@@ -655,7 +656,6 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     }
   }
   // ---- 7. latent-token attention -----------------------------------------------------------------------------------
-  bool fcb_summed = false;            // d fc_b already accumulated by the dV products (tensor-core epilogues)
   {
     // dQraw = G . Tp^T -> gQ ; dL2 (in place) ; d_gate_av
     EpiOut e1 = eo(gQ, bf, K, (long long)N * K, OUT_STORE);
@@ -679,7 +679,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     const void* dTpOp = dTp;
     long long dTp_bs = (long long)K * C;
     { StageScope _sc(ST_MISC, st); count_launch(2);
-      sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, st>>>(dTp, BT, (size_t)K * C, G.tokens);
+      sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, st>>>(dTp, BT, (size_t)K * C, G.tokens, G.fc_b, C, dobar);   // + d fc_b (exact)
       if (tcp) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
       KCHECK("dtok_sum"); }
     // dP = V . dTp^T (fp32) ; dL1 = P (dP - sum_n dP P) -> gQ
@@ -695,20 +695,14 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
         col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
       KCHECK("col_softmax_bwd"); }
     // dV = P . dTp + dL1 . T + dobar / N
-    // (tensor-core path: d fc_b = column sums of dV are taken here from the fp32 accumulators, see tc::EpiOut GCOLSUM)
     EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
     const void* dL1 = gQ; long long dL1_ld = K, dL1_bs = (long long)N * K;
-    bool fcb_tc6 = false, fcb_tc7 = false;
     {
-      auto t6 = to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false, true>>(e6); t6.gcolsum = G.fc_b;
       RC(run_gemm(G_TK, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
-                  t6, e6, AxIdentity{}, true, 0, false, false, &fcb_tc6));
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
       EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
-      auto t7 = to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false, true>>(e7); t7.gcolsum = G.fc_b;
       RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
-                  t7, e7, AxIdentity{}, true, 0, false, false, &fcb_tc7));
-      if (tcp && fcb_tc6 != fcb_tc7) return DGSCT_ERR_UNSUPPORTED;      // (same operand geometry: both or neither)
-      fcb_summed = fcb_tc6 && fcb_tc7;
+                  to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
     }
     // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
     RC(fork_side());                                                  // dL1 is final; sum_frames already added its share
@@ -728,10 +722,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       fc_rowsum_kernel<<<ceil_div(C, 8), 256, 0, st>>>((const bf16*)Wfc_op, C, Co, ld_fc, fcs);
       KCHECK("fc_rowsum");
     }
-    RC(fork_side());                                                  // gV is final
-    if (!fcb_summed) { StageScope _sc(ST_MISC, sst); count_launch();
-      col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
-      KCHECK("dfc_b"); }
+    RC(fork_side());                                                  // gV is final (d fc_b: see sum_frames_kernel)
     // dO'[b] (No,C) = Wres^T . dV[b]  -> gU
     EpiOut e1 = eo(gU, bf, C, (long long)No * C, OUT_STORE);
     RC(run_gemm(G_DO, MN_(Wres_op, N, No, ld_res, 0), wbf, MN_(gV, N, C, C, (long long)N * C), bf, No, C, N, BT,
@@ -762,10 +753,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("dfc_w_rank1");
     }
   } else {
-    RC(fork_side());                                                  // gV is final
-    if (!fcb_summed) { StageScope _sc(ST_MISC, sst); count_launch();   // (else: summed by the dV products' epilogues)
-      col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, C, nullptr, 0, 0, R, C, G.fc_b, nullptr);
-      KCHECK("dfc_b"); }
+    RC(fork_side());                                                  // gV is final (d fc_b: see sum_frames_kernel)
     // dU = dV . Wfc ; dWfc += dV^T . U
     EpiOut e1 = eo(gU, bf, Co, (long long)N * Co, OUT_STORE);
     RC(run_gemm(G_FC, K_(gV, N, C, C, (long long)N * C), bf, MN_(Wfc_op, C, Co, ld_fc, 0), wbf, N, Co, C, BT,

@@ -441,12 +441,24 @@ inline void launch_affine_combine(void* g, int g_bf16, long long g_ld, const flo
                                   const float* Cc, long long rows, int C, int ew_grid, cudaStream_t st);
 
 // out[k,c] += sum_b in[b,k,c]     (gradient of the shared latent tokens through T' = T + ...)
-__global__ void sum_frames_kernel(const float* __restrict__ in, int BT, size_t per_frame, float* __restrict__ out) {
+// out[i] += sum_b in[b, i]  (i < per_frame = K*C).  With d_fcb != NULL the same sums also feed the gradient of fc.bias:
+//   d fc_b[c] = sum_{b,n} dV[b,n,c]  with  dV = P dT' + dL1 T + dobar/N .
+// Column sums over n of the three terms: sum_n P[n,k] = 1 (softmax over n), sum_n dL1[n,k] = 0 (softmax backward), and the
+// broadcast term gives dobar, hence EXACTLY  d fc_b[c] = sum_b ( sum_k dT'[b,k,c] + dobar[b,c] )  -- no pass over the
+// (BT,N,C) tensor, and none of its bf16 rounding (summing 10^5 rounded rows left fc.bias at 0.6-0.8 rel-L2 in round 1).
+__global__ void sum_frames_kernel(const float* __restrict__ in, int BT, size_t per_frame, float* __restrict__ out,
+                                  float* __restrict__ d_fcb = nullptr, int C = 0, const float* __restrict__ dobar = nullptr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_frame) return;
   float s = 0.f;
   for (int b = 0; b < BT; ++b) s += in[(size_t)b * per_frame + i];
   out[i] += s;
+  if (d_fcb) {
+    const int c = (int)(i % (size_t)C);
+    if (i < (size_t)C)                      // first token row also carries sum_b dobar[b, c]
+      for (int b = 0; b < BT; ++b) s += dobar[(size_t)b * C + c];
+    atomicAdd(&d_fcb[c], s);
+  }
 }
 
 // fp32 -> act dtype copy with scale (operand copies for the tensor-core products)

@@ -32,6 +32,10 @@ struct Params {
   int fpack;                    // frames packed side by side along the instruction N (MN-major batched B, shared A)
   int kb_frames;                // >0: a tile accumulates over this many consecutive frames (K extended over the batch:
                                 // weight gradients sum_b A_b . B_b^T); the epilogue then receives the frame-GROUP index
+  int kflat;                    // weight gradients with both operands token-major (MN-major) and frames contiguous: the sum over
+                                // frames IS a longer K, so (batch, K) is flattened into one K extent cut into `batch` equal chunks
+                                // of K rows (no per-frame padding to BK: 36 / 144-token frames wasted 44 % / 25 % of every tile);
+                                // the k coordinate of a load is then chunk * K + k0 and the tensor maps are 2-D
   int BK;                       // K elements per pipeline stage (64 or 32)
   int stages;
   int a_stage_bytes, b_stage_bytes;
@@ -150,6 +154,12 @@ template <typename T, typename = void>
 struct epi_has_chunk32 { static constexpr bool value = false; };
 template <typename T>
 struct epi_has_chunk32<T, decltype((void)T::kHasChunk32)> { static constexpr bool value = T::kHasChunk32; };
+// functors that take both 16-column halves of a 32-column block at once declare pair(...): every global load of the block is
+// issued before the first dependent use (read-modify-write epilogues were one exposed L2 round trip per 16 columns)
+template <typename T, typename = void>
+struct epi_has_pair { static constexpr bool value = false; };
+template <typename T>
+struct epi_has_pair<T, decltype((void)T::kHasPair)> { static constexpr bool value = T::kHasPair; };
 // functors whose chunk() tolerates a different frame index b in every lane (no warp-wide per-frame reduction)
 template <typename T, typename = void>
 struct epi_row_independent { static constexpr bool value = false; };
@@ -315,7 +325,8 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
         const int bfirst = kbf > 0 ? grp * kbf : grp * fpack;
         const int nfr = kbf > 0 ? min(kbf, p.batch - bfirst) : 1;
         const int m0 = mi * BM, n0 = ni * p.BN;
-        int b = bfirst, k0 = 0;
+        int b = bfirst, k0 = p.kflat ? bfirst * p.K : 0;      // (kflat: absolute row of the flattened K extent)
+        const int kend = p.kflat ? k0 + p.K : p.K;
         const int total = nfr * num_k;
         for (int kk = 0; kk < total; ++kk) {
           ok = mbar_wait(empty0 + 8u * st_i, st_ph ^ 1, p.err_flag);
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           }
           if (++st_i == p.stages) { st_i = 0; st_ph ^= 1; }
           k0 += p.BK;
-          if (k0 >= p.K) { k0 = 0; ++b; }                     // next frame of the group (weight gradients)
+          if (k0 >= kend) { k0 = 0; ++b; }                    // next frame of the group (weight gradients)
         }
       }
     }
@@ -458,6 +469,12 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
           if constexpr (epi_has_chunk32<EPI>::value) {
             if (p.stage_out && fpack == 1) {
               epi.chunk32(bq, m, n0 + c, v0, v1, two, row_ok, p.N, out_stage + (size_t)(warp - 2) * p.stage_out);
+              continue;
+            }
+          }
+          if constexpr (epi_has_pair<EPI>::value) {
+            if (fpack == 1) {
+              epi.pair(bq, m, n0 + c, v0, v1, two, row_ok, p.N);
               continue;
             }
           }

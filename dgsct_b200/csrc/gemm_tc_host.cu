@@ -73,10 +73,34 @@ int num_sms() {
   return n;
 }
 
-int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint,
+int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B_in, int M, int N, int K, int batch, int BN_hint,
                 int stages_hint, bool sum_over_batch, bool allow_flatten, int stage_bytes_per_warp) {
-  if (!operands_ok(A_in, B, K)) return DGSCT_ERR_UNSUPPORTED;
-  OperandDesc A = A_in;
+  if (!operands_ok(A_in, B_in, K)) return DGSCT_ERR_UNSUPPORTED;
+  OperandDesc A = A_in, B = B_in;
+  // Weight gradients sum_b A_b^T B_b with token-major operands whose frames are contiguous: one flattened K extent of batch*K
+  // rows cut into equal chunks (see Params::kflat).  Chosen so that every CTA slot gets a chunk of >= 8 k-blocks.
+  p.kflat = 0;
+  int kflat_chunk = 0, kflat_groups = 0;
+  if (sum_over_batch && A.mn_major && B.mn_major && batch > 1 && A.batch_stride == (long long)K * A.ld &&
+      B.batch_stride == (long long)K * B.ld && (long long)K * batch < (1LL << 30) && !getenv("DGSCT_NO_KFLAT")) {
+    const long long rows = (long long)K * batch;
+    const int bk = 64;
+    const long long nk = (rows + bk - 1) / bk;
+    int bn = BN_hint > 0 ? BN_hint : (N <= 256 ? round_up(N, 16) : round_up((N + (N + 255) / 256 - 1) / ((N + 255) / 256), 16));
+    const long long tiles = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    long long groups = (2LL * num_sms() + tiles - 1) / tiles;
+    if (groups > nk / 8) groups = nk / 8;
+    if (groups < 1) groups = 1;
+    const long long kbpg = (nk + groups - 1) / groups;
+    groups = (nk + kbpg - 1) / kbpg;
+    kflat_chunk = (int)(kbpg * bk);
+    kflat_groups = (int)groups;
+    A.rows = (int)rows; A.batch_stride = 0;
+    B.rows = (int)rows; B.batch_stride = 0;
+    K = kflat_chunk;
+    batch = kflat_groups;
+    p.kflat = 1;
+  }
   // Frames flattened into one M extent: A[b] (M, K) rows are contiguous across frames and B is shared, so
   // (batch, M) is just (batch*M) rows -- no 128-row tile padding per frame (N = 36/64/144 tokens at the deep stages).
   p.rows_per_frame = 0;
@@ -121,7 +145,9 @@ int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B, int M,
   p.b_stage_bytes = round_up(p.fpack * p.b_boxes * p.b_box_bytes, 1024);
   const int num_k = (K + p.BK - 1) / p.BK;
   const int n_blocks = (N + BN - 1) / BN;
-  if (sum_over_batch) {
+  if (p.kflat) {
+    p.kb_frames = 1;              // one K chunk per tile; the epilogue receives the chunk index and adds atomically
+  } else if (sum_over_batch) {
     // frames per tile: enough frame groups to fill ~2 tiles per SM, the rest of the batch is accumulated in the tile
     const long long tiles = (long long)((M + BM - 1) / BM) * n_blocks;
     long long groups = (2LL * num_sms() + tiles - 1) / tiles;
@@ -192,6 +218,7 @@ int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B, int M,
   p.tmem_cols = cols;
   p.err_flag = tc_err_flag_device_ptr();
   p.debug_mode = 0;
+  if (sum_over_batch && getenv("DGSCT_DW_EPI_SKIP")) p.debug_mode = 2;   // measurement only: weight-gradient main loop without its epilogue
   int rc;
   if (A.mn_major) rc = encode(&p.mapA, A, batch, a_atom, p.BK, p.a_sw);
   else rc = encode(&p.mapA, A, batch, p.BK, BM, p.a_sw);

@@ -60,6 +60,36 @@ __device__ __forceinline__ void store_row16(void* out, size_t idx, const float (
   }
 }
 
+// 16 bf16 starting at p (16-byte aligned, all valid) as two 128-bit loads; unpack after ALL loads of a block were issued
+struct Raw16 { uint4 a, b; };
+__device__ __forceinline__ Raw16 ldg_raw16(const bf16* __restrict__ p) {
+  Raw16 r; r.a = reinterpret_cast<const uint4*>(p)[0]; r.b = reinterpret_cast<const uint4*>(p)[1];
+  return r;
+}
+__device__ __forceinline__ void add_raw16(const Raw16& r, float (&v)[16]) {
+  const uint32_t w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    v[2 * j] += __bfloat162float(t.x);
+    v[2 * j + 1] += __bfloat162float(t.y);
+  }
+}
+// fp32 atomic accumulation of 16 consecutive values: four vector reductions when the address is 16-byte aligned
+__device__ __forceinline__ void red_add16(float* o, const float (&v)[16], int nvalid) {
+  if (nvalid == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
+                   "f"(v[4 * j + 3])
+                   : "memory");
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) atomicAdd(o + j, v[j]);
+  }
+}
+
 __device__ __forceinline__ int nvalid16(int n0, int N) { const int r = N - n0; return r < 0 ? 0 : (r > 16 ? 16 : r); }
 
 // ---- warp-cooperative block I/O through the per-warp staging buffer (Params::stage_out) -------------------------------
@@ -309,9 +339,26 @@ struct EpiResidual {
   // accesses save (x_update 2.33 ms staged vs 1.79 ms direct over the 48 calls), so this functor keeps the direct path;
   // pure stores keep the staged one (up_sampler fp32: 1.27 vs 1.74 ms)
   static constexpr bool kHasChunk32 = false;
+  static constexpr bool kHasPair = true;
   static constexpr int kStageBytes = 2048;
   static constexpr bool kRowIndependent = true;
   bf16* out; const bf16* resid; long long ld, sb; const float* gate; float g;
+  // both halves of a 32-column block: the four 128-bit residual loads are in flight together
+  __device__ __forceinline__ void pair(int b, int m, int n0, float (&v0)[16], float (&v1)[16], bool two, bool row_ok, int N) {
+    const int nv0 = nvalid16(n0, N), nv1 = two ? nvalid16(n0 + 16, N) : 0;
+    const size_t idx = (size_t)((long long)b * sb + (long long)m * ld + n0);
+    if (row_ok && nv0 == 16 && nv1 == 16 && ((idx * 2) & 15) == 0) {
+      const Raw16 r0 = ldg_raw16(resid + idx), r1 = ldg_raw16(resid + idx + 16);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { v0[j] *= g; v1[j] *= g; }
+      add_raw16(r0, v0); add_raw16(r1, v1);
+      store_row16<true>(out, idx, v0, 16);
+      store_row16<true>(out, idx + 16, v1, 16);
+      return;
+    }
+    chunk(b, m, n0, v0, row_ok, N);
+    if (two) chunk(b, m, n0 + 16, v1, row_ok, N);
+  }
   __device__ __forceinline__ void begin(int, int, bool) { g = gate[0]; }
   __device__ __forceinline__ void end(int, int, bool) {}
   __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
