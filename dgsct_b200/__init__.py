@@ -10,7 +10,8 @@ Public surface mirrors the reference's call boundary (DG-SCT/AVE/nets/net_trans.
 from .adapter import VisualAdapter, patch, adapter_forward_raw, VARIANT_DEFAULTS  # noqa: F401
 from .adapter import adapter_backward_raw  # noqa: F401
 from .ddp import AdapterDDP, FlatAdam, GradBucketer  # noqa: F401
+from .heads import TemporalGates, pool_tokens  # noqa: F401
 from ._lib import build, lib  # noqa: F401
 
 __all__ = ["VisualAdapter", "patch", "adapter_forward_raw", "adapter_backward_raw", "AdapterDDP", "FlatAdam", "GradBucketer", "build", "lib",
-           "VARIANT_DEFAULTS"]
+           "VARIANT_DEFAULTS", "TemporalGates", "pool_tokens"]

@@ -54,7 +54,8 @@ EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgs
            "dgsct_adapter_fwd", "dgsct_bicubic_matrix", "dgsct_num_stages", "dgsct_stage_name",
            "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
            "dgsct_tc_error_flag", "dgsct_bicubic_csr_capacity", "dgsct_bicubic_csr",
-           "dgsct_adam_tick", "dgsct_adam_flat", "dgsct_cast_bucket_bf16"]
+           "dgsct_adam_tick", "dgsct_adam_flat", "dgsct_cast_bucket_bf16",
+           "dgsct_pool_tokens_fwd", "dgsct_pool_tokens_bwd", "dgsct_temporal_gates_fwd", "dgsct_temporal_gates_bwd"]
 
 _lib = None
 
@@ -107,6 +108,14 @@ def lib() -> C.CDLL:
     L.dgsct_bicubic_csr_capacity.argtypes = [C.c_int, C.c_int]
     L.dgsct_bicubic_csr.restype = C.c_int
     L.dgsct_bicubic_csr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dgsct_pool_tokens_fwd.restype = C.c_int
+    L.dgsct_pool_tokens_fwd.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
+    L.dgsct_pool_tokens_bwd.restype = C.c_int
+    L.dgsct_pool_tokens_bwd.argtypes = [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]
+    L.dgsct_temporal_gates_fwd.restype = C.c_int
+    L.dgsct_temporal_gates_fwd.argtypes = [C.c_void_p] * 8 + [C.c_float] + [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_void_p]
+    L.dgsct_temporal_gates_bwd.restype = C.c_int
+    L.dgsct_temporal_gates_bwd.argtypes = [C.c_void_p] * 6 + [C.c_float] + [C.c_void_p] * 12 + [C.c_int] * 3 + [C.c_void_p]
     L.dgsct_adam_tick.restype = C.c_int
     L.dgsct_adam_tick.argtypes = [C.c_void_p, C.c_void_p]
     L.dgsct_adam_flat.restype = C.c_int

@@ -259,33 +259,11 @@ static T to_tcT(const EpiOut& e) {
 #define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 #define KCHECK(name) DGSCT_LAUNCH_CHECK(name)
 
-// ---- side stream for the parameter-gradient products ------------------------------------------------------------------
-// Every weight gradient (sum_b A_b . B_b^T, accumulated atomically into G.*) is off the critical path of the backward: the
-// activation gradients never read it.  They are therefore issued on an auxiliary stream forked from the caller's stream
-// (event record / wait: graph-capturable, so inside a captured train step they become parallel branches) and joined before
-// the call returns.  One auxiliary stream per (thread, device, caller stream), created on first use.
-struct SideStream { cudaStream_t s; cudaEvent_t ev; };
-static SideStream* side_stream_for(cudaStream_t main) {
-  struct Key { int dev; cudaStream_t st; SideStream side; };
-  static thread_local std::vector<Key> cache;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  for (Key& k : cache)
-    if (k.dev == dev && k.st == main) return &k.side;
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(main, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;   // never create inside a capture
-  SideStream sd{};
-  if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-  if (cudaEventCreateWithFlags(&sd.ev, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(sd.s); return nullptr; }
-  cache.push_back(Key{dev, main, sd});
-  return &cache.back().side;
-}
-
 struct BwdPlan {
   size_t fwd;                        // keep-mode forward workspace
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
   size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, dWup_d, dWd_d, zero_end;
-  size_t vA, vB, vC, vD, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
+  size_t vA, vB, vC, vD, wA, wB, wC, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
   size_t total;
 };
 
@@ -321,6 +299,7 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.zero_end = off;
   p.fc_s = take(C * 4);
   p.vA = take(BT * C * 4); p.vD = take(BT * C * 4);
+  p.wA = take(BT * C * 4); p.wB = take(BT * C * 4); p.wC = take(BT * C * 4);   // second vector chain (own stream: own scratch)
   p.coefA = take(C * 4); p.coefB = take(C * 4); p.coefC = take(C * 4);
   p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
   p.opm = take(BT * C * 4);
@@ -390,6 +369,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   float* dr1 = (float*)(ws + bp.dr1); float* colA = (float*)(ws + bp.colA); float* colB = (float*)(ws + bp.colB);
   float* dWup_d = (float*)(ws + bp.dWup_d); float* dWd_d = (float*)(ws + bp.dWd_d);
   float* vA = (float*)(ws + bp.vA); float* vB = (float*)(ws + bp.vB); float* vC = (float*)(ws + bp.vC);
+  float* wA = (float*)(ws + bp.wA); float* wB = (float*)(ws + bp.wB); float* wC = (float*)(ws + bp.wC);
   float* coefA = (float*)(ws + bp.coefA); float* coefB = (float*)(ws + bp.coefB); float* coefC = (float*)(ws + bp.coefC);
   float* Wd_f = (float*)(ws + bp.Wd_f32); float* Wup_f = (float*)(ws + bp.Wup_f32); float* opm = (float*)(ws + bp.opm);
   float* daq1 = daq; float* daq2 = daq + C; const int daq_ld = C + H;
@@ -436,6 +416,23 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     return DGSCT_OK;
   };
   // (stage "bwd_dw" = the weight-gradient products sum_b A_b^T B_b of the small matrices; "bwd_dwres" = the resampler's)
+  SideStream* side2 = side ? side_stream_for(st, 1) : nullptr;
+  const cudaStream_t s2 = side2 ? side2->s : st;
+  bool side2_used = false;
+  auto fork_side2 = [&]() -> int {
+    if (!side2) return DGSCT_OK;
+    DGSCT_CUDA_CHECK(cudaEventRecord(side2->ev, st));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(side2->s, side2->ev, 0));
+    side2_used = true;
+    return DGSCT_OK;
+  };
+  auto join_side2 = [&]() -> int {
+    if (!side2 || !side2_used) return DGSCT_OK;
+    DGSCT_CUDA_CHECK(cudaEventRecord(side2->ev, side2->s));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(st, side2->ev, 0));
+    side2_used = false;
+    return DGSCT_OK;
+  };
   const Gemm S_UD{ST_BWD_DW, "bwd_updown_dw", sst, tcp}, S_SP{ST_BWD_DW, "bwd_spatial_dw", sst, tcp},
       S_CH{ST_BWD_DW, "bwd_channel_dw", sst, tcp}, S_TK{ST_BWD_DW, "bwd_token_dw", sst, tcp},
       S_FC{ST_BWD_DW, "bwd_fc_dw", sst, tcp}, S_DW{ST_BWD_DWRES, "bwd_dwres", sst, tcp};
@@ -588,23 +585,26 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   // ---- 6. channel gate ---------------------------------------------------------------------------------------------
   {
     // dpm = dm * m (1-m) -> vA (BT,C)
-    const Gemm GS{ST_BWD_SMALL, "bwd_small", st, false};
+    // (the parameter gradients of this chain -- two outer products over the BT rows and two bias sums -- go to the side stream)
+    const Gemm GS{ST_BWD_SMALL, "bwd_small", st, false}, GSW{ST_BWD_SMALL, "bwd_small_dw", sst, false};
     count_launch();
     vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_SIGMOID_BWD, dm, C, mvec, C, 0.f, vA, C, BT, C);
     KCHECK("dpm");
     // d_cb += colsum dpm ; dWc (C,H) += dpm^T h ; dh = dpm . Wc -> vB (BT,H)
-    col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, st>>>(vA, 0, C, nullptr, 0, 0, BT, C, G.c_b, nullptr);
+    RC(fork_side());                                                  // vA = dpm is final
+    col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, sst>>>(vA, 0, C, nullptr, 0, 0, BT, C, G.c_b, nullptr);
     EpiOut e1 = eo(G.c_w, 0, H, 0, OUT_ADD);
-    RC(run_gemm(GS, MN_(vA, BT, C, C, 0), 0, MN_(hsrc, BT, H, h_ld, 0), 0, C, H, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
+    RC(run_gemm(GSW, MN_(vA, BT, C, C, 0), 0, MN_(hsrc, BT, H, h_ld, 0), 0, C, H, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
     EpiOut e2 = eo(vB, 0, H, 0, OUT_STORE);
     RC(run_gemm(GS, K_(vA, BT, C, C, 0), 0, MN_(P.c_w, C, H, H, 0), 0, BT, H, C, 1, tc::EpiNone{}, e2, AxIdentity{}, true, 0, false, true));
     // dph = dh * 1[h>0] -> vB in place ; d_bb += colsum ; dWb (H,C) += dph^T q ; dq = dph . Wb -> vC (BT,C)
     count_launch(2);
     vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, vB, H, hsrc, h_ld, 0.f, vB, H, BT, H);
-    col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, st>>>(vB, 0, H, nullptr, 0, 0, BT, H, G.bott_b, nullptr);
+    RC(fork_side());                                                  // vB = dph is final
+    col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, sst>>>(vB, 0, H, nullptr, 0, 0, BT, H, G.bott_b, nullptr);
     KCHECK("dph");
     EpiOut e3 = eo(G.bott_w, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, MN_(vB, BT, H, H, 0), 0, MN_(qvec, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
+    RC(run_gemm(GSW, MN_(vB, BT, H, H, 0), 0, MN_(qvec, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
     EpiOut e4 = eo(vC, 0, C, 0, OUT_STORE);
     RC(run_gemm(GS, K_(vB, BT, H, H, 0), 0, MN_(P.bott_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e4, AxIdentity{}, true, 0, false, true));
     // q = aq1 * r1sum / N : daq1 = dq * r1sum / N ; dr1 = dq * aq1 / N
@@ -633,25 +633,27 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   }
   {
     // aq1 = relu(Wa1 obar + b), aq2 = relu(Wa2 obar + b), tau = sigmoid(wt obar + bt)   [obar = osum / N]
-    const Gemm GS{ST_BWD_SMALL, "bwd_small", st, false};
+    // Runs on the second auxiliary stream with scratch of its own: d obar is first read by sum_frames_kernel / the dV products.
+    RC(fork_side2());                                                 // daq1 / daq2 / dtau are final
+    const Gemm GS{ST_BWD_SMALL, "bwd_small", s2, false};
     count_launch(3);
-    cast_scale_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(osum, invN, vA, 0, (size_t)BT * C);                     // obar -> vA
-    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_RELU_BWD, daq1, daq_ld, aq1, aq_ld, 0.f, vB, C, BT, C);  // dpa1 -> vB
-    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, daq2, daq_ld, aq2, aq2_ld, 0.f, vC, H, BT, H); // dpa2 -> vC
+    cast_scale_kernel<<<ceil_div(BT * C, 256), 256, 0, s2>>>(osum, invN, wA, 0, (size_t)BT * C);                     // obar -> wA
+    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, s2>>>(VOP_RELU_BWD, daq1, daq_ld, aq1, aq_ld, 0.f, wB, C, BT, C);  // dpa1 -> wB
+    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, s2>>>(VOP_RELU_BWD, daq2, daq_ld, aq2, aq2_ld, 0.f, wC, H, BT, H); // dpa2 -> wC
     KCHECK("dpa");
     count_launch(2);
-    col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, st>>>(vB, 0, C, nullptr, 0, 0, BT, C, G.a1_b, nullptr);
-    col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, st>>>(vC, 0, H, nullptr, 0, 0, BT, H, G.a2_b, nullptr);
+    col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, s2>>>(wB, 0, C, nullptr, 0, 0, BT, C, G.a1_b, nullptr);
+    col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, s2>>>(wC, 0, H, nullptr, 0, 0, BT, H, G.a2_b, nullptr);
     EpiOut e1 = eo(G.a1_w, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, MN_(vB, BT, C, C, 0), 0, MN_(vA, BT, C, C, 0), 0, C, C, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
+    RC(run_gemm(GS, MN_(wB, BT, C, C, 0), 0, MN_(wA, BT, C, C, 0), 0, C, C, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
     EpiOut e2 = eo(G.a2_w, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, MN_(vC, BT, H, H, 0), 0, MN_(vA, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
+    RC(run_gemm(GS, MN_(wC, BT, H, H, 0), 0, MN_(wA, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
     EpiOut e3 = eo(dobar, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, K_(vB, BT, C, C, 0), 0, MN_(P.a1_w, C, C, C, 0), 0, BT, C, C, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
-    RC(run_gemm(GS, K_(vC, BT, H, H, 0), 0, MN_(P.a2_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
+    RC(run_gemm(GS, K_(wB, BT, C, C, 0), 0, MN_(P.a1_w, C, C, C, 0), 0, BT, C, C, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
+    RC(run_gemm(GS, K_(wC, BT, H, H, 0), 0, MN_(P.a2_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
     if (d.flags & DGSCT_F_TEMPORAL) {
       count_launch();
-      temporal_bwd_kernel<<<BT, 128, 0, st>>>(use_tau ? dtau : nullptr, dtmap, tau, vA, P.t_w, C, dobar, G.t_w, G.t_b);
+      temporal_bwd_kernel<<<BT, 128, 0, s2>>>(use_tau ? dtau : nullptr, dtmap, tau, wA, P.t_w, C, dobar, G.t_w, G.t_b);
       KCHECK("temporal_bwd");
     }
   }
@@ -676,6 +678,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
     // d tokens += sum_b dTp[b]
+    RC(join_side2());                                                 // d obar (second vector chain) is needed from here on
     const void* dTpOp = dTp;
     long long dTp_bs = (long long)K * C;
     { StageScope _sc(ST_MISC, st); count_launch(2);
@@ -783,6 +786,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
                   to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e4), e4, AxIdentity{}, true));
     }
   }
+  RC(join_side2());
   RC(join_side());
   return DGSCT_OK;
 }

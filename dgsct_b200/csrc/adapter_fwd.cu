@@ -10,6 +10,7 @@
 #include "profile.h"
 #include "tc_epilogues.cuh"
 #include "rowwise.cuh"
+#include "side_stream.h"
 
 namespace dgsct {
 
@@ -74,6 +75,7 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
     p.packed = take(make_pack_plan(d).total);
     p.aq = take(BT * (C + H) * 4);
     p.vec_bf = take(BT * (size_t)pad8((int)C) * 2);
+    p.vec_bf_o = take(BT * (size_t)pad8((int)C) * 2);
     p.Qb = p.Pb;
     if (keep) { p.Qb = take(BT * N * K * 2); p.XcBuf = take(BT * N * C * 2); }
   }
@@ -486,6 +488,39 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     DGSCT_RC(gemm_auto(ST_RESAMPLE_FC, "resample_fc", true, kmaj(U, N, Co, Co, (long long)N * Co), kmaj(Wfc, C, Co, pp.ld_fc, 0),
                        N, C, Co, BT, te, se, st));
   }
+  float* aq = (float*)(ws + pl.aq);
+  bf16* vecb = (bf16*)(ws + pl.vec_bf);         // bf16 per-frame vectors of the channel-gate chain (q)
+  bf16* vecb_o = (bf16*)(ws + pl.vec_bf_o);     // bf16 obar (own buffer: written on the auxiliary stream)
+  const int ldv = pad8(C);
+  const float* aq1 = aq; const float* aq2 = aq + C; const int aq_ld = C + H;
+  // (C1) per-frame linears on tensor cores: [aq1 | aq2] = relu(obar [Wa1; Wa2]^T + b) ; tau stays SIMT (N = 1).
+  // They need only the column sums of V, and nothing needs them before the channel query: they run on an auxiliary stream
+  // underneath the latent-token attention.
+  SideStream* side = (prof_enabled() || getenv("DGSCT_NO_SIDE")) ? nullptr : side_stream_for(st, 2);
+  const cudaStream_t sx = side ? side->s : st;
+  auto c1_chain = [&]() -> int {
+    { StageScope _sc(ST_SMALL_LINEAR, sx); count_launch();
+      scale_to_bf16_kernel<<<ceil_div(BT * C, 256), 256, 0, sx>>>(osum, invN, vecb_o, (size_t)BT * C);
+      DGSCT_LAUNCH_CHECK("obar_bf16"); }
+    auto te = tc_store<false, false, false, ACT_RELU>(aq, aq_ld, 0);
+    te.bias_n = (const float*)(pk + pp.cat1_bias);
+    EpiBiasStore se = epi_store(aq, 0, aq_ld, 0); se.bias_n = te.bias_n; se.act = ACT_RELU;
+    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "aq12", true, kmaj(vecb_o, BT, C, C, 0), kmaj(pk + pp.cat1, C + H, C, pp.ld_c, 0),
+                       BT, C + H, C, 1, te, se, sx, 64));
+    if (d.flags & DGSCT_F_TEMPORAL) {
+      cudaStream_t st = sx;                       // (DGSCT_GEMM launches on `st`)
+      GemmShape sh3{BT, 1, C, 1, 1};
+      EpiBiasStore e3 = epi_store(tau, 0, 1, 0); e3.bias_n = P.t_b; e3.alpha = invN; e3.act = ACT_SIGMOID;
+      DGSCT_GEMM(ST_SMALL_LINEAR, sh3, op(osum, C, 1, 0, 0), op(P.t_w, C, 1, 0, 0), AxIdentity{}, e3, "tau");
+      if (tmap) DGSCT_CUDA_CHECK(cudaMemcpyAsync(tmap, tau, (size_t)BT * 4, cudaMemcpyDeviceToDevice, sx));
+    }
+    return DGSCT_OK;
+  };
+  if (side) {                                     // fork: osum is final
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, st));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->ev, 0));
+    DGSCT_RC(c1_chain());
+  }
   if (taps) DGSCT_RC(tap(V, 1, taps->V, (size_t)BT * N * C, st));
   const bool tok_tc = (K == 32);
   // (T1) L[b,n,k] = V[b,n,:] . tok[k,:]  (fp32) ; P = softmax over tokens (bf16)
@@ -542,28 +577,14 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
                        N, C, K, BT, te, se, st));
   }
   if (taps) DGSCT_RC(tap(X1, 1, taps->X1, (size_t)BT * N * C, st));
-  // (C1) per-frame linears on tensor cores: [aq1 | aq2] = relu(obar [Wa1; Wa2]^T + b) ; tau stays SIMT (N = 1)
-  float* aq = (float*)(ws + pl.aq);
-  bf16* vecb = (bf16*)(ws + pl.vec_bf);
-  const int ldv = pad8(C);
-  const float* aq1 = aq; const float* aq2 = aq + C; const int aq_ld = C + H;
-  {
-    { StageScope _sc(ST_SMALL_LINEAR, st); count_launch();
-      scale_to_bf16_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(osum, invN, vecb, (size_t)BT * C);
-      DGSCT_LAUNCH_CHECK("obar_bf16"); }
-    auto te = tc_store<false, false, false, ACT_RELU>(aq, aq_ld, 0);
-    te.bias_n = (const float*)(pk + pp.cat1_bias);
-    EpiBiasStore se = epi_store(aq, 0, aq_ld, 0); se.bias_n = te.bias_n; se.act = ACT_RELU;
-    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "aq12", true, kmaj(vecb, BT, C, C, 0), kmaj(pk + pp.cat1, C + H, C, pp.ld_c, 0),
-                       BT, C + H, C, 1, te, se, st, 64));
-    if (d.flags & DGSCT_F_TEMPORAL) {
-      GemmShape sh3{BT, 1, C, 1, 1};
-      EpiBiasStore e3 = epi_store(tau, 0, 1, 0); e3.bias_n = P.t_b; e3.alpha = invN; e3.act = ACT_SIGMOID;
-      DGSCT_GEMM(ST_SMALL_LINEAR, sh3, op(osum, C, 1, 0, 0), op(P.t_w, C, 1, 0, 0), AxIdentity{}, e3, "tau");
-      if (tmap) DGSCT_CUDA_CHECK(cudaMemcpyAsync(tmap, tau, (size_t)BT * 4, cudaMemcpyDeviceToDevice, st));
-    }
-    if (taps && taps->obar) DGSCT_RC(tap(osum, 0, taps->obar, (size_t)BT * C, st));
+  // (C1) joins here: [aq1 | aq2] (and tau) were computed on the auxiliary stream underneath the token attention
+  if (side) {
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, side->s));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev, 0));
+  } else {
+    DGSCT_RC(c1_chain());
   }
+  if (taps && taps->obar) DGSCT_RC(tap(osum, 0, taps->obar, (size_t)BT * C, st));
   // (C2) qsum[b,c] = sum_n aq1[b,c] relu(X1[b,n,:] . Wv1[c,:] + b)
   {
     tc::EpiReluMulColsum te{P.v1_b, nullptr, qsum, C, aq_ld};     // r1sum[b,c] = sum_n relu(z1), unscaled

@@ -11,7 +11,7 @@ struct FwdPlan {
   size_t aq1, aq2, h, m, tau, sig, bn1_scale, bn1_shift, bn2_scale, bn2_shift;
   size_t csm_part;                                // column-softmax partials (BT, chunks, 2, K) fp32
   size_t fc_s;                                    // row sums of fc.weight (C) fp32 (re-associated resampler, DGSCT_FC_FIRST)
-  size_t Pb, TpB, Zr, Uo32, packed, aq, vec_bf;   // tensor-core path: bf16 P, bf16 latent tokens, bf16 relu(bn1(Z)), fp32 up-sampler
+  size_t Pb, TpB, Zr, Uo32, packed, aq, vec_bf, vec_bf_o;   // tensor-core path: bf16 P, bf16 latent tokens, bf16 relu(bn1(Z)), fp32 up-sampler
                                                   // output, packed weights, [aq1 | aq2] fp32 (BT, C+H), bf16 per-frame vectors
   // Regions that alias others unless the plan is built with keep = true (training forward: everything the
   // backward needs survives the call): Y (else the V buffer), Q fp32 / bf16 (else the P buffers), Xc (else U).

@@ -163,6 +163,26 @@ int dgsct_adapter_bwd_saved(const dgsct_desc *desc, const dgsct_params *params, 
                             const void *d_spatial_map, const float *d_temporal_map, void *dx, void *dother,
                             const dgsct_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
+/* the two ops directly behind the adapters in the task networks.
+ *   dgsct_pool_tokens_*     out (BT,C) = sum_n spatial_map[b,n] f[b,n,c]  -- torch.bmm(spatial_att_maps, f) of
+ *                           DG-SCT/AVE/nets/net_trans.py:922,924 (the adapter's second return value pools the tokens);
+ *                           bwd writes d_map (BT,N) and / or d_f (BT,N,C) (either may be NULL)
+ *   dgsct_temporal_gates_*  the sigmoid gates closing TemporalAttention.forward (net_trans.py:243-249): rows = T*B rows of
+ *                           D channels; a_kv / v_kv = encoder outputs, vq / aq = decoder outputs; wa, ba, wv, bv = the
+ *                           audio_gated.0 / video_gated.0 Linear(D,1) parameters (fp32); `gates` (rows,2) fp32 keeps
+ *                           (audio_gate, video_gate) for the backward; parameter gradients are ADDED.
+ * activations are io_dtype (dgsct_dtype). */
+int dgsct_pool_tokens_fwd(const void *spatial_map, const void *f, void *out, int BT, int N, int C, int io_dtype, void *stream);
+int dgsct_pool_tokens_bwd(const void *spatial_map, const void *f, const void *d_out, void *d_map, void *d_f, int BT, int N, int C,
+                          int io_dtype, void *stream);
+int dgsct_temporal_gates_fwd(const void *a_kv, const void *v_kv, const void *vq, const void *aq, const float *wa, const float *ba,
+                             const float *wv, const float *bv, float gamma, void *vq_out, void *aq_out, void *av_gate, float *gates,
+                             int rows, int D, int io_dtype, void *stream);
+int dgsct_temporal_gates_bwd(const void *a_kv, const void *v_kv, const void *vq, const void *aq, const float *wa, const float *wv,
+                             float gamma, const float *gates, const void *d_vq_out, const void *d_aq_out, const void *d_av_gate,
+                             void *d_a_kv, void *d_v_kv, void *d_vq, void *d_aq, float *d_wa, float *d_ba, float *d_wv, float *d_bv,
+                             int rows, int D, int io_dtype, void *stream);
+
 /* Optimizer over FLAT buffers (the gradient buckets of the data-parallel wrapper): torch.optim.Adam semantics
  * (DG-SCT/AVE/main_trans.py:276: Adam over the trainable adapter parameters), one fused kernel per bucket.
  *   dgsct_adam_tick   increments the device-resident step counter (once per optimizer step; graph-capturable)
