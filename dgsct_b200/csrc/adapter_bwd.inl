@@ -285,7 +285,7 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   { size_t gu = BT * N * Co;                           // dU (BT,N,Co), or dO' (BT,No,C) of the re-associated resampler
     if (BT * (size_t)d.No * C > gu) gu = BT * (size_t)d.No * C;
     p.gU = take(gu * es); }
-  p.gQ = take(BT * N * K * es);          // dQraw -> dL2 ; later dL1
+  p.gQ = take(BT * N * (size_t)pad8((int)K) * es);   // dQraw -> dL2 ; later dL1 (bf16 rows padded to 16 bytes)
   p.gP = take(BT * N * K * 4);           // dP fp32
   p.dTp = take(BT * K * C * 4);
   p.dTpB = take(BT * K * C * 2);
@@ -341,6 +341,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   const void* U = fw + fp.bufA; const void* V = fw + fp.bufV; const void* X1 = fw + fp.bufX1; const void* Y = fw + fp.Ybuf;
   const void* Pm = tcp ? (const void*)(fw + fp.Pb) : (const void*)(fw + fp.bufL);
   const void* Qm = tcp ? (const void*)(fw + fp.Qb) : (const void*)(fw + fp.Qf);
+  const int ldq = tcp ? pad8(K) : K;                  // row pitch of P, Q, dQ / dL1 (bf16 rows are padded to 16 bytes)
+  const long long sbq = (long long)N * ldq;
   const float* Tp = (const float*)(fw + fp.Tp); const void* TpOp = tcp ? (const void*)(fw + fp.TpB) : (const void*)Tp;
   const float* Z = (const float*)(fw + fp.Z); const float* Uo = (const float*)(fw + fp.Uo32);
   const float* osum = (const float*)(fw + fp.osum); const float* r1sum = (const float*)(fw + fp.r1sum);
@@ -660,22 +662,22 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   // ---- 7. latent-token attention -----------------------------------------------------------------------------------
   {
     // dQraw = G . Tp^T -> gQ ; dL2 (in place) ; d_gate_av
-    EpiOut e1 = eo(gQ, bf, K, (long long)N * K, OUT_STORE);
+    EpiOut e1 = eo(gQ, bf, ldq, sbq, OUT_STORE);
     RC(run_gemm(G_TK, K_(gX1, N, C, C, (long long)N * C), bf, K_(TpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
     { StageScope _sc(ST_ROW_SOFTMAX, st); count_launch();
-      row_softmax_bwd_kernel<<<rgrid, 256, 0, st>>>(gQ, Qm, bf, R, K, P.gate_av, G.gate_av);
+      row_softmax_bwd_kernel<<<rgrid, 256, 0, st>>>(gQ, Qm, bf, R, K, ldq, P.gate_av, G.gate_av);
       KCHECK("row_softmax_bwd"); }
     // dTp[b,k,c] = g sum_n Q G + sum_n dL2 x     (computed as D(c,k), written transposed)
     EpiOut e2 = eo(dTp, 0, C, (long long)K * C, OUT_STORE); e2.transposed = 1; e2.alpha_ptr = P.gate_av;
-    RC(run_gemm(G_TK, MN_(gX1, N, C, C, (long long)N * C), bf, MN_(Qm, N, K, K, (long long)N * K), bf, C, K, N, BT,
+    RC(run_gemm(G_TK, MN_(gX1, N, C, C, (long long)N * C), bf, MN_(Qm, N, K, ldq, sbq), bf, C, K, N, BT,
                 to_tcT<tc::EpiOutT<OUT_STORE>>(e2), e2, AxIdentity{}, true));
     EpiOut e3 = eo(dTp, 0, C, (long long)K * C, OUT_ADD); e3.transposed = 1;
-    RC(run_gemm(G_TK, MN_(x, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, K, (long long)N * K), bf, C, K, N, BT,
+    RC(run_gemm(G_TK, MN_(x, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, ldq, sbq), bf, C, K, N, BT,
                 to_tcT<tc::EpiOutT<OUT_ADD>>(e3), e3, AxIdentity{}, true));
     // dx = G + dL2 . Tp
     EpiOut e4 = eo(dx, bf, C, (long long)N * C, OUT_STORE); e4.resid = gX1; e4.resid_bf16 = bf;
-    RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+    RC(run_gemm(G_TK, K_(gQ, N, K, ldq, sbq), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                 to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
     // d tokens += sum_b dTp[b]
     RC(join_side2());                                                 // d obar (second vector chain) is needed from here on
@@ -694,17 +696,17 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       { const dim3 grid(csm_num_chunks(N), BT);
         float* part = (float*)(ws + bp.csm_part);
         count_launch();
-        col_softmax_bwd_partial_kernel<<<grid, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, part, N, K);
-        col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K); }
+        col_softmax_bwd_partial_kernel<<<grid, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, part, N, K, ldq);
+        col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K, ldq); }
       KCHECK("col_softmax_bwd"); }
     // dV = P . dTp + dL1 . T + dobar / N
     EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
-    const void* dL1 = gQ; long long dL1_ld = K, dL1_bs = (long long)N * K;
+    const void* dL1 = gQ; long long dL1_ld = ldq, dL1_bs = sbq;
     {
-      RC(run_gemm(G_TK, K_(Pm, N, K, K, (long long)N * K), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+      RC(run_gemm(G_TK, K_(Pm, N, K, ldq, sbq), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
                   to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
       EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
-      RC(run_gemm(G_TK, K_(gQ, N, K, K, (long long)N * K), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
+      RC(run_gemm(G_TK, K_(gQ, N, K, ldq, sbq), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
                   to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
     }
     // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)

@@ -66,7 +66,8 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
     if (d.io_dtype != DGSCT_BF16) p.Uo32 = take(BT * N * C * 4);
   }
   if (d.io_dtype == DGSCT_BF16) {
-    p.Pb = take(BT * N * K * 2);
+    const size_t Kp = (size_t)pad8((int)K);            // bf16 P / Q rows padded to 16 bytes (TMA-describable for any K)
+    p.Pb = take(BT * N * Kp * 2);
     p.csm_part = take(BT * (size_t)CSM_MAX_CHUNKS * 2 * K * 4);
     p.fc_s = take(C * 4);
     p.TpB = take(BT * K * C * 2);
@@ -77,7 +78,7 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
     p.vec_bf = take(BT * (size_t)pad8((int)C) * 2);
     p.vec_bf_o = take(BT * (size_t)pad8((int)C) * 2);
     p.Qb = p.Pb;
-    if (keep) { p.Qb = take(BT * N * K * 2); p.XcBuf = take(BT * N * C * 2); }
+    if (keep) { p.Qb = take(BT * N * Kp * 2); p.XcBuf = take(BT * N * C * 2); }
   }
   p.total = off;
   return p;
@@ -522,7 +523,8 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     DGSCT_RC(c1_chain());
   }
   if (taps) DGSCT_RC(tap(V, 1, taps->V, (size_t)BT * N * C, st));
-  const bool tok_tc = (K == 32);
+  const bool tok_tc = true;                 // any K: P / Q pitches are padded, ragged N / K edges are TMA zero fill
+  const int Kp = pad8(K);
   // (T1) L[b,n,k] = V[b,n,:] . tok[k,:]  (fp32) ; P = softmax over tokens (bf16)
   {
     auto te = tc_store<false>(L, K, (long long)N * K);
@@ -536,7 +538,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
       float* part = (float*)(ws + pl.csm_part);
       count_launch();
       col_softmax_partial_kernel<<<grid, 256, (size_t)2 * groups * K * 4, st>>>(L, part, N, K);
-      col_softmax_apply_kernel<<<grid, 256, 0, st>>>(L, part, Pb, N, K);
+      col_softmax_apply_kernel<<<grid, 256, 0, st>>>(L, part, Pb, N, K, Kp);
     } else {
       return DGSCT_ERR_UNSUPPORTED;
     }
@@ -547,33 +549,33 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     tc::EpiTokUpdate te{TpB, Tp, P.tokens, C, K};
     // SIMT twin computes the same D(c,k) orientation: rows m = c, columns n = k
     SimtTokUpdate se{TpB, Tp, P.tokens, C, K};
-    DGSCT_RC(gemm_auto(ST_TOK_UPDATE, "tok_update", tok_tc, mnmaj(V, N, C, C, (long long)N * C), mnmaj(Pb, N, K, K, (long long)N * K),
+    DGSCT_RC(gemm_auto(ST_TOK_UPDATE, "tok_update", tok_tc, mnmaj(V, N, C, C, (long long)N * C), mnmaj(Pb, N, K, Kp, (long long)N * Kp),
                        C, K, N, BT, te, se, st));
   }
   if (taps && taps->Tp) DGSCT_RC(tap(Tp, 0, taps->Tp, (size_t)BT * K * C, st));
   // (T4a) Q[b,n,:] = softmax_k(x[b,n,:] . Tp[b,k,:])  (bf16, reuses the P buffer)
-  if (tok_tc) {
-    tc::EpiRowSoftmax32 te{}; te.out = Qb; te.ld = K; te.sb = (long long)N * K;
+  if (K == 32) {
+    tc::EpiRowSoftmax32 te{}; te.out = Qb; te.ld = Kp; te.sb = (long long)N * Kp;
     EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);   // unused twin (operands are always TMA-describable here)
     DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", true, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
                        N, K, C, BT, te, se, st));
   } else {
     auto te = tc_store<false>(L, K, (long long)N * K);
     EpiBiasStore se = epi_store(L, 0, K, (long long)N * K);
-    DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", false, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
+    DGSCT_RC(gemm_auto(ST_X_LOGITS, "x_logits", true, kmaj(x, N, C, C, (long long)N * C), kmaj(TpB, K, C, C, (long long)K * C),
                        N, K, C, BT, te, se, st));
     StageScope _sc(ST_ROW_SOFTMAX, st); count_launch(2);
     row_softmax_kernel<<<(unsigned)((rowsBT + 7) / 8), 256, 0, st>>>(L, rowsBT, K);
     // Q as bf16 for the next product
     pack_rows_kernel<<<(unsigned)(((size_t)rowsBT * K + 255) / 256 > 4096 ? 4096 : ((size_t)rowsBT * K + 255) / 256), 256, 0, st>>>(
-        L, (int)rowsBT, K, Qb, K);
+        L, (int)rowsBT, K, Qb, Kp);
     DGSCT_LAUNCH_CHECK("row_softmax");
   }
   // (T4b) X1 = x + gate_av * Q . Tp
   {
     tc::EpiResidual te{X1, (const bf16*)x, C, (long long)N * C, P.gate_av, 0.f};
     EpiResidual se{X1, x, 1, C, (long long)N * C, P.gate_av};
-    DGSCT_RC(gemm_auto(ST_X_UPDATE, "x_update", tok_tc, kmaj(Qb, N, K, K, (long long)N * K), mnmaj(TpB, K, C, C, (long long)K * C),
+    DGSCT_RC(gemm_auto(ST_X_UPDATE, "x_update", tok_tc, kmaj(Qb, N, K, Kp, (long long)N * Kp), mnmaj(TpB, K, C, C, (long long)K * C),
                        N, C, K, BT, te, se, st));
   }
   if (taps) DGSCT_RC(tap(X1, 1, taps->X1, (size_t)BT * N * C, st));

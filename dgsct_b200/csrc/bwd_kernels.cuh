@@ -356,19 +356,20 @@ __global__ void vec_op_kernel(int op, const float* g, int g_ld, const float* __r
 
 // ---- token attention backward helpers ----------------------------------------------------------------------------
 // rows of (R,K): dL2 = Q*(g*dQraw - sum_k g*dQraw*Q) in place on dq ; d_gate_av += sum Q*dQraw
-__global__ void row_softmax_bwd_kernel(void* __restrict__ dq, const void* __restrict__ q, int bf, long long rows, int K,
+// (ld = row pitch of dq and q, >= K)
+__global__ void row_softmax_bwd_kernel(void* __restrict__ dq, const void* __restrict__ q, int bf, long long rows, int K, int ld,
                                        const float* __restrict__ gate_av, float* __restrict__ d_gate_av) {
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float g = gate_av[0];
   float gacc = 0.f;
   for (long long row = (long long)blockIdx.x * warps + warp; row < rows; row += (long long)gridDim.x * warps) {
     float dot = 0.f;
-    for (int k = lane; k < K; k += 32) dot += ld_act(dq, (size_t)(row * K + k), bf) * ld_act(q, (size_t)(row * K + k), bf);
+    for (int k = lane; k < K; k += 32) dot += ld_act(dq, (size_t)(row * ld + k), bf) * ld_act(q, (size_t)(row * ld + k), bf);
     dot = warp_sum(dot);
     gacc += (lane == 0) ? dot : 0.f;
     for (int k = lane; k < K; k += 32) {
-      const float qq = ld_act(q, (size_t)(row * K + k), bf);
-      st_act(dq, (size_t)(row * K + k), g * qq * (ld_act(dq, (size_t)(row * K + k), bf) - dot), bf);
+      const float qq = ld_act(q, (size_t)(row * ld + k), bf);
+      st_act(dq, (size_t)(row * ld + k), g * qq * (ld_act(dq, (size_t)(row * ld + k), bf) - dot), bf);
     }
   }
   if (lane == 0 && d_gate_av && gacc != 0.f) atomicAdd(d_gate_av, gacc);
@@ -377,8 +378,9 @@ __global__ void row_softmax_bwd_kernel(void* __restrict__ dq, const void* __rest
 // per frame, columns of (N,K): dL1 = P*(dP - sum_n dP*P)   (dP fp32 in, dL1 act dtype out)
 // Two kernels over a (row-chunk, frame) grid like the forward's column softmax (a frame per block would leave half of
 // the SMs idle at BT = 80): per-chunk partial dot products, then combine + apply.
+// (dP is fp32 with pitch K; P and dL1 have pitch ldp >= K)
 __global__ void __launch_bounds__(256) col_softmax_bwd_partial_kernel(const float* __restrict__ dP, const void* __restrict__ P, int p_bf,
-                                                                      float* __restrict__ part, int N, int K) {
+                                                                      float* __restrict__ part, int N, int K, int ldp) {
   extern __shared__ float sm[];             // [groups][K]
   const int s_ = blockIdx.x, b = blockIdx.y, S = gridDim.x;
   const int groups = blockDim.x / K;
@@ -386,10 +388,10 @@ __global__ void __launch_bounds__(256) col_softmax_bwd_partial_kernel(const floa
   const bool active = g < groups;
   const int rows = csm_chunk_rows(N);
   const int n0 = s_ * rows, n1 = min(N, n0 + rows);
-  const size_t base = (size_t)b * N * K;
+  const size_t base = (size_t)b * N * K, basep = (size_t)b * N * ldp;
   float acc = 0.f;
   if (active) {
-    for (int n = n0 + g; n < n1; n += groups) acc += dP[base + (size_t)n * K + k] * ld_act(P, base + (size_t)n * K + k, p_bf);
+    for (int n = n0 + g; n < n1; n += groups) acc += dP[base + (size_t)n * K + k] * ld_act(P, basep + (size_t)n * ldp + k, p_bf);
     sm[g * K + k] = acc;
   }
   __syncthreads();
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(256) col_softmax_bwd_partial_kernel(const floa
 }
 __global__ void __launch_bounds__(256) col_softmax_bwd_apply_kernel(const float* __restrict__ dP, const void* __restrict__ P, int p_bf,
                                                                     const float* __restrict__ part, void* __restrict__ dL1, int out_bf,
-                                                                    int N, int K) {
+                                                                    int N, int K, int ldp) {
   const int s_ = blockIdx.x, b = blockIdx.y, S = gridDim.x;
   const int groups = blockDim.x / K;
   const int k = threadIdx.x % K, g = threadIdx.x / K;
@@ -410,10 +412,10 @@ __global__ void __launch_bounds__(256) col_softmax_bwd_apply_kernel(const float*
   for (int j = 0; j < S; ++j) t += part[((size_t)b * S + j) * K + k];
   const int rows = csm_chunk_rows(N);
   const int n0 = s_ * rows, n1 = min(N, n0 + rows);
-  const size_t base = (size_t)b * N * K;
+  const size_t base = (size_t)b * N * K, basep = (size_t)b * N * ldp;
   for (int n = n0 + g; n < n1; n += groups) {
-    const size_t i = base + (size_t)n * K + k;
-    st_act(dL1, i, ld_act(P, i, p_bf) * (dP[i] - t), out_bf);
+    const size_t i = base + (size_t)n * K + k, ip = basep + (size_t)n * ldp + k;
+    st_act(dL1, ip, ld_act(P, ip, p_bf) * (dP[i] - t), out_bf);
   }
 }
 

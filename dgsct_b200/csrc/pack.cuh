@@ -209,8 +209,9 @@ __global__ void __launch_bounds__(256) col_softmax_partial_kernel(const float* _
     o[K + k] = Z;
   }
 }
+// (P has row pitch ldp >= K: pitches are padded to 16 bytes so that TMA can describe P for any K, e.g. AVQA's K = 2)
 __global__ void __launch_bounds__(256) col_softmax_apply_kernel(const float* __restrict__ L, const float* __restrict__ part,
-                                                                bf16* __restrict__ P, int N, int K) {
+                                                                bf16* __restrict__ P, int N, int K, int ldp) {
   const int s = blockIdx.x, b = blockIdx.y, S = gridDim.x;
   const int groups = blockDim.x / K;
   const int k = threadIdx.x % K, g = threadIdx.x / K;
@@ -227,9 +228,9 @@ __global__ void __launch_bounds__(256) col_softmax_apply_kernel(const float* __r
   const int rows = csm_chunk_rows(N);
   const int n0 = s * rows, n1 = min(N, n0 + rows);
   const float* base = L + (size_t)b * N * K;
-  bf16* out = P + (size_t)b * N * K;
+  bf16* out = P + (size_t)b * N * ldp;
   for (int n = n0 + g; n < n1; n += groups)
-    out[(size_t)n * K + k] = __float2bfloat16_rn(__expf(base[(size_t)n * K + k] - M) * inv);
+    out[(size_t)n * ldp + k] = __float2bfloat16_rn(__expf(base[(size_t)n * K + k] - M) * inv);
 }
 
 }  // namespace dgsct
