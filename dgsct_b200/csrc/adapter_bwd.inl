@@ -502,7 +502,11 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     if (use_bn) {
       DGSCT_CUDA_CHECK(cudaMemsetAsync(colA, 0, (size_t)C * 4, st));
       DGSCT_CUDA_CHECK(cudaMemsetAsync(colB, 0, (size_t)C * 4, st));
-      col_reduce_kernel<<<dim3(ceil_div(Cd, 32), 64), 256, 0, st>>>(gZ, bf, ldz, Z, 0, Cd, R, Cd, colA, colB);
+      { const int gx = ceil_div(Cd, 32);                      // narrow (C/r columns): spread the rows over ~4 blocks per SM
+        long long gy = (R + 255) / 256;
+        if (gy > (148 * 4) / gx) gy = (148 * 4) / gx;
+        if (gy < 1) gy = 1;
+        col_reduce_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(gZ, bf, ldz, Z, 0, Cd, R, Cd, colA, colB); }
       bn_bwd_coeffs_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, 1, train, colA, colB, (const float*)(fw + fp.bn1_mean),
                                                               (const float*)(fw + fp.bn1_rstd), P.bn1_w, (double)R, coefA, coefB, coefC,
                                                               G.bn1_w, G.bn1_b);
@@ -739,9 +743,12 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
                   to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e3), e3, AxIdentity{}, true, 0, true));
     }
     if (has_bias && G.resample_b) {
-      StageScope _sc(ST_MISC, sst); count_launch(2);
-      rowsum_frames_weighted_kernel<<<N, 256, 0, sst>>>(gV, bf, BT, N, C, fcs, G.resample_b);
-      col_reduce_rowweight_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, R, N, C, P.resample_b, fct);
+      StageScope _sc(ST_MISC, sst); count_launch();
+      if (!launch_dv_bias_sums(gV, bf, R, N, C, fcs, P.resample_b, G.resample_b, fct, sst)) {
+        count_launch();
+        rowsum_frames_weighted_kernel<<<N, 256, 0, sst>>>(gV, bf, BT, N, C, fcs, G.resample_b);
+        col_reduce_rowweight_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, sst>>>(gV, bf, R, N, C, P.resample_b, fct);
+      }
       KCHECK("dres_b_reassoc");
     }
     // dother[b] (No,Co) = dO'[b] . Wfc ; side: dWfc += sum_b dO'_b^T . other_b (+ t broadcast over co)

@@ -308,24 +308,32 @@ int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaSt
   const PackPlan pp = make_pack_plan(d);
   const int N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2;
   StageScope _sc(ST_MISC, st);
-  auto rows = [&](const float* src, int r, int c, size_t off, int ld) {
-    const size_t n = (size_t)r * ld;
-    count_launch();
-    pack_rows_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, st>>>(src, r, c, (bf16*)(packed + off), ld);
+  PackTable t{};
+  size_t biggest = 0;
+  auto seg = [&](int kind, const float* src, const float* src2, size_t off, int r, int c, int ld, int g) {
+    PackSeg& e = t.seg[t.n++];
+    e.src = src; e.src2 = src2; e.dst = packed + off; e.kind = kind; e.rows = r; e.cols = c; e.ld = ld; e.groups = g;
+    const size_t n = kind == 2 ? (size_t)(r + c) : (size_t)r * ld;
+    if (n > biggest) biggest = n;
   };
-  if (P.resample_w) rows(P.resample_w, N, No, pp.res, pp.ld_res);
-  rows(P.fc_w, C, Co, pp.fc, pp.ld_fc);
-  rows(P.tokens, K, C, pp.tok, pp.ld_c);
-  rows(P.v1_w, C, C, pp.v1, pp.ld_c);
-  rows(P.v2_w, H, C, pp.v2, pp.ld_c);
-  rows(P.a1_w, C, C, pp.cat1, pp.ld_c);
-  rows(P.a2_w, H, C, pp.cat1 + (size_t)C * pp.ld_c * 2, pp.ld_c);
-  rows(P.bott_w, H, C, pp.bott, pp.ld_c);
-  rows(P.c_w, C, H, pp.catt, pp.ld_h);
-  count_launch(3);
-  concat2_f32_kernel<<<ceil_div(C + H, 256), 256, 0, st>>>(P.a1_b, C, P.a2_b, H, (float*)(packed + pp.cat1_bias));
-  pack_grouped_kernel<<<ceil_div(Cd * pp.ld_c, 256), 256, 0, st>>>(P.down_w, Cd, C, d.g, (bf16*)(packed + pp.down), pp.ld_c);
-  pack_grouped_kernel<<<ceil_div(C * pp.ld_up, 256), 256, 0, st>>>(P.up_w, C, Cd, d.g, (bf16*)(packed + pp.up), pp.ld_up);
+  seg(0, P.resample_w, nullptr, pp.res, N, No, pp.ld_res, 1);      // (NULL with the sparse resampler: the segment is skipped)
+  seg(0, P.fc_w, nullptr, pp.fc, C, Co, pp.ld_fc, 1);
+  seg(0, P.tokens, nullptr, pp.tok, K, C, pp.ld_c, 1);
+  seg(0, P.v1_w, nullptr, pp.v1, C, C, pp.ld_c, 1);
+  seg(0, P.v2_w, nullptr, pp.v2, H, C, pp.ld_c, 1);
+  seg(0, P.a1_w, nullptr, pp.cat1, C, C, pp.ld_c, 1);
+  seg(0, P.a2_w, nullptr, pp.cat1 + (size_t)C * pp.ld_c * 2, H, C, pp.ld_c, 1);
+  seg(0, P.bott_w, nullptr, pp.bott, H, C, pp.ld_c, 1);
+  seg(0, P.c_w, nullptr, pp.catt, C, H, pp.ld_h, 1);
+  seg(2, P.a1_b, P.a2_b, pp.cat1_bias, C, H, 0, 1);
+  seg(1, P.down_w, nullptr, pp.down, Cd, C, pp.ld_c, d.g);
+  seg(1, P.up_w, nullptr, pp.up, C, Cd, pp.ld_up, d.g);
+  count_launch();
+  // the x extent covers the LARGEST segment with ~8 elements per thread; small segments finish in their first blocks
+  size_t bx = (biggest + 256 * 8 - 1) / (256 * 8);
+  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx < 1) bx = 1;
+  pack_all_kernel<<<dim3((unsigned)bx, t.n), 256, 0, st>>>(t);
   DGSCT_LAUNCH_CHECK("pack_params");
   return DGSCT_OK;
 }
@@ -339,7 +347,7 @@ static int gemm_auto(int stage, const char* name, bool allow_tc, const tc::Opera
   if (allow_tc) {
     tc::Params p;
     const int rc = tc::make_params(p, A, B, M, N, K, batch, bn_hint, 0, false, tc::epi_row_independent<TE>::value,
-                                   tc::epi_stage_bytes<TE>::value);
+                                   tc::epi_stage_bytes<TE>::value, tc::epi_block_stats<TE>::value ? 1 : 0);
     if (rc == DGSCT_OK) {
       cudaError_t e = tc::launch(p, te, st);
       if (e != cudaSuccess) { set_cuda_error(e, name); return DGSCT_ERR_CUDA; }

@@ -3,6 +3,7 @@
 // gradient is accumulated in fp32.  Column reductions are staged in shared memory per block and flushed with
 // one global atomicAdd per column per block.
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dgsct {
@@ -480,6 +481,74 @@ __global__ void rowsum_frames_kernel(const void* __restrict__ du, int bf, int BT
   if (threadIdx.x == 0) atomicAdd(&out[n], s);
 }
 
+// ---- re-associated resampler: both bias-related reductions of dV in ONE pass -------------------------------------------------
+//   d_bres[n] += sum_{b,c} dV[b,n,c] * s[c]          (s = row sums of fc.weight)
+//   t[c]      += sum_{b,n} dV[b,n,c] * b_res[n]      (rank-1 part of d fc.weight, added by add_col_broadcast_kernel)
+// One warp per row, lanes stride over 16-byte vectors; the column sums stay in registers across the rows a warp visits (<= 6
+// vectors per lane: C <= 1536) and are flushed once per warp.  Replaces two kernels that each read dV completely.
+template <int VPL>
+__global__ void __launch_bounds__(256) dv_bias_sums_kernel(const bf16* __restrict__ dv, long long rows, int N, int C,
+                                                           const float* __restrict__ s, const float* __restrict__ b_res,
+                                                           float* __restrict__ d_bres, float* __restrict__ t) {
+  const int lane = threadIdx.x & 31, nvec = C >> 3;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  float sv[VPL][8], acc[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[i][j] = 0.f; sv[i][j] = (vi < nvec) ? s[vi * 8 + j] : 0.f; }
+  }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float br = b_res[(int)(row % N)];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dv + row * C + vi * 8));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[q]);
+          const float a = __bfloat162float(h.x), b = __bfloat162float(h.y);
+          dot = fmaf(a, sv[i][2 * q], fmaf(b, sv[i][2 * q + 1], dot));
+          acc[i][2 * q] = fmaf(a, br, acc[i][2 * q]);
+          acc[i][2 * q + 1] = fmaf(b, br, acc[i][2 * q + 1]);
+        }
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) atomicAdd(&d_bres[(int)(row % N)], dot);
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&t[vi * 8 + j], acc[i][j]);
+    }
+  }
+}
+// returns false when the shape is outside the vector kernel's range (C % 8, C > 1536): the caller runs the two scalar kernels
+inline bool launch_dv_bias_sums(const void* dv, int bf, long long rows, int N, int C, const float* s, const float* b_res, float* d_bres,
+                                float* t, cudaStream_t st) {
+  if (!bf || C % 8 || C > 1536) return false;
+  const int nvec = C / 8, vpl = (nvec + 31) / 32;
+  long long blocks = (rows + 63) / 64;             // >= 8 rows per warp
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  const bf16* p = reinterpret_cast<const bf16*>(dv);
+  switch (vpl) {
+    case 1: dv_bias_sums_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
+    case 2: dv_bias_sums_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
+    case 3: dv_bias_sums_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
+    case 4: dv_bias_sums_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
+    default: dv_bias_sums_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
+  }
+  return true;
+}
+
 // ---- re-associated resampler (DGSCT_FC_FIRST): the rank-1 bias term b_res[n] * s[c] of V --------------------------------
 // d_bres[n] += sum_{b,c} dV[b,n,c] * s[c]
 __global__ void rowsum_frames_weighted_kernel(const void* __restrict__ dv, int bf, int BT, int N, int C, const float* __restrict__ s,
@@ -579,7 +648,7 @@ __device__ __forceinline__ float rowgroups_sum(float v) {      // sum over the 3
 // out = gate * LN_post(B2) [AVE] or LN_post(gate * B2) [AVS], B2 = uo*scale + shift.  Also accumulates the bn2-backward
 // column sums colA[c] += sum dB2, colB[c] += sum dB2*uo (NULL to skip) so that no separate reduction pass is needed.
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256, 1) bwd_out_vec_kernel(BwdOutArgs a, float* __restrict__ colA, float* __restrict__ colB) {
+__global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_out_vec_kernel(BwdOutArgs a, float* __restrict__ colA, float* __restrict__ colB) {
   extern __shared__ float sm[];                 // [4][C] block partials: d_lnw, d_lnb, colA, colB
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR;
@@ -719,7 +788,7 @@ __global__ void __launch_bounds__(256, 1) bwd_out_vec_kernel(BwdOutArgs a, float
 // LN_before + gate-combine backward; grid (row chunks, BT): a block stays inside one frame, so the channel-gate gradient
 // dm[b, c] is a per-lane register sum as well.
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256, 1) bwd_gate_ln_vec_kernel(BwdGateLnArgs a, int rows_per_chunk) {
+__global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kernel(BwdGateLnArgs a, int rows_per_chunk) {
   extern __shared__ float sm[];                 // [3][C] block partials: d_lnw, d_lnb, dm
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR;
@@ -857,7 +926,7 @@ struct BwdOutLaunch {
     if (VPL > 4) { *ok = false; return; }
     const long long rows_per_block = 8LL * (32 / LPR);
     long long blocks = (a.rows + rows_per_block - 1) / rows_per_block;
-    if (blocks > 2 * 148) blocks = 2 * 148;
+    if (blocks > 2 * 148) blocks = 2 * 148;              // every block resident (1 or 2 per SM): one flush per block
     bwd_out_vec_kernel<LPR, (VPL > 4 ? 1 : VPL)><<<(unsigned)blocks, 256, (size_t)4 * a.C * 4, st>>>(a, colA, colB);
     *ok = true;
   }
@@ -866,7 +935,9 @@ struct BwdOutLaunch {
 inline bool launch_bwd_out_vec(const BwdOutArgs& a, float* colA, float* colB, cudaStream_t st) {
   if (a.C % 8 || !a.dout_bf16 || !a.db2_bf16 || a.C > 2048) return false;
   bool ok = false;
-  if (!dispatch_row_geometry(a.C / 8, BwdOutLaunch{a, colA, colB, st, &ok})) return false;
+  static const bool heavy = getenv("DGSCT_ROW_HEAVY") != nullptr;       // round-1 geometry (A/B switch)
+  if (!heavy && a.C <= 1024) { if (!dispatch_row_geometry_light(a.C / 8, BwdOutLaunch{a, colA, colB, st, &ok})) return false; }
+  else if (!dispatch_row_geometry(a.C / 8, BwdOutLaunch{a, colA, colB, st, &ok})) return false;
   return ok;
 }
 
@@ -889,7 +960,9 @@ struct BwdGateLnLaunch {
 inline bool launch_bwd_gate_ln_vec(const BwdGateLnArgs& a, int BT, cudaStream_t st) {
   if (a.C % 8 || !a.dy_bf16 || !a.x1_bf16 || !a.dx1_bf16 || a.C > 2048) return false;
   bool ok = false;
-  if (!dispatch_row_geometry(a.C / 8, BwdGateLnLaunch{a, BT, st, &ok})) return false;
+  static const bool heavy = getenv("DGSCT_ROW_HEAVY") != nullptr;
+  if (!heavy && a.C <= 1024) { if (!dispatch_row_geometry_light(a.C / 8, BwdGateLnLaunch{a, BT, st, &ok})) return false; }
+  else if (!dispatch_row_geometry(a.C / 8, BwdGateLnLaunch{a, BT, st, &ok})) return false;
   return ok;
 }
 

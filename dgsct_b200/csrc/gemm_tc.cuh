@@ -48,6 +48,9 @@ struct Params {
   int stage_out;                // short-K products: functors with chunk32() write their tile through a per-warp shared-memory
                                 // staging buffer (this many bytes per epilogue warp, 0 = off) so that global stores / residual
                                 // loads are row-contiguous 64-128 B segments
+  int stats_cols;               // > 0: the functor reduces per-column statistics (BatchNorm moments): 2 x stats_cols floats of
+                                // shared memory hold the CTA's partial sums, flushed with ONE global atomic per column per CTA
+                                // (one per warp per 32 rows put 5760 same-address fp64 atomics on every column at stage 0)
   int rows_per_frame;           // > 0: A is (batch*rows_per_frame, K) contiguous and B is shared, so the frames are flattened
                                 // into one M extent (no per-frame tile padding); the epilogue recovers (b, m) per row
   int* err_flag;                // device int set to non-zero when a bounded wait expires
@@ -160,6 +163,12 @@ template <typename T, typename = void>
 struct epi_has_pair { static constexpr bool value = false; };
 template <typename T>
 struct epi_has_pair<T, decltype((void)T::kHasPair)> { static constexpr bool value = T::kHasPair; };
+// functors that keep per-CTA column statistics in shared memory (Params::stats_cols) declare kBlockStats and have a `blk`
+// pointer member plus flush_block(blk, N, tid, nthreads)
+template <typename T, typename = void>
+struct epi_block_stats { static constexpr bool value = false; };
+template <typename T>
+struct epi_block_stats<T, decltype((void)T::kBlockStats)> { static constexpr bool value = T::kBlockStats; };
 // functors whose chunk() tolerates a different frame index b in every lane (no warp-wide per-frame reduction)
 template <typename T, typename = void>
 struct epi_row_independent { static constexpr bool value = false; };
@@ -261,6 +270,8 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   uint64_t* bres_bar = bars + 2 * MAX_STAGES + 5;
   uint8_t* out_stage = reinterpret_cast<uint8_t*>(bars) + 256;   // 16-byte aligned (bars is 1024-aligned)
+  float* blk_stats = reinterpret_cast<float*>(out_stage + (size_t)EPI_WARPS * p.stage_out);
+  for (int i = threadIdx.x; i < 2 * p.stats_cols; i += THREADS) blk_stats[i] = 0.f;
 
   const int tiles_per_batch = n_blocks * m_blocks;
   const int fpack = p.fpack;                              // frames per tile (1 unless packed)
@@ -428,6 +439,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
     // ===== epilogue warps: warp w owns TMEM lanes [32 (w % 4), +32); the two warps of a lane group take
     // alternating 32-column blocks (functors that need a whole row in one thread set kWholeRow) =====
     EPI epi = epi_in;
+    if constexpr (epi_block_stats<EPI>::value) epi.blk = p.stats_cols ? blk_stats : nullptr;
     const int lane_grp = warp & 3;
     const int half = (warp - 2) >> 2;
     const bool whole_row = epi_whole_row<EPI>::value;
@@ -497,6 +509,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (epi_block_stats<EPI>::value) {
+    if (p.stats_cols) epi_in.flush_block(blk_stats, p.N, (int)threadIdx.x, THREADS);
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -517,7 +532,8 @@ int* tc_err_flag_device_ptr();
 // Fills `p` (tensor maps, tile recipe) for D = A . B^T.  Returns DGSCT_OK, or DGSCT_ERR_UNSUPPORTED when the
 // operands cannot be described to TMA (alignment) so the caller can take the SIMT kernel instead.
 int make_params(Params& p, const OperandDesc& A, const OperandDesc& B, int M, int N, int K, int batch, int BN_hint = 0,
-                int stages_hint = 0, bool sum_over_batch = false, bool allow_flatten = false, int stage_bytes_per_warp = 0);
+                int stages_hint = 0, bool sum_over_batch = false, bool allow_flatten = false, int stage_bytes_per_warp = 0,
+                int block_stats_cols = 0);
 size_t smem_bytes(const Params& p);
 int num_sms();
 bool operands_ok(const OperandDesc& A, const OperandDesc& B, int K);

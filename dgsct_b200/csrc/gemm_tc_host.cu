@@ -58,7 +58,7 @@ size_t smem_bytes(const Params& p) {
   const int num_k = (p.K + p.BK - 1) / p.BK, n_blocks = (p.N + p.BN - 1) / p.BN;
   const size_t ring = (size_t)p.stages * (p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes));
   const size_t bres = p.b_resident ? (size_t)n_blocks * num_k * p.b_stage_bytes : 0;
-  return 1024 + ring + bres + 256 + (size_t)EPI_WARPS * p.stage_out;
+  return 1024 + ring + bres + 256 + (size_t)EPI_WARPS * p.stage_out + (size_t)2 * p.stats_cols * 4;
 }
 
 int num_sms() {
@@ -74,7 +74,7 @@ int num_sms() {
 }
 
 int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B_in, int M, int N, int K, int batch, int BN_hint,
-                int stages_hint, bool sum_over_batch, bool allow_flatten, int stage_bytes_per_warp) {
+                int stages_hint, bool sum_over_batch, bool allow_flatten, int stage_bytes_per_warp, int block_stats_cols) {
   if (!operands_ok(A_in, B_in, K)) return DGSCT_ERR_UNSUPPORTED;
   OperandDesc A = A_in, B = B_in;
   // Weight gradients sum_b A_b^T B_b with token-major operands whose frames are contiguous: one flattened K extent of batch*K
@@ -163,7 +163,8 @@ int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B_in, int
   //  * the output tile is staged through shared memory for row-contiguous stores;
   //  * two CTAs per SM (when both keep a double-buffered accumulator) hide each other's TMA round trips.
   p.stage_out = (short_k && p.fpack == 1 && !getenv("DGSCT_NO_STAGE_OUT")) ? stage_bytes_per_warp : 0;
-  const size_t out_stage = (size_t)EPI_WARPS * p.stage_out;
+  p.stats_cols = block_stats_cols > 0 ? N : 0;
+  const size_t out_stage = (size_t)EPI_WARPS * p.stage_out + (size_t)2 * p.stats_cols * 4;
   const size_t bres_total = (size_t)n_blocks * num_k * p.b_stage_bytes;
   const bool bres_possible = !p.b_batched && !sum_over_batch && p.fpack == 1 && !getenv("DGSCT_NO_BRES");
   const char* force = getenv("DGSCT_TC_CTAS");

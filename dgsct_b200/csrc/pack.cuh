@@ -56,6 +56,46 @@ __global__ void pack_grouped_kernel(const float* __restrict__ src, int out_ch, i
   }
 }
 
+// ---- all packed operands of one adapter in ONE launch ------------------------------------------------------------------
+// Training re-packs after every optimizer step; as twelve launches per adapter that was 576 tiny kernels at the head of the 48
+// forward calls.  grid = (blocks, segments): blockIdx.y selects the segment, the x blocks stride over its elements.
+struct PackSeg {
+  const float* src; const float* src2;   // src2: second source of a concatenation (kind 2)
+  void* dst;
+  int kind;                              // 0: rows fp32 -> bf16 (pad columns zeroed); 1: grouped 1x1 conv -> dense block-diagonal bf16;
+                                         // 2: fp32 concat [src (rows) ; src2 (cols)] -> fp32
+  int rows, cols, ld, groups;
+};
+constexpr int PACK_MAX_SEGS = 12;
+struct PackTable { PackSeg seg[PACK_MAX_SEGS]; int n; };
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackTable t) {
+  const PackSeg& g = t.seg[blockIdx.y];
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g.kind == 0) {
+    if (!g.src) return;
+    bf16* dst = reinterpret_cast<bf16*>(g.dst);
+    const size_t n = (size_t)g.rows * g.ld;
+    for (size_t i = i0; i < n; i += stride) {
+      const int r = (int)(i / g.ld), c = (int)(i % g.ld);
+      dst[i] = __float2bfloat16_rn(c < g.cols ? g.src[(size_t)r * g.cols + c] : 0.f);
+    }
+  } else if (g.kind == 1) {
+    bf16* dst = reinterpret_cast<bf16*>(g.dst);
+    const size_t n = (size_t)g.rows * g.ld;
+    const int ipg = g.cols / g.groups, opg = g.rows / g.groups;
+    for (size_t i = i0; i < n; i += stride) {
+      const int o = (int)(i / g.ld), c = (int)(i % g.ld);
+      float v = 0.f;
+      if (c < g.cols && c / ipg == o / opg) v = g.src[(size_t)o * ipg + (c - (o / opg) * ipg)];
+      dst[i] = __float2bfloat16_rn(v);
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(g.dst);
+    for (size_t i = i0; i < (size_t)(g.rows + g.cols); i += stride) dst[i] = i < (size_t)g.rows ? g.src[i] : g.src2[i - g.rows];
+  }
+}
+
 // dst bf16 = alpha * src fp32 (per-frame vectors feeding the small tensor-core linears)
 __global__ void scale_to_bf16_kernel(const float* __restrict__ src, float alpha, bf16* __restrict__ dst, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

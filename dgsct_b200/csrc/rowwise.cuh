@@ -388,6 +388,24 @@ inline bool dispatch_row_geometry(int nvec, F&& f) {
   return false;
 }
 
+// "Light" geometry for the register-heavy backward row kernels: as few vectors per lane as possible (a whole warp per row once
+// the row has more than 16 vectors), trading idle lanes (C = 192 / 384: 25 %) for ~half the registers per thread, i.e. two
+// resident blocks per SM instead of one (the column accumulators alone are 3-4 x VPL x 8 registers).
+inline RowGeom row_geometry_light(int nvec) {
+  int lpr = 32;
+  while (lpr > 1 && lpr / 2 >= nvec) lpr >>= 1;
+  return RowGeom{lpr, (nvec + lpr - 1) / lpr};
+}
+template <typename F>
+inline bool dispatch_row_geometry_light(int nvec, F&& f) {
+  const RowGeom g = row_geometry_light(nvec);
+#define DGSCT_ROW_CASE(L_, V_) if (g.lpr == L_ && g.vpl == V_) { f.template run<L_, V_>(); return true; }
+  DGSCT_ROW_CASE(1, 1) DGSCT_ROW_CASE(2, 1) DGSCT_ROW_CASE(4, 1) DGSCT_ROW_CASE(8, 1) DGSCT_ROW_CASE(16, 1)
+  DGSCT_ROW_CASE(32, 1) DGSCT_ROW_CASE(32, 2) DGSCT_ROW_CASE(32, 3) DGSCT_ROW_CASE(32, 4)
+#undef DGSCT_ROW_CASE
+  return false;
+}
+
 inline unsigned row_grid(long long rows, int lpr) {
   const long long rows_per_block = 8LL * (32 / lpr);
   const long long blocks_needed = (rows + rows_per_block - 1) / rows_per_block;

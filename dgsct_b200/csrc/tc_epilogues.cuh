@@ -232,11 +232,19 @@ struct EpiStore {
   static constexpr bool kHasChunk32 = true;
   static constexpr int kStageBytes = OUT_BF16 ? 2048 : 4096;
   static constexpr bool kRowIndependent = true;
+  static constexpr bool kBlockStats = STATS;
   void* out; long long ld, sb;
   const float* bias_m; const float* bias_n;
   float alpha;
   float* colsum; int ncols_total;
   double* stat_sum; double* stat_sq;
+  float* blk;                 // CTA-level partial moments in shared memory ([2][N] floats), set by the kernel (may be NULL)
+  __device__ __forceinline__ void flush_block(const float* b, int N, int tid, int nthreads) const {
+    for (int c = tid; c < N; c += nthreads) {
+      atomicAdd(&stat_sum[c], (double)b[c]);
+      atomicAdd(&stat_sq[c], (double)b[N + c]);
+    }
+  }
   const float* bias_m_coln;   // non-NULL: the row bias enters as the rank-1 term bias_m[m] * bias_m_coln[n] (DGSCT_FC_FIRST)
   __device__ __forceinline__ void begin(int, int, bool) {}
   __device__ __forceinline__ void end(int, int, bool) {}
@@ -290,7 +298,10 @@ struct EpiStore {
         const float s2 = warp_colsum16(q);
         const int lane = threadIdx.x & 31;
         const int col = n0 + colsum16_owner_col(lane);
-        if (((lane & 1) == 0) && col < N) { atomicAdd(&stat_sum[col], (double)s); atomicAdd(&stat_sq[col], (double)s2); }
+        if (((lane & 1) == 0) && col < N) {
+          if (blk) { atomicAdd(&blk[col], s); atomicAdd(&blk[N + col], s2); }
+          else { atomicAdd(&stat_sum[col], (double)s); atomicAdd(&stat_sq[col], (double)s2); }
+        }
       }
     }
   }
