@@ -8,10 +8,10 @@ Public surface mirrors the reference's call boundary (DG-SCT/AVE/nets/net_trans.
     dgsct_b200.FlatAdam(ddp.bucketer, lr=...)     # Adam over the flat gradient buckets, one fused kernel per bucket
 """
 from .adapter import VisualAdapter, patch, adapter_forward_raw, VARIANT_DEFAULTS  # noqa: F401
-from .adapter import adapter_backward_raw  # noqa: F401
+from .adapter import adapter_backward_raw, adapter_pair  # noqa: F401
 from .ddp import AdapterDDP, FlatAdam, GradBucketer  # noqa: F401
 from .heads import TemporalGates, pool_tokens  # noqa: F401
 from ._lib import build, lib  # noqa: F401
 
-__all__ = ["VisualAdapter", "patch", "adapter_forward_raw", "adapter_backward_raw", "AdapterDDP", "FlatAdam", "GradBucketer", "build", "lib",
+__all__ = ["VisualAdapter", "patch", "adapter_forward_raw", "adapter_backward_raw", "adapter_pair", "AdapterDDP", "FlatAdam", "GradBucketer", "build", "lib",
            "VARIANT_DEFAULTS", "TemporalGates", "pool_tokens"]

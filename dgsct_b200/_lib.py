@@ -55,6 +55,7 @@ EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgs
            "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
            "dgsct_tc_error_flag", "dgsct_bicubic_csr_capacity", "dgsct_bicubic_csr",
            "dgsct_adam_tick", "dgsct_adam_flat", "dgsct_cast_bucket_bf16",
+           "dgsct_adapter_pair_fwd", "dgsct_adapter_pair_bwd_saved",
            "dgsct_pool_tokens_fwd", "dgsct_pool_tokens_bwd", "dgsct_temporal_gates_fwd", "dgsct_temporal_gates_bwd"]
 
 _lib = None
@@ -108,6 +109,13 @@ def lib() -> C.CDLL:
     L.dgsct_bicubic_csr_capacity.argtypes = [C.c_int, C.c_int]
     L.dgsct_bicubic_csr.restype = C.c_int
     L.dgsct_bicubic_csr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.dgsct_adapter_pair_fwd.restype = C.c_int
+    L.dgsct_adapter_pair_fwd.argtypes = ([C.POINTER(Desc), C.POINTER(Params), C.c_void_p] * 2 + [C.c_void_p] * 10 +
+                                         [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p])
+    L.dgsct_adapter_pair_bwd_saved.restype = C.c_int
+    L.dgsct_adapter_pair_bwd_saved.argtypes = ([C.POINTER(Desc), C.POINTER(Params), C.c_void_p, C.c_void_p] * 2 + [C.c_void_p] * 10 +
+                                               [C.POINTER(Grads), C.POINTER(Grads), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                C.c_void_p])
     L.dgsct_pool_tokens_fwd.restype = C.c_int
     L.dgsct_pool_tokens_fwd.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
     L.dgsct_pool_tokens_bwd.restype = C.c_int

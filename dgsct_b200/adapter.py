@@ -523,6 +523,137 @@ class VisualAdapter(nn.Module):
         return output, spatial_att_maps
 
 
+class _PairFn(torch.autograd.Function):
+    """Both adapters of one position through dgsct_adapter_pair_fwd / _pair_bwd_saved."""
+
+    @staticmethod
+    def forward(ctx, mod_a, mod_v, names_a, names_v, f_a, f_v, base_a, base_v, *flat):
+        lib = L.lib()
+        dev = f_a.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        sides = []
+        for mod, x, o in ((mod_a, f_a, f_v), (mod_v, f_v, f_a)):
+            cfg, params = mod._cfg(), mod._param_dict()
+            d, P, alive, x, o = _describe(cfg, params, x, o, mod.training)
+            d.flags |= L.F_KEEP
+            packed = mod._packed_weights(cfg, params, x, o)
+            nbytes = lib.dgsct_workspace_bytes(C.byref(d))
+            if nbytes == 0:
+                raise ValueError("dgsct: invalid adapter description")
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            sides.append(dict(cfg=cfg, params=params, d=d, P=P, alive=alive, x=x, o=o, packed=packed, ws=ws, nbytes=nbytes,
+                              out=torch.empty_like(x), smap=torch.empty(x.shape[0], x.shape[1], dtype=x.dtype, device=dev)))
+        A, V = sides
+        pa = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)
+        al = lambda t: C.c_void_p((t.data_ptr() + 255) // 256 * 256)
+        bases = [b.contiguous() if b is not None else None for b in (base_a, base_v)]
+        with torch.cuda.device(dev):
+            rc = lib.dgsct_adapter_pair_fwd(C.byref(A["d"]), C.byref(A["P"]), pa(A["packed"]), C.byref(V["d"]), C.byref(V["P"]), pa(V["packed"]),
+                                            pa(A["x"]), pa(V["x"]), pa(bases[0]), pa(bases[1]), pa(A["out"]), pa(V["out"]),
+                                            pa(A["smap"]), pa(V["smap"]), None, None, al(A["ws"]), C.c_size_t(A["nbytes"]),
+                                            al(V["ws"]), C.c_size_t(V["nbytes"]), C.c_void_p(stream))
+        L.check(rc, "adapter_pair_fwd")
+        ctx.mods, ctx.names, ctx.training = (mod_a, mod_v), (names_a, names_v), (mod_a.training, mod_v.training)
+        ctx.packed, ctx.saved_ws = (A["packed"], V["packed"]), (A["ws"], V["ws"])
+        ctx.has_base = (base_a is not None, base_v is not None)
+        ctx.save_for_backward(A["x"], V["x"])
+        return A["out"], V["out"], A["smap"], V["smap"]
+
+    @staticmethod
+    def backward(ctx, g_a, g_v, gs_a, gs_v):
+        f_a, f_v = ctx.saved_tensors
+        lib = L.lib()
+        dev = f_a.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        g_a = (g_a if g_a is not None else torch.zeros_like(f_a)).to(f_a.dtype).contiguous()
+        g_v = (g_v if g_v is not None else torch.zeros_like(f_v)).to(f_v.dtype).contiguous()
+        gs = [g.to(f_a.dtype).contiguous() if g is not None else None for g in (gs_a, gs_v)]
+        sides, grads_out = [], []
+        for mod, names, x, o, training in ((ctx.mods[0], ctx.names[0], f_a, f_v, ctx.training[0]),
+                                           (ctx.mods[1], ctx.names[1], f_v, f_a, ctx.training[1])):
+            cfg, params = mod._cfg(), mod._param_dict()
+            d, P, alive, x, o = _describe(cfg, params, x, o, training)
+            G = L.Grads()
+            fresh, grads = [], {}
+            fused = getattr(mod, "fused_grad_accumulation", False)
+            tens = dict(mod._named_tensors())
+            bicubic = cfg.get("resampler", "conv") == "bicubic"
+            for field, name in _GRAD_NAMES.items():
+                t = params.get(name)
+                if t is None or (bicubic and field in ("resample_w", "resample_b")) or (field in ("t_w", "t_b") and not cfg.get("temporal", False)):
+                    continue
+                tgt = tens[name].grad if (fused and name in names and tens[name].is_leaf) else None
+                if tgt is not None and tgt.dtype == torch.float32 and tgt.is_contiguous() and tgt.device == dev:
+                    setattr(G, field, tgt.data_ptr())
+                else:
+                    fresh.append((field, name, t))
+            if fresh:
+                total = sum((t.numel() + 3) // 4 * 4 for _, _, t in fresh)
+                flat = torch.zeros(total, dtype=torch.float32, device=dev)
+                off = 0
+                for field, name, t in fresh:
+                    g = flat[off:off + t.numel()].view(t.shape)
+                    grads[name] = g
+                    setattr(G, field, g.data_ptr())
+                    off += (t.numel() + 3) // 4 * 4
+            nbytes = lib.dgsct_bwd_saved_workspace_bytes(C.byref(d))
+            ws = _workspace(dev, ("pair_bwd", len(sides), stream), nbytes + 256)
+            sides.append(dict(d=d, P=P, G=G, alive=alive, ws=ws, nbytes=nbytes, params=params))
+            grads_out.append((names, grads, params))
+        A, V = sides
+        d_fa, d_fv, t_fa, t_fv = torch.empty_like(f_a), torch.empty_like(f_v), torch.empty_like(f_a), torch.empty_like(f_v)
+        pa = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)
+        al = lambda t: C.c_void_p((t.data_ptr() + 255) // 256 * 256)
+        with torch.cuda.device(dev):
+            rc = lib.dgsct_adapter_pair_bwd_saved(C.byref(A["d"]), C.byref(A["P"]), pa(ctx.packed[0]), al(ctx.saved_ws[0]),
+                                                  C.byref(V["d"]), C.byref(V["P"]), pa(ctx.packed[1]), al(ctx.saved_ws[1]),
+                                                  pa(f_a), pa(f_v), pa(g_a), pa(g_v), pa(gs[0]), pa(gs[1]), pa(d_fa), pa(d_fv),
+                                                  pa(t_fa), pa(t_fv), C.byref(A["G"]), C.byref(V["G"]), al(A["ws"]),
+                                                  C.c_size_t(A["nbytes"]), al(V["ws"]), C.c_size_t(V["nbytes"]), C.c_void_p(stream))
+        L.check(rc, "adapter_pair_bwd")
+        ctx.saved_ws = None
+        flat_grads = []
+        for names, grads, params in grads_out:
+            for n in names:
+                g, p_ = grads.get(n), params.get(n)
+                flat_grads.append(g.view_as(p_) if (g is not None and p_ is not None) else None)
+        for mod in ctx.mods:
+            cb = getattr(mod, "_ddp_done_cb", None)
+            if cb is not None:
+                cb()
+        return (None, None, None, None, d_fa, d_fv, g_a if ctx.has_base[0] else None, g_v if ctx.has_base[1] else None, *flat_grads)
+
+
+def adapter_pair(audio_adapter: "VisualAdapter", vis_adapter: "VisualAdapter", f_a: torch.Tensor, f_v: torch.Tensor,
+                 base_a: Optional[torch.Tensor] = None, base_v: Optional[torch.Tensor] = None):
+    """Both adapters of one position in ONE engine call.  The interleave loop's
+
+        f_a_res, _ = audio_adapter_blocks_pX[i](f_a.permute(0,2,1).unsqueeze(-1), f_v.permute(0,2,1).unsqueeze(-1))
+        f_v_res, _ = vis_adapter_blocks_pX[i](f_v.permute(0,2,1).unsqueeze(-1), f_a.permute(0,2,1).unsqueeze(-1))
+        ... f_v = <frozen block>(f_v) + f_v_res.squeeze(-1).permute(0,2,1) ; f_a likewise           (net_trans.py:891-906)
+
+    becomes ``f_a, f_v, smap_a, smap_v = adapter_pair(aud, vis, f_a, f_v, base_a=<block output a>, base_v=<block output v>)``
+    on token-major tensors f_a (BT,Na,Ca), f_v (BT,Nv,Cv): the two adapters run concurrently on forked streams and the
+    residual add is folded into their last pass (``base_*`` None: the plain adapter outputs are returned).  Returns
+    ``(out_a (BT,Na,Ca), out_v (BT,Nv,Cv), spatial_att_maps_a (BT,1,Na), spatial_att_maps_v (BT,1,Nv))``.
+    Variants with a temporal gate (3-tuple adapters) are not covered by the pair entry."""
+    for m in (audio_adapter, vis_adapter):
+        if VARIANT_DEFAULTS[m.variant]["temporal"]:
+            raise NotImplementedError("adapter_pair covers the 2-tuple variants (AVE / AVVP / AVQA / S4 / MS3)")
+    if f_a.dim() != 3 or f_v.dim() != 3 or f_a.shape[0] != f_v.shape[0]:
+        raise ValueError("expected token-major f_a (BT,Na,Ca) and f_v (BT,Nv,Cv)")
+    ta, tv = audio_adapter._named_tensors(), vis_adapter._named_tensors()
+    na = [(n, p) for n, p in ta if p.requires_grad and n in _GRAD_NAMES.values()]
+    nv = [(n, p) for n, p in tv if p.requires_grad and n in _GRAD_NAMES.values()]
+    out_a, out_v, sm_a, sm_v = _PairFn.apply(audio_adapter, vis_adapter, tuple(n for n, _ in na), tuple(n for n, _ in nv),
+                                             f_a, f_v, base_a, base_v, *[p for _, p in na], *[p for _, p in nv])
+    for m in (audio_adapter, vis_adapter):
+        if m.training and m.use_bn:
+            m.bn1.num_batches_tracked += 1
+            m.bn2.num_batches_tracked += 1
+    return out_a, out_v, sm_a.unsqueeze(1), sm_v.unsqueeze(1)
+
+
 def patch(module, variant: str = "ave"):
     """Replace ``module.VisualAdapter`` (a reference task module such as ``nets.net_trans``) by the engine class
     bound to ``variant`` so the task script builds engine adapters without further changes."""

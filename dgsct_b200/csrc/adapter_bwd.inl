@@ -262,7 +262,7 @@ static T to_tcT(const EpiOut& e) {
 struct BwdPlan {
   size_t fwd;                        // keep-mode forward workspace
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
-  size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, dWup_d, dWd_d, zero_end;
+  size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, colA1, colB1, dWup_d, dWd_d, zero_end;
   size_t vA, vB, vC, vD, wA, wB, wC, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
   size_t total;
 };
@@ -292,7 +292,7 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.zero_begin = off;
   p.dm = take(BT * C * 4); p.dsig = take(BT * N * 4); p.ds = take(BT * N * 4); p.dtau = take(BT * 4);
   p.daq = take(BT * (C + H) * 4); p.dobar = take(BT * C * 4); p.dr1 = take(BT * C * 4);
-  p.colA = take(C * 4); p.colB = take(C * 4);
+  p.colA = take(C * 4); p.colB = take(C * 4); p.colA1 = take(C * 4); p.colB1 = take(C * 4);
   p.dWup_d = take(C * ldz * 4); p.dWd_d = take(Cd * C * 4);
   p.vB = take(BT * C * 4); p.vC = take(BT * C * 4);     // split-K targets of the skinny products (added atomically)
   p.fc_t = take(C * 4);                                 // sum_{b,n} dV b_res (re-associated resampler)
@@ -369,6 +369,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   float* dm = (float*)(ws + bp.dm); float* dsig = (float*)(ws + bp.dsig); float* ds = (float*)(ws + bp.ds);
   float* dtau = (float*)(ws + bp.dtau); float* daq = (float*)(ws + bp.daq); float* dobar = (float*)(ws + bp.dobar);
   float* dr1 = (float*)(ws + bp.dr1); float* colA = (float*)(ws + bp.colA); float* colB = (float*)(ws + bp.colB);
+  float* colA1 = (float*)(ws + bp.colA1); float* colB1 = (float*)(ws + bp.colB1);       // bn1-backward sums (own zeroed slots)
   float* dWup_d = (float*)(ws + bp.dWup_d); float* dWd_d = (float*)(ws + bp.dWd_d);
   float* vA = (float*)(ws + bp.vA); float* vB = (float*)(ws + bp.vB); float* vC = (float*)(ws + bp.vC);
   float* wA = (float*)(ws + bp.wA); float* wB = (float*)(ws + bp.wB); float* wC = (float*)(ws + bp.wC);
@@ -500,14 +501,12 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     StageScope _sc(ST_BN_FINALIZE, st); count_launch(4);
     relu_mask_kernel<<<ew_grid, 256, 0, st>>>(gZ, bf, ldz, Z, Cd, sc1, sh1, R, Cd);
     if (use_bn) {
-      DGSCT_CUDA_CHECK(cudaMemsetAsync(colA, 0, (size_t)C * 4, st));
-      DGSCT_CUDA_CHECK(cudaMemsetAsync(colB, 0, (size_t)C * 4, st));
       { const int gx = ceil_div(Cd, 32);                      // narrow (C/r columns): spread the rows over ~4 blocks per SM
         long long gy = (R + 255) / 256;
         if (gy > (148 * 4) / gx) gy = (148 * 4) / gx;
         if (gy < 1) gy = 1;
-        col_reduce_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(gZ, bf, ldz, Z, 0, Cd, R, Cd, colA, colB); }
-      bn_bwd_coeffs_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, 1, train, colA, colB, (const float*)(fw + fp.bn1_mean),
+        col_reduce_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(gZ, bf, ldz, Z, 0, Cd, R, Cd, colA1, colB1); }
+      bn_bwd_coeffs_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, 1, train, colA1, colB1, (const float*)(fw + fp.bn1_mean),
                                                               (const float*)(fw + fp.bn1_rstd), P.bn1_w, (double)R, coefA, coefB, coefC,
                                                               G.bn1_w, G.bn1_b);
       launch_affine_combine(gZ, bf, ldz, Z, Cd, coefA, coefB, coefC, R, Cd, ew_grid, st);
@@ -572,8 +571,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       bwd_xc_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, gX1, X1, bf, C, N, mvec, dm);
       KCHECK("bwd_xc");
     }
-    // opm = 1 + m
-    { StageScope _sc(ST_MISC, st); count_launch();
+    // opm = 1 + m   (operand scale of the exact-fp32 path's dWv2 product; the tensor-core path kept Xc = X1 (1+m))
+    if (!tcp) { StageScope _sc(ST_MISC, st); count_launch();
       one_plus_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(mvec, opm, BT * C);
       KCHECK("opm"); }
     // dWv2[j,c] += sum_b (1+m[b,c]) sum_n dz2[b,n,j] X1[b,n,c]

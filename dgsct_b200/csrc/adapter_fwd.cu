@@ -110,7 +110,7 @@ static int tap(const void* src, int is_bf16, float* dst, size_t n, cudaStream_t 
 }
 
 int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, const void* other, void* out,
-                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep) {
+                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep, const void* resid) {
   const FwdPlan pl = make_fwd_plan(d, keep);
   const int upd = (d.flags & DGSCT_F_NO_STAT_UPDATE) ? 0 : 1;
   const int BT = d.BT, N = d.N, C = d.C, Co = d.Co, No = d.No, K = d.K, Cd = d.C / d.r, H = d.C / 2, G = d.g;
@@ -286,7 +286,7 @@ int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, 
     a.ln_w = lnp ? P.lnp_w : nullptr; a.ln_b = lnp ? P.lnp_b : nullptr;
     a.gate = (d.flags & DGSCT_F_USE_GATE) ? P.gate : nullptr;
     a.gate_before_ln = (d.flags & DGSCT_F_GATE_BEFORE_LN) ? 1 : 0;
-    a.eps = d.eps_ln; a.C = C; a.rows = (long long)BT * N;
+    a.eps = d.eps_ln; a.C = C; a.rows = (long long)BT * N; a.resid = resid;
     const int wpb = 4;
     { StageScope _sc(ST_OUT_LN, st); count_launch();
   out_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
@@ -419,7 +419,7 @@ struct SimtAffineRelu {
 #define DGSCT_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packed_in, const void* x, const void* other,
-                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep) {
+                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep, const void* resid) {
   const FwdPlan pl = make_fwd_plan(d, keep);
   const int upd = (d.flags & DGSCT_F_NO_STAT_UPDATE) ? 0 : 1;
   const PackPlan pp = make_pack_plan(d);
@@ -706,7 +706,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     a.ln_w = lnp ? P.lnp_w : nullptr; a.ln_b = lnp ? P.lnp_b : nullptr;
     a.gate = (d.flags & DGSCT_F_USE_GATE) ? P.gate : nullptr;
     a.gate_before_ln = (d.flags & DGSCT_F_GATE_BEFORE_LN) ? 1 : 0;
-    a.eps = d.eps_ln; a.C = C; a.rows = rowsBT;
+    a.eps = d.eps_ln; a.C = C; a.rows = rowsBT; a.resid = resid;
     const int wpb = 4;
     StageScope _sc(ST_OUT_LN, st); count_launch();
     if (!launch_out_ln_vec(a, st))

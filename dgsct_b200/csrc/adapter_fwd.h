@@ -31,12 +31,14 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep = false);
 
 // bf16 tensor-core pipeline (tcgen05 GEMMs); `packed` = pre-packed bf16 weights or NULL (packed per call)
 int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packed, const void* x, const void* other,
-                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep = false);
+                   void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep = false,
+                   const void* resid = nullptr);
 int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaStream_t st);
 size_t packed_bytes(const dgsct_desc& d);
 
 int adapter_fwd_simt(const dgsct_desc& d, const dgsct_params& P, const void* x, const void* other, void* out,
-                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep = false);
+                     void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep = false,
+                     const void* resid = nullptr);
 
 // `saved` = workspace of a forward run with the keep plan (DGSCT_F_KEEP), or NULL to recompute the forward inside `ws`
 size_t bwd_workspace_bytes(const dgsct_desc& d, bool have_saved = false);

@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "adapter_fwd.h"
+#include "profile.h"
+#include "side_stream.h"
 
 namespace dgsct {
 static thread_local char g_err[512] = "";
@@ -54,6 +56,17 @@ static int entry_checks() {
 }  // namespace dgsct
 
 using namespace dgsct;
+
+// ---- both directions of one position in one call ------------------------------------------------
+__global__ void __launch_bounds__(256) pair_add_kernel(void* __restrict__ dst, const void* __restrict__ src, size_t n, int bf) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    st_act(dst, i, ld_act(dst, i, bf) + ld_act(src, i, bf), bf);
+}
+static int pair_consistent(const dgsct_desc* a, const dgsct_desc* v) {
+  if (!a || !v) return DGSCT_ERR_NULL;
+  if (a->BT != v->BT || a->C != v->Co || a->N != v->No || v->C != a->Co || v->N != a->No || a->io_dtype != v->io_dtype) return DGSCT_ERR_BAD_DESC;
+  return DGSCT_OK;
+}
 
 extern "C" {
 
@@ -126,6 +139,43 @@ int dgsct_adapter_fwd(const dgsct_desc* desc, const dgsct_params* params, const 
   return adapter_fwd_simt(d, P, x, other, out, spatial_map, temporal_map, taps, (char*)workspace, (cudaStream_t)stream, keep);
 }
 
+int dgsct_adapter_pair_fwd(const dgsct_desc* desc_a, const dgsct_params* params_a, const void* packed_a, const dgsct_desc* desc_v,
+                           const dgsct_params* params_v, const void* packed_v, const void* f_a, const void* f_v, const void* base_a,
+                           const void* base_v, void* out_a, void* out_v, void* smap_a, void* smap_v, float* tmap_a, float* tmap_v,
+                           void* ws_a, size_t ws_a_bytes, void* ws_v, size_t ws_v_bytes, void* stream) {
+  int rc = pair_consistent(desc_a, desc_v);
+  if (rc != DGSCT_OK) return rc;
+  if ((rc = validate_desc(desc_a)) != DGSCT_OK || (rc = validate_desc(desc_v)) != DGSCT_OK) return rc;
+  if (!params_a || !params_v || !f_a || !f_v || !out_a || !out_v || !smap_a || !smap_v || !ws_a || !ws_v) return DGSCT_ERR_NULL;
+  if ((rc = entry_checks()) != DGSCT_OK) return rc;
+  const bool keep_a = (desc_a->flags & DGSCT_F_KEEP) != 0, keep_v = (desc_v->flags & DGSCT_F_KEEP) != 0;
+  if (ws_a_bytes < make_fwd_plan(*desc_a, keep_a).total || ws_v_bytes < make_fwd_plan(*desc_v, keep_v).total ||
+      ((uintptr_t)ws_a & 255) || ((uintptr_t)ws_v & 255))
+    return DGSCT_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the two adapters read the same two tensors and are independent (net_trans.py:891-892): the audio one runs on an
+  // auxiliary stream forked from the caller's, the visual one on the caller's stream
+  SideStream* side = (prof_enabled() || getenv("DGSCT_NO_SIDE")) ? nullptr : side_stream_for(st, 3);
+  cudaStream_t sa = side ? side->s : st;
+  if (side) {
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, st));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->ev, 0));
+  }
+  auto run = [&](const dgsct_desc& d, const dgsct_params& P, const void* pk, const void* x, const void* o, void* out, void* smap,
+                 float* tmap, void* ws, bool keep, const void* base, cudaStream_t s) -> int {
+    if (d.io_dtype == DGSCT_BF16 && !(d.flags & DGSCT_F_FORCE_SIMT))
+      return adapter_fwd_tc(d, P, pk, x, o, out, smap, tmap, nullptr, (char*)ws, s, keep, base);
+    return adapter_fwd_simt(d, P, x, o, out, smap, tmap, nullptr, (char*)ws, s, keep, base);
+  };
+  rc = run(*desc_a, *params_a, packed_a, f_a, f_v, out_a, smap_a, tmap_a, ws_a, keep_a, base_a, sa);
+  const int rc2 = run(*desc_v, *params_v, packed_v, f_v, f_a, out_v, smap_v, tmap_v, ws_v, keep_v, base_v, st);
+  if (side) {
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, side->s));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev, 0));
+  }
+  return rc != DGSCT_OK ? rc : rc2;
+}
+
 size_t dgsct_bwd_workspace_bytes(const dgsct_desc* desc) {
   if (validate_desc(desc) != DGSCT_OK) return 0;
   return bwd_workspace_bytes(*desc);
@@ -175,6 +225,41 @@ int dgsct_adapter_bwd_saved(const dgsct_desc* desc, const dgsct_params* params, 
                             const dgsct_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
   return bwd_entry(desc, params, packed, saved_forward_workspace, x, other, d_out, d_spatial_map, d_temporal_map, dx, dother,
                    grads, workspace, workspace_bytes, stream, true);
+}
+
+int dgsct_adapter_pair_bwd_saved(const dgsct_desc* desc_a, const dgsct_params* params_a, const void* packed_a, const void* saved_a,
+                                 const dgsct_desc* desc_v, const dgsct_params* params_v, const void* packed_v, const void* saved_v,
+                                 const void* f_a, const void* f_v, const void* d_out_a, const void* d_out_v, const void* d_smap_a,
+                                 const void* d_smap_v, void* d_f_a, void* d_f_v, void* tmp_f_a, void* tmp_f_v,
+                                 const dgsct_grads* grads_a, const dgsct_grads* grads_v, void* ws_a, size_t ws_a_bytes, void* ws_v,
+                                 size_t ws_v_bytes, void* stream) {
+  int rc = pair_consistent(desc_a, desc_v);
+  if (rc != DGSCT_OK) return rc;
+  if (!d_f_a || !d_f_v || !tmp_f_a || !tmp_f_v) return DGSCT_ERR_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  SideStream* side = (prof_enabled() || getenv("DGSCT_NO_SIDE")) ? nullptr : side_stream_for(st, 3);
+  cudaStream_t sa = side ? side->s : st;
+  if (side) {
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, st));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->ev, 0));
+  }
+  // audio adapter: x = f_a (dx -> d_f_a), other = f_v (dother -> tmp_f_v); visual adapter: x = f_v (dx -> d_f_v), other = f_a
+  rc = bwd_entry(desc_a, params_a, packed_a, saved_a, f_a, f_v, d_out_a, d_smap_a, nullptr, d_f_a, tmp_f_v, grads_a, ws_a, ws_a_bytes,
+                 (void*)sa, true);
+  const int rc2 = bwd_entry(desc_v, params_v, packed_v, saved_v, f_v, f_a, d_out_v, d_smap_v, nullptr, d_f_v, tmp_f_a, grads_v, ws_v,
+                            ws_v_bytes, stream, true);
+  if (side) {
+    DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, side->s));
+    DGSCT_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev, 0));
+  }
+  if (rc != DGSCT_OK || rc2 != DGSCT_OK) return rc != DGSCT_OK ? rc : rc2;
+  const int bf = desc_a->io_dtype == DGSCT_BF16;
+  const size_t na = (size_t)desc_a->BT * desc_a->N * desc_a->C, nv = (size_t)desc_v->BT * desc_v->N * desc_v->C;
+  StageScope _sc(ST_MISC, st); count_launch(2);
+  pair_add_kernel<<<148 * 4, 256, 0, st>>>(d_f_a, tmp_f_a, na, bf);     // d f_a = dx(audio adapter) + dother(visual adapter)
+  pair_add_kernel<<<148 * 4, 256, 0, st>>>(d_f_v, tmp_f_v, nv, bf);
+  DGSCT_LAUNCH_CHECK("pair_add");
+  return DGSCT_OK;
 }
 
 // Cubic convolution coefficients (A = -0.75), the kernel torch uses for mode='bicubic'.

@@ -481,31 +481,45 @@ __global__ void rowsum_frames_kernel(const void* __restrict__ du, int bf, int BT
   if (threadIdx.x == 0) atomicAdd(&out[n], s);
 }
 
+template <int LPR>
+__device__ __forceinline__ float rowgroups_sum(float v) {      // sum over the 32/LPR row groups of a warp (same columns)
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // ---- re-associated resampler: both bias-related reductions of dV in ONE pass -------------------------------------------------
 //   d_bres[n] += sum_{b,c} dV[b,n,c] * s[c]          (s = row sums of fc.weight)
 //   t[c]      += sum_{b,n} dV[b,n,c] * b_res[n]      (rank-1 part of d fc.weight, added by add_col_broadcast_kernel)
 // One warp per row, lanes stride over 16-byte vectors; the column sums stay in registers across the rows a warp visits (<= 6
 // vectors per lane: C <= 1536) and are flushed once per warp.  Replaces two kernels that each read dV completely.
-template <int VPL>
+template <int LPR, int VPL>
 __global__ void __launch_bounds__(256) dv_bias_sums_kernel(const bf16* __restrict__ dv, long long rows, int N, int C,
                                                            const float* __restrict__ s, const float* __restrict__ b_res,
                                                            float* __restrict__ d_bres, float* __restrict__ t) {
-  const int lane = threadIdx.x & 31, nvec = C >> 3;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  extern __shared__ float blk_t[];               // [C] block partial of t (one global atomic per column per BLOCK)
+  constexpr int RPW = 32 / LPR;                  // rows per warp iteration (LPR lanes share a row, as in rowwise.cuh)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR, nvec = C >> 3;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) blk_t[c] = 0.f;
+  __syncthreads();
   float sv[VPL][8], acc[VPL][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
+    const int vi = sub + LPR * i;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[i][j] = 0.f; sv[i][j] = (vi < nvec) ? s[vi * 8 + j] : 0.f; }
   }
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const float br = b_res[(int)(row % N)];
+  const long long step = (long long)gridDim.x * 8 * RPW;
+  for (long long base = ((long long)blockIdx.x * 8 + warp) * RPW; base < rows; base += step) {
+    const long long row = base + rsub;
+    const bool rv = row < rows;
+    const int n = rv ? (int)(row % N) : 0;
+    const float br = rv ? b_res[n] : 0.f;
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
+      const int vi = sub + LPR * i;
+      if (rv && vi < nvec) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(dv + row * C + vi * 8));
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -518,35 +532,40 @@ __global__ void __launch_bounds__(256) dv_bias_sums_kernel(const bf16* __restric
         }
       }
     }
-    dot = warp_sum(dot);
-    if (lane == 0) atomicAdd(&d_bres[(int)(row % N)], dot);
+    dot = group_sum<LPR>(dot);
+    if (rv && sub == 0) atomicAdd(&d_bres[n], dot);
   }
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
+    const int vi = sub + LPR * i;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&t[vi * 8 + j], acc[i][j]);
+    for (int j = 0; j < 8; ++j) {
+      const float v = rowgroups_sum<LPR>(acc[i][j]);
+      if (rsub == 0 && vi < nvec) atomicAdd(&blk_t[vi * 8 + j], v);
     }
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&t[c], blk_t[c]);
 }
-// returns false when the shape is outside the vector kernel's range (C % 8, C > 1536): the caller runs the two scalar kernels
+struct DvBiasLaunch {
+  const bf16* p; long long rows; int N, C; const float* s; const float* b_res; float* d_bres; float* t; cudaStream_t st; bool* ok;
+  template <int LPR, int VPL> void run() {
+    if (VPL > 6) { *ok = false; return; }
+    const long long rows_per_block = 8LL * (32 / LPR);
+    long long blocks = (rows + 4 * rows_per_block - 1) / (4 * rows_per_block);        // >= 4 iterations per block
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    dv_bias_sums_kernel<LPR, (VPL > 6 ? 1 : VPL)><<<(unsigned)blocks, 256, (size_t)C * 4, st>>>(p, rows, N, C, s, b_res, d_bres, t);
+    *ok = true;
+  }
+};
+// returns false when the shape is outside the vector kernel's range: the caller runs the two scalar kernels
 inline bool launch_dv_bias_sums(const void* dv, int bf, long long rows, int N, int C, const float* s, const float* b_res, float* d_bres,
                                 float* t, cudaStream_t st) {
   if (!bf || C % 8 || C > 1536) return false;
-  const int nvec = C / 8, vpl = (nvec + 31) / 32;
-  long long blocks = (rows + 63) / 64;             // >= 8 rows per warp
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
-  const bf16* p = reinterpret_cast<const bf16*>(dv);
-  switch (vpl) {
-    case 1: dv_bias_sums_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
-    case 2: dv_bias_sums_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
-    case 3: dv_bias_sums_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
-    case 4: dv_bias_sums_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
-    default: dv_bias_sums_kernel<6><<<(unsigned)blocks, 256, 0, st>>>(p, rows, N, C, s, b_res, d_bres, t); break;
-  }
-  return true;
+  bool ok = false;
+  if (!dispatch_row_geometry(C / 8, DvBiasLaunch{reinterpret_cast<const bf16*>(dv), rows, N, C, s, b_res, d_bres, t, st, &ok})) return false;
+  return ok;
 }
 
 // ---- re-associated resampler (DGSCT_FC_FIRST): the rank-1 bias term b_res[n] * s[c] of V --------------------------------
@@ -638,12 +657,6 @@ __global__ void densify_grouped_kernel(const float* __restrict__ src, int out_ch
 // over the block's rows and flushed once per block -- the scalar kernels issue one shared-memory (and, for the channel
 // gate, one GLOBAL) atomic per element.
 // =====================================================================================================================
-template <int LPR>
-__device__ __forceinline__ float rowgroups_sum(float v) {      // sum over the 32/LPR row groups of a warp (same columns)
-#pragma unroll
-  for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 // out = gate * LN_post(B2) [AVE] or LN_post(gate * B2) [AVS], B2 = uo*scale + shift.  Also accumulates the bn2-backward
 // column sums colA[c] += sum dB2, colB[c] += sum dB2*uo (NULL to skip) so that no separate reduction pass is needed.

@@ -147,6 +147,8 @@ struct OutLnArgs {
   const float* ln_w; const float* ln_b;    // NULL => no ln_post
   const float* gate;                       // NULL => no gate
   int gate_before_ln; float eps; int C; long long rows;
+  const void* resid;                       // non-NULL: out = resid + adapter output (the caller's residual add, net_trans.py:895-906,
+                                           // folded into this pass by the pair entry point; same dtype as out)
 };
 
 // out = gate * LN_post(bn2(u))   (AVE order, net_trans.py:667-672)  or  LN_post(gate * bn2(u))  (AVS order)
@@ -172,9 +174,11 @@ __global__ void out_ln_kernel(OutLnArgs a) {
     sq = warp_sum(sq);
     const float rstd = rsqrtf(sq / a.C + a.eps);
     for (int c = lane; c < a.C; c += 32)
-      st_act(a.out, (size_t)row * a.C + c, ((buf[c] - mean) * rstd * a.ln_w[c] + a.ln_b[c]) * gpost, a.out_bf16);
+      st_act(a.out, (size_t)row * a.C + c, ((buf[c] - mean) * rstd * a.ln_w[c] + a.ln_b[c]) * gpost +
+             (a.resid ? ld_act(a.resid, (size_t)row * a.C + c, a.out_bf16) : 0.f), a.out_bf16);
   } else {
-    for (int c = lane; c < a.C; c += 32) st_act(a.out, (size_t)row * a.C + c, buf[c] * gpost, a.out_bf16);
+    for (int c = lane; c < a.C; c += 32)
+      st_act(a.out, (size_t)row * a.C + c, buf[c] * gpost + (a.resid ? ld_act(a.resid, (size_t)row * a.C + c, a.out_bf16) : 0.f), a.out_bf16);
   }
 }
 
@@ -354,6 +358,12 @@ __global__ void __launch_bounds__(256) out_ln_vec_kernel(OutLnArgs a) {
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[i][j] *= gpost;
+        }
+        if (a.resid) {
+          float rr[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + row * a.C + vi * 8)), rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += rr[j];
         }
         *reinterpret_cast<uint4*>(out + row * a.C + vi * 8) = pack8(v[i]);
       }

@@ -163,6 +163,26 @@ int dgsct_adapter_bwd_saved(const dgsct_desc *desc, const dgsct_params *params, 
                             const void *d_spatial_map, const float *d_temporal_map, void *dx, void *dother,
                             const dgsct_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
+/* BOTH directions of one position in one call.  The interleave loop calls
+ * audio_adapter_blocks_pX[i](f_a, f_v) and vis_adapter_blocks_pX[i](f_v, f_a) back to back on the same two tensors
+ * (net_trans.py:891-892, 900-901) and later adds the results to the token streams (:895-906).  desc_a / params_a describe
+ * the audio adapter (x = f_a (BT,Na,Ca), other = f_v), desc_v / params_v the visual one (x = f_v, other = f_a); the two run
+ * concurrently on forked streams and are joined before the call returns.  base_a / base_v (io_dtype, shapes of f_a / f_v, may be
+ * NULL): out_a = base_a + adapter_a(...), the caller's residual add folded into the last pass (pass the output of the frozen
+ * block, which the reference adds the adapter result to).  Workspaces as in dgsct_adapter_fwd (one per adapter).
+ * The backward (saved activations) returns d_f_a = dx(audio) + dother(visual) and d_f_v likewise; tmp_f_a / tmp_f_v are scratch
+ * tensors of the shapes of f_a / f_v; the gradient w.r.t. base_* is d_out_* itself. */
+int dgsct_adapter_pair_fwd(const dgsct_desc *desc_a, const dgsct_params *params_a, const void *packed_a, const dgsct_desc *desc_v,
+                           const dgsct_params *params_v, const void *packed_v, const void *f_a, const void *f_v, const void *base_a,
+                           const void *base_v, void *out_a, void *out_v, void *smap_a, void *smap_v, float *tmap_a, float *tmap_v,
+                           void *ws_a, size_t ws_a_bytes, void *ws_v, size_t ws_v_bytes, void *stream);
+int dgsct_adapter_pair_bwd_saved(const dgsct_desc *desc_a, const dgsct_params *params_a, const void *packed_a, const void *saved_a,
+                                 const dgsct_desc *desc_v, const dgsct_params *params_v, const void *packed_v, const void *saved_v,
+                                 const void *f_a, const void *f_v, const void *d_out_a, const void *d_out_v, const void *d_smap_a,
+                                 const void *d_smap_v, void *d_f_a, void *d_f_v, void *tmp_f_a, void *tmp_f_v,
+                                 const dgsct_grads *grads_a, const dgsct_grads *grads_v, void *ws_a, size_t ws_a_bytes, void *ws_v,
+                                 size_t ws_v_bytes, void *stream);
+
 /* the two ops directly behind the adapters in the task networks.
  *   dgsct_pool_tokens_*     out (BT,C) = sum_n spatial_map[b,n] f[b,n,c]  -- torch.bmm(spatial_att_maps, f) of
  *                           DG-SCT/AVE/nets/net_trans.py:922,924 (the adapter's second return value pools the tokens);

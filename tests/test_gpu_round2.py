@@ -69,7 +69,7 @@ def test_s4_bt20_forward_backward(shape, dtype):
     errs.pop("gate", None)
     assert "conv_adapter.weight" not in grads            # the stencil has no trainable matrix
     bad = {k: f"{v:.2e}" for k, v in errs.items() if v > gtol}
-    assert not bad, bad
+    assert not bad, (bad, {k: f"{v:.2e}" for k, v in errs.items()})
 
 
 def test_s4_sparse_stencil_equals_dense_matrix_path():
@@ -185,7 +185,8 @@ def test_adapter_ddp_with_engine_adapters_and_flat_adam():
             # three Adam steps of lr 1e-3 move every element by <= 3e-3; elements whose gradient is numerically zero may
             # take opposite signs in the two runs (fp32 atomics reorder sums), everything else must agree closely
             assert float((qa - qb).abs().max()) < 6.5e-3, n
-            assert rel_l2(qb.detach().cpu(), qa.detach().cpu()) < 2e-3, n
+            if not n.endswith("ln_before.bias"):       # zero gradient in exact arithmetic (bias in front of a batch-stat BN):
+                assert rel_l2(qb.detach().cpu(), qa.detach().cpu()) < 2e-3, n      # Adam turns its fp32 noise into +-lr steps
 
 
 def test_flat_adam_matches_torch_adam_elementwise():
@@ -254,3 +255,52 @@ def test_boundary_reports_errors():
     p = _dev(O.random_params(cfg, seed=1))
     with pytest.raises(RuntimeError):
         adapter_forward_raw(dataclasses.asdict(cfg), p, torch.randn(2, 36, 768), torch.randn(2, 64, 384))      # CPU tensors
+
+
+# ---- both directions of one position in one call, residual add folded ---------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_adapter_pair_equals_two_calls_plus_residual_add(dtype):
+    Ca, Na, Cv, Nv = 384, 256, 768, 144                   # stage-2 pair (net_trans.py:882-885)
+    aud = _make_adapter(Ca, Na, Cv, Nv, 11)
+    vis = _make_adapter(Cv, Nv, Ca, Na, 12)
+    g = torch.Generator().manual_seed(13)
+    f_a = torch.randn(10, Na, Ca, generator=g).to(dtype).cuda()
+    f_v = torch.randn(10, Nv, Cv, generator=g).to(dtype).cuda()
+    blk_a = torch.randn(10, Na, Ca, generator=g).to(dtype).cuda()      # stands in for the frozen blocks' outputs
+    blk_v = torch.randn(10, Nv, Cv, generator=g).to(dtype).cuda()
+
+    def reference():
+        xa, xv = f_a.clone().requires_grad_(True), f_v.clone().requires_grad_(True)
+        ra, sa = aud(xa.permute(0, 2, 1).unsqueeze(-1), xv.permute(0, 2, 1).unsqueeze(-1))       # net_trans.py:891
+        rv, sv = vis(xv.permute(0, 2, 1).unsqueeze(-1), xa.permute(0, 2, 1).unsqueeze(-1))       # net_trans.py:892
+        oa = blk_a + ra.squeeze(-1).permute(0, 2, 1)                                             # net_trans.py:895-898
+        ov = blk_v + rv.squeeze(-1).permute(0, 2, 1)
+        ((oa.float() ** 2).sum() * 1e-2 + (ov.float() ** 2).sum() * 1e-2 + sa.float()[:, 0, ::3].sum() + sv.float()[:, 0, ::5].sum()).backward()
+        gp = {("a", n): q.grad.clone() for n, q in aud.named_parameters() if q.grad is not None}
+        gp.update({("v", n): q.grad.clone() for n, q in vis.named_parameters() if q.grad is not None})
+        aud.zero_grad(); vis.zero_grad()
+        return oa.detach(), ov.detach(), sa.detach(), sv.detach(), xa.grad, xv.grad, gp
+
+    def paired():
+        xa, xv = f_a.clone().requires_grad_(True), f_v.clone().requires_grad_(True)
+        ba, bv = blk_a.clone().requires_grad_(True), blk_v.clone().requires_grad_(True)
+        oa, ov, sa, sv = dgsct_b200.adapter_pair(aud, vis, xa, xv, base_a=ba, base_v=bv)
+        ((oa.float() ** 2).sum() * 1e-2 + (ov.float() ** 2).sum() * 1e-2 + sa.float()[:, 0, ::3].sum() + sv.float()[:, 0, ::5].sum()).backward()
+        gp = {("a", n): q.grad.clone() for n, q in aud.named_parameters() if q.grad is not None}
+        gp.update({("v", n): q.grad.clone() for n, q in vis.named_parameters() if q.grad is not None})
+        aud.zero_grad(); vis.zero_grad()
+        return oa.detach(), ov.detach(), sa.detach(), sv.detach(), xa.grad, xv.grad, gp, ba.grad, bv.grad, oa
+
+    r, p = reference(), paired()
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 6e-3        # bf16: the folded add rounds once instead of twice
+    for i, name in enumerate(("out_a", "out_v", "smap_a", "smap_v")):
+        assert p[i].shape == r[i].shape and rel_l2(p[i].float().cpu(), r[i].float().cpu()) < tol, name
+    gtol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel_l2(p[4].float().cpu(), r[4].float().cpu()) < gtol and rel_l2(p[5].float().cpu(), r[5].float().cpu()) < gtol
+    for k, v in r[6].items():
+        if float(v.abs().max()) > 1e-7 and not k[1].endswith(("ln_before.bias", "fc_affine_v_s_att.bias")):
+            assert rel_l2(p[6][k].cpu(), v.cpu()) < 10 * gtol, k
+    # gradient of the folded residual base is the output gradient itself
+    assert rel_l2(p[7].float().cpu(), (2e-2 * p[9].float()).cpu()) < (1e-5 if dtype == torch.float32 else 1e-2)
+    assert L.lib().dgsct_tc_error_flag(1) == 0
