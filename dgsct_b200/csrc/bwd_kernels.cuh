@@ -661,7 +661,7 @@ __global__ void densify_grouped_kernel(const float* __restrict__ src, int out_ch
 // out = gate * LN_post(B2) [AVE] or LN_post(gate * B2) [AVS], B2 = uo*scale + shift.  Also accumulates the bn2-backward
 // column sums colA[c] += sum dB2, colB[c] += sum dB2*uo (NULL to skip) so that no separate reduction pass is needed.
 template <int LPR, int VPL>
-__global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_out_vec_kernel(BwdOutArgs a, float* __restrict__ colA, float* __restrict__ colB) {
+__global__ void __launch_bounds__(256, (VPL <= 1 ? 2 : 1)) bwd_out_vec_kernel(BwdOutArgs a, float* __restrict__ colA, float* __restrict__ colB) {
   extern __shared__ float sm[];                 // [4][C] block partials: d_lnw, d_lnb, colA, colB
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR;
@@ -680,18 +680,46 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_out_vec_kernel(Bw
     for (int j = 0; j < 8; ++j) { cw[i][j] = 0.f; cb[i][j] = 0.f; ca[i][j] = 0.f; cq[i][j] = 0.f; }
   float gate_acc = 0.f;
   const long long step = (long long)gridDim.x * 8 * RPW;
+  // software pipeline (see bwd_gate_ln_vec_kernel): next row group's loads are in flight during this group's reductions
+  float4 nu0[VPL], nu1[VPL];
+  uint4 ndo[VPL];
+  auto fetch = [&](long long base_) {
+    const long long r_ = base_ + rsub;
+    const bool ok = base_ < a.rows && r_ < a.rows;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      if (ok && vi < nvec) {
+        const float4* up = reinterpret_cast<const float4*>(a.uo + r_ * C + vi * 8);
+        nu0[i] = __ldg(up); nu1[i] = __ldg(up + 1);
+        ndo[i] = __ldg(reinterpret_cast<const uint4*>(dout + r_ * C + vi * 8));
+      } else {
+        nu0[i] = make_float4(0.f, 0.f, 0.f, 0.f); nu1[i] = nu0[i]; ndo[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  fetch(((long long)blockIdx.x * 8 + warp) * RPW);
   for (long long base = ((long long)blockIdx.x * 8 + warp) * RPW; base < a.rows; base += step) {
     const long long row = base + rsub;
     const bool rv = row < a.rows;
-    float v[VPL][8], dy[VPL][8];
+    float v[VPL][8], dy[VPL][8], ucur[VPL][8];
+    uint4 rawd[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      ucur[i][0] = nu0[i].x; ucur[i][1] = nu0[i].y; ucur[i][2] = nu0[i].z; ucur[i][3] = nu0[i].w;
+      ucur[i][4] = nu1[i].x; ucur[i][5] = nu1[i].y; ucur[i][6] = nu1[i].z; ucur[i][7] = nu1[i].w;
+      rawd[i] = ndo[i];
+    }
+    fetch(base + step);
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = sub + LPR * i;
       if (rv && vi < nvec) {
         float sc[8], sh[8];
-        ldf8(a.uo + row * C + vi * 8, v[i]);
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dout + row * C + vi * 8));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = ucur[i][j];
+        const uint4 raw = rawd[i];
         ldf8(a.scale + vi * 8, sc);
         ldf8(a.shift + vi * 8, sh);
         unpack8(raw, dy[i]);
@@ -741,7 +769,8 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_out_vec_kernel(Bw
       const int vi = sub + LPR * i;
       if (rv && vi < nvec) {
         float u[8], o[8];
-        ldf8(a.uo + row * C + vi * 8, u);                 // second touch of the row: L1/L2 hit
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = ucur[i][j];    // (register copy of the row: no second global read)
         if (a.ln_w) {
           if (a.gate_before_ln && a.gate) {
             float sc[8], sh[8];
@@ -822,20 +851,41 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kerne
   float tau_acc = 0.f;
   const int n_begin = blockIdx.x * rows_per_chunk;
   const int n_end = min(a.N, n_begin + rows_per_chunk);
+  // Software pipeline: the two 16-byte loads per vector of the NEXT row group are issued before the current group's
+  // shuffle reductions (8-16 warps x one row group each is < 24 KB in flight per SM: latency-bound at ~1 TB/s without it).
+  uint4 nx[VPL], nd[VPL];
+  auto fetch = [&](int nb_) {
+    const int n_ = nb_ + rsub;
+    const bool ok = nb_ < n_end && n_ < n_end;
+    const long long r_ = (long long)b * a.N + n_;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = sub + LPR * i;
+      if (ok && vi < nvec) {
+        nx[i] = __ldg(reinterpret_cast<const uint4*>(x1 + r_ * C + vi * 8));
+        nd[i] = __ldg(reinterpret_cast<const uint4*>(dyp + r_ * C + vi * 8));
+      } else {
+        nx[i] = make_uint4(0u, 0u, 0u, 0u); nd[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  fetch(n_begin + warp * RPW);
   for (int nb = n_begin + warp * RPW; nb < n_end; nb += 8 * RPW) {
     const int n = nb + rsub;
     const bool rv = n < n_end;
     const long long row = (long long)b * a.N + n;
     const float gbase = rv ? (a.beta * a.sig[row] + tau_term + 1.f - a.alpha) : 0.f;
     float v[VPL][8], dv[VPL][8];
-    uint4 raw[VPL];
+    uint4 raw[VPL], rawd[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { raw[i] = nx[i]; rawd[i] = nd[i]; }
+    fetch(nb + 8 * RPW);
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = sub + LPR * i;
       if (rv && vi < nvec) {
-        raw[i] = __ldg(reinterpret_cast<const uint4*>(x1 + row * C + vi * 8));
-        const uint4 rd = __ldg(reinterpret_cast<const uint4*>(dyp + row * C + vi * 8));
+        const uint4 rd = rawd[i];
         float mm[8];
         ldf8(mrow + vi * 8, mm);
         unpack8(raw[i], v[i]);

@@ -41,3 +41,35 @@ def test_adapter_parameter_count():
         total += sum(v.numel() for k, v in p.items() if "running" not in k)
     # 188.5 M over the 48 adapters (gate_tk, one scalar per adapter, is not part of the engine's table)
     assert abs(total - 188.5e6) < 0.2e6, total
+
+
+def test_workloads_cover_the_baseline_configs():
+    """BASELINE.json configs: ave (1-3), s4 (4: B=4 clips x 5 frames, bicubic resampler), avqa_t60 (5: T=60, K=2, g=4), b224."""
+    b = _bench()
+    assert set(b.WORKLOADS) == {"ave", "b224", "s4", "avqa_t60"}
+    assert (b.WORKLOADS["s4"]["B"], b.WORKLOADS["s4"]["T"], b.WORKLOADS["s4"]["cfg"]["resampler"]) == (4, 5, "bicubic")
+    assert (b.WORKLOADS["avqa_t60"]["T"], b.WORKLOADS["avqa_t60"]["cfg"]["K"], b.WORKLOADS["avqa_t60"]["cfg"]["g"]) == (60, 2, 4)
+    assert b.WORKLOADS["b224"]["vis"] == [(128, 3136), (256, 784), (512, 196), (1024, 49)]
+    # the S4 stencil needs square token grids on both sides
+    import math
+    for (C, N) in b.WORKLOADS["s4"]["vis"] + b.AUD:
+        assert math.isqrt(N) ** 2 == N
+
+
+def test_stage_work_models_match_the_survey_totals():
+    b = _bench()
+    b._WL["name"] = "ave"
+    w = b.stage_work(80, b.ADAPTER_CFG)
+    # reference-order conv flops: 2.04 TFLOP of the resampler's 2.495 (SURVEY 8d; the fc product is the rest); the re-associated
+    # product contracts over min(C, C') columns, so the executed conv flops are lower
+    ref_order = sum(2 * 80 * b.dims(k, s)[1] * b.dims(k, s)[3] * b.dims(k, s)[2] for k, _, _, s in b.layer_list())
+    assert abs(ref_order / 1e12 - 2.04) < 0.02
+    assert 0.55 * ref_order < w["resample_conv"][0] < ref_order and w["resample_conv"][1] == "tensor"
+    assert w["bwd_dwres"][0] == w["resample_conv"][0] == w["bwd_dother"][0]
+    # row kernels: bytes = rows x C x bytes per element moved
+    rows_c = sum(80 * b.dims(k, s)[1] * b.dims(k, s)[0] for k, _, _, s in b.layer_list())
+    assert w["gate_ln"] == (rows_c * 4, "hbm", w["gate_ln"][2]) and w["bwd_out"][0] == rows_c * 8
+    b._WL["name"] = "s4"
+    ws = b.stage_work(20, b.WORKLOADS["s4"]["cfg"])
+    assert "resample_conv" not in ws and "bwd_dw" in ws          # the stencil is a gather, not a GEMM
+    b._WL["name"] = "ave"
