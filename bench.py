@@ -625,25 +625,30 @@ def run_engine(args, rank, world, local_rank):
     roof = None
     stage_ms = None
     eager_gpu = None
-    if rank == 0:
-        def step_sequential():                # one stream, so per-stage event times do not overlap
-            for kind, s_, p_, pk_ in stack:
-                x_, o_ = (vis[s_], aud[s_]) if kind == "vis" else (aud[s_], vis[s_])
-                adapter_forward_raw(CFG, p_, x_, o_, training=False, packed=pk_)
 
-        prof_fn = step_sequential
-        if args.mode == "train":
-            train_streams[0] = 1
-            prof_fn = step_train
+    def step_sequential():                # one stream, so per-stage event times do not overlap
+        for kind, s_, p_, pk_ in stack:
+            x_, o_ = (vis[s_], aud[s_]) if kind == "vis" else (aud[s_], vis[s_])
+            adapter_forward_raw(CFG, p_, x_, o_, training=False, packed=pk_)
+
+    prof_fn = step_sequential
+    if args.mode == "train":
+        train_streams[0] = 1
+        prof_fn = step_train
+    psteps = 2
+    prof = None
+    # The profiled train step contains the gradient all-reduce: EVERY rank must run it (rank 0 alone would wait for its
+    # peers inside NCCL forever); only rank 0 keeps the stage times.  The forward-only profile has no collective.
+    if rank == 0 or (args.mode == "train" and dist is not None):
         prof_fn()
         torch.cuda.synchronize(dev)
         L.profile_enable(True)
-        psteps = 2
         for _ in range(psteps):
             prof_fn()
         torch.cuda.synchronize(dev)
         prof = L.profile_collect()
         L.profile_enable(False)
+    if rank == 0:
         stage_ms = {k: round(v[0] / psteps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         peaks = {}
         try:
