@@ -679,6 +679,7 @@ def run_engine(args, rank, world, local_rank):
         roof["traffic"] = tr["bytes"] if tr else None     # dram bytes per launch from a committed `ncu --set full` capture, else null
         if tr:
             roof["traffic_source"] = tr["source"]
+            roof["traffic_algorithmic"] = tr.get("algorithmic_bytes")      # algorithmic bytes of that same launch
         roof["stages"] = entries
         tot_bytes = sum(alg_bytes(*dims(k, s), BT, K=CFG["K"], r=CFG["r"], g=CFG["g"]) for k, _, _, s in layer_list())
         tot_flops = sum(alg_flops(*dims(k, s), BT, K=CFG["K"], r=CFG["r"], g=CFG["g"]) for k, _, _, s in layer_list())

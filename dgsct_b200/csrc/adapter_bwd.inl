@@ -263,7 +263,7 @@ struct BwdPlan {
   size_t fwd;                        // keep-mode forward workspace
   size_t gUo, gZ, gY, gX1, S1, S2, gV, gU, gQ, gP, dTp, dTpB;
   size_t zero_begin, dm, dsig, ds, dtau, daq, dobar, dr1, colA, colB, colA1, colB1, dWup_d, dWd_d, zero_end;
-  size_t vA, vB, vC, vD, wA, wB, wC, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
+  size_t vA, vB, vC, vD, wA, wB, wC, vAb, vBb, wcatb, coefA, coefB, coefC, Wd_f32, Wup_f32, opm, out_fwd, smap_fwd, tmap_fwd, csm_part, fc_t, fc_s;
   size_t total;
 };
 
@@ -299,7 +299,9 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
   p.zero_end = off;
   p.fc_s = take(C * 4);
   p.vA = take(BT * C * 4); p.vD = take(BT * C * 4);
-  p.wA = take(BT * C * 4); p.wB = take(BT * C * 4); p.wC = take(BT * C * 4);   // second vector chain (own stream: own scratch)
+  p.wA = take(BT * C * 4); p.wB = take(BT * (C + H) * 4); p.wC = take(BT * C * 4);   // second vector chain (own stream: own scratch)
+  p.vAb = take(BT * (size_t)pad8((int)C) * 2); p.vBb = take(BT * (size_t)pad8((int)H) * 2);      // bf16 operand copies of the
+  p.wcatb = take(BT * (size_t)pad8((int)(C + H)) * 2);                                           // per-frame gradient vectors
   p.coefA = take(C * 4); p.coefB = take(C * 4); p.coefC = take(C * 4);
   p.Wd_f32 = take(Cd * C * 4); p.Wup_f32 = take(C * ldz * 4);
   p.opm = take(BT * C * 4);
@@ -373,6 +375,18 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   float* dWup_d = (float*)(ws + bp.dWup_d); float* dWd_d = (float*)(ws + bp.dWd_d);
   float* vA = (float*)(ws + bp.vA); float* vB = (float*)(ws + bp.vB); float* vC = (float*)(ws + bp.vC);
   float* wA = (float*)(ws + bp.wA); float* wB = (float*)(ws + bp.wB); float* wC = (float*)(ws + bp.wC);
+  bf16* vAb = (bf16*)(ws + bp.vAb); bf16* vBb = (bf16*)(ws + bp.vBb); bf16* wcatb = (bf16*)(ws + bp.wcatb);
+  const int ldcb = pad8(C), ldhb = pad8(H), ldcat = pad8(C + H);
+  // The per-frame-vector products (M or K = BT rows) run on the tcgen05 kernel with bf16 copies of the gradient vectors and
+  // the forward's packed weights (round 1: eight launches of the SIMT kernel, ~15 us each); DGSCT_VEC_SIMT=1 keeps the fp32 path.
+  const bool vec_tc = tcp && C % 8 == 0 && H % 8 == 0 && getenv("DGSCT_VEC_SIMT") == nullptr;
+  // D = A . B^T through the tensor-core kernel, or DGSCT_ERR_UNSUPPORTED (the caller then runs its SIMT twin)
+  auto vec_gemm = [&](const Gemm& g, const tc::OperandDesc& A, const tc::OperandDesc& B, int M_, int N_, int K_d, float* out, int ld,
+                      int mode) -> int {
+    EpiOut e = eo(out, 0, ld, 0, mode);
+    if (mode == OUT_ATOMIC) return run_tc_only(g, A, B, M_, N_, K_d, 1, to_tc_full<tc::EpiOut<false, OUT_ATOMIC, false, false, false>>(e));
+    return run_tc_only(g, A, B, M_, N_, K_d, 1, to_tc_full<tc::EpiOut<false, OUT_STORE, false, false, false>>(e));
+  };
   float* coefA = (float*)(ws + bp.coefA); float* coefB = (float*)(ws + bp.coefB); float* coefC = (float*)(ws + bp.coefC);
   float* Wd_f = (float*)(ws + bp.Wd_f32); float* Wup_f = (float*)(ws + bp.Wup_f32); float* opm = (float*)(ws + bp.opm);
   float* daq1 = daq; float* daq2 = daq + C; const int daq_ld = C + H;
@@ -592,26 +606,40 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     // dpm = dm * m (1-m) -> vA (BT,C)
     // (the parameter gradients of this chain -- two outer products over the BT rows and two bias sums -- go to the side stream)
     const Gemm GS{ST_BWD_SMALL, "bwd_small", st, false}, GSW{ST_BWD_SMALL, "bwd_small_dw", sst, false};
+    const bf16* hb = (const bf16*)(fw + fp.h);                 // forward's h (BT, ld_h) bf16 and q (BT, pad8(C)) bf16
+    const bf16* qb = (const bf16*)(fw + fp.vec_bf);
     count_launch();
-    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_SIGMOID_BWD, dm, C, mvec, C, 0.f, vA, C, BT, C);
+    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_SIGMOID_BWD, dm, C, mvec, C, 0.f, vA, C, BT, C, vec_tc ? vAb : nullptr, ldcb);
     KCHECK("dpm");
     // d_cb += colsum dpm ; dWc (C,H) += dpm^T h ; dh = dpm . Wc -> vB (BT,H)
     RC(fork_side());                                                  // vA = dpm is final
     col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, sst>>>(vA, 0, C, nullptr, 0, 0, BT, C, G.c_b, nullptr);
-    EpiOut e1 = eo(G.c_w, 0, H, 0, OUT_ADD);
-    RC(run_gemm(GSW, MN_(vA, BT, C, C, 0), 0, MN_(hsrc, BT, H, h_ld, 0), 0, C, H, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
-    EpiOut e2 = eo(vB, 0, H, 0, OUT_STORE);
-    RC(run_gemm(GS, K_(vA, BT, C, C, 0), 0, MN_(P.c_w, C, H, H, 0), 0, BT, H, C, 1, tc::EpiNone{}, e2, AxIdentity{}, true, 0, false, true));
+    int rcv = vec_tc ? vec_gemm(GSW, MN_(vAb, BT, C, ldcb, 0), MN_(hb, BT, H, pp.ld_h, 0), C, H, BT, G.c_w, H, OUT_ATOMIC) : DGSCT_ERR_UNSUPPORTED;
+    if (rcv == DGSCT_ERR_UNSUPPORTED) {
+      EpiOut e1 = eo(G.c_w, 0, H, 0, OUT_ADD);
+      RC(run_gemm(GSW, MN_(vA, BT, C, C, 0), 0, MN_(hsrc, BT, H, h_ld, 0), 0, C, H, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
+    } else if (rcv) return rcv;
+    rcv = vec_tc ? vec_gemm(GS, K_(vAb, BT, C, ldcb, 0), MN_(pk + pp.catt, C, H, pp.ld_h, 0), BT, H, C, vB, H, OUT_STORE) : DGSCT_ERR_UNSUPPORTED;
+    if (rcv == DGSCT_ERR_UNSUPPORTED) {
+      EpiOut e2 = eo(vB, 0, H, 0, OUT_STORE);
+      RC(run_gemm(GS, K_(vA, BT, C, C, 0), 0, MN_(P.c_w, C, H, H, 0), 0, BT, H, C, 1, tc::EpiNone{}, e2, AxIdentity{}, true, 0, false, true));
+    } else if (rcv) return rcv;
     // dph = dh * 1[h>0] -> vB in place ; d_bb += colsum ; dWb (H,C) += dph^T q ; dq = dph . Wb -> vC (BT,C)
     count_launch(2);
-    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, vB, H, hsrc, h_ld, 0.f, vB, H, BT, H);
+    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, vB, H, hsrc, h_ld, 0.f, vB, H, BT, H, vec_tc ? vBb : nullptr, ldhb);
     RC(fork_side());                                                  // vB = dph is final
     col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, sst>>>(vB, 0, H, nullptr, 0, 0, BT, H, G.bott_b, nullptr);
     KCHECK("dph");
-    EpiOut e3 = eo(G.bott_w, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GSW, MN_(vB, BT, H, H, 0), 0, MN_(qvec, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
-    EpiOut e4 = eo(vC, 0, C, 0, OUT_STORE);
-    RC(run_gemm(GS, K_(vB, BT, H, H, 0), 0, MN_(P.bott_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e4, AxIdentity{}, true, 0, false, true));
+    rcv = vec_tc ? vec_gemm(GSW, MN_(vBb, BT, H, ldhb, 0), MN_(qb, BT, C, pad8(C), 0), H, C, BT, G.bott_w, C, OUT_ATOMIC) : DGSCT_ERR_UNSUPPORTED;
+    if (rcv == DGSCT_ERR_UNSUPPORTED) {
+      EpiOut e3 = eo(G.bott_w, 0, C, 0, OUT_ADD);
+      RC(run_gemm(GSW, MN_(vB, BT, H, H, 0), 0, MN_(qvec, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e3, AxIdentity{}, true));
+    } else if (rcv) return rcv;
+    rcv = vec_tc ? vec_gemm(GS, K_(vBb, BT, H, ldhb, 0), MN_(pk + pp.bott, H, C, pp.ld_c, 0), BT, C, H, vC, C, OUT_STORE) : DGSCT_ERR_UNSUPPORTED;
+    if (rcv == DGSCT_ERR_UNSUPPORTED) {
+      EpiOut e4 = eo(vC, 0, C, 0, OUT_STORE);
+      RC(run_gemm(GS, K_(vB, BT, H, H, 0), 0, MN_(P.bott_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e4, AxIdentity{}, true, 0, false, true));
+    } else if (rcv) return rcv;
     // q = aq1 * r1sum / N : daq1 = dq * r1sum / N ; dr1 = dq * aq1 / N
     count_launch(2);
     vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_MUL_SCALE, vC, C, r1sum, C, invN, daq1, daq_ld, BT, C);
@@ -641,21 +669,42 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     // Runs on the second auxiliary stream with scratch of its own: d obar is first read by sum_frames_kernel / the dV products.
     RC(fork_side2());                                                 // daq1 / daq2 / dtau are final
     const Gemm GS{ST_BWD_SMALL, "bwd_small", s2, false};
-    count_launch(3);
-    cast_scale_kernel<<<ceil_div(BT * C, 256), 256, 0, s2>>>(osum, invN, wA, 0, (size_t)BT * C);                     // obar -> wA
-    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, s2>>>(VOP_RELU_BWD, daq1, daq_ld, aq1, aq_ld, 0.f, wB, C, BT, C);  // dpa1 -> wB
-    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, s2>>>(VOP_RELU_BWD, daq2, daq_ld, aq2, aq2_ld, 0.f, wC, H, BT, H); // dpa2 -> wC
-    KCHECK("dpa");
-    count_launch(2);
-    col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, s2>>>(wB, 0, C, nullptr, 0, 0, BT, C, G.a1_b, nullptr);
-    col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, s2>>>(wC, 0, H, nullptr, 0, 0, BT, H, G.a2_b, nullptr);
-    EpiOut e1 = eo(G.a1_w, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, MN_(wB, BT, C, C, 0), 0, MN_(wA, BT, C, C, 0), 0, C, C, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
-    EpiOut e2 = eo(G.a2_w, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, MN_(wC, BT, H, H, 0), 0, MN_(wA, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
-    EpiOut e3 = eo(dobar, 0, C, 0, OUT_ADD);
-    RC(run_gemm(GS, K_(wB, BT, C, C, 0), 0, MN_(P.a1_w, C, C, C, 0), 0, BT, C, C, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
-    RC(run_gemm(GS, K_(wC, BT, H, H, 0), 0, MN_(P.a2_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
+    const bf16* obar_b = (const bf16*)(fw + fp.vec_bf_o);         // forward's bf16 obar (BT, pad8(C))
+    // [dpa1 | dpa2] = [daq1 | daq2] * 1[[aq1 | aq2] > 0] in ONE pass over the concatenated (BT, C+H) vectors -> wB (+ bf16 copy)
+    count_launch((d.flags & DGSCT_F_TEMPORAL) ? 2 : 1);
+    if (d.flags & DGSCT_F_TEMPORAL)
+      cast_scale_kernel<<<ceil_div(BT * C, 256), 256, 0, s2>>>(osum, invN, wA, 0, (size_t)BT * C);                   // obar -> wA (temporal gate)
+    bool cat_ok = vec_tc && aq_ld == C + H && aq2_ld == C + H && daq_ld == C + H;
+    if (cat_ok) {
+      vec_op_kernel<<<ceil_div(BT * (C + H), 256), 256, 0, s2>>>(VOP_RELU_BWD, daq1, daq_ld, aq1, aq_ld, 0.f, wB, C + H, BT, C + H, wcatb, ldcat);
+      KCHECK("dpa");
+      count_launch(2);
+      col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, s2>>>(wB, 0, C + H, nullptr, 0, 0, BT, C, G.a1_b, nullptr);
+      col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, s2>>>(wB + C, 0, C + H, nullptr, 0, 0, BT, H, G.a2_b, nullptr);
+      int r1 = vec_gemm(GS, MN_(wcatb, BT, C, ldcat, 0), MN_(obar_b, BT, C, pad8(C), 0), C, C, BT, G.a1_w, C, OUT_ATOMIC);
+      int r2 = r1 ? r1 : vec_gemm(GS, MN_(wcatb + C, BT, H, ldcat, 0), MN_(obar_b, BT, C, pad8(C), 0), H, C, BT, G.a2_w, C, OUT_ATOMIC);
+      // d obar = [dpa1 | dpa2] . [Wa1 ; Wa2]  : one product over K = C + H (the forward's packed [a1_w ; a2_w])
+      int r3 = r2 ? r2 : vec_gemm(GS, K_(wcatb, BT, C + H, ldcat, 0), MN_(pk + pp.cat1, C + H, C, pp.ld_c, 0), BT, C, C + H, dobar, C, OUT_ATOMIC);
+      if (r3 == DGSCT_ERR_UNSUPPORTED && r1 == DGSCT_ERR_UNSUPPORTED) cat_ok = false;       // nothing was launched: SIMT chain below
+      else if (r3) return r3;
+    }
+    if (!cat_ok) {
+      if (!(d.flags & DGSCT_F_TEMPORAL)) { count_launch(); cast_scale_kernel<<<ceil_div(BT * C, 256), 256, 0, s2>>>(osum, invN, wA, 0, (size_t)BT * C); }
+      count_launch(2);
+      vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, s2>>>(VOP_RELU_BWD, daq1, daq_ld, aq1, aq_ld, 0.f, wB, C, BT, C);  // dpa1 -> wB
+      vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, s2>>>(VOP_RELU_BWD, daq2, daq_ld, aq2, aq2_ld, 0.f, wC, H, BT, H); // dpa2 -> wC
+      KCHECK("dpa");
+      count_launch(2);
+      col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, s2>>>(wB, 0, C, nullptr, 0, 0, BT, C, G.a1_b, nullptr);
+      col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, s2>>>(wC, 0, H, nullptr, 0, 0, BT, H, G.a2_b, nullptr);
+      EpiOut e1 = eo(G.a1_w, 0, C, 0, OUT_ADD);
+      RC(run_gemm(GS, MN_(wB, BT, C, C, 0), 0, MN_(wA, BT, C, C, 0), 0, C, C, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
+      EpiOut e2 = eo(G.a2_w, 0, C, 0, OUT_ADD);
+      RC(run_gemm(GS, MN_(wC, BT, H, H, 0), 0, MN_(wA, BT, C, C, 0), 0, H, C, BT, 1, tc::EpiNone{}, e2, AxIdentity{}, true));
+      EpiOut e3 = eo(dobar, 0, C, 0, OUT_ADD);
+      RC(run_gemm(GS, K_(wB, BT, C, C, 0), 0, MN_(P.a1_w, C, C, C, 0), 0, BT, C, C, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
+      RC(run_gemm(GS, K_(wC, BT, H, H, 0), 0, MN_(P.a2_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e3, AxIdentity{}, true, 0, false, true));
+    }
     if (d.flags & DGSCT_F_TEMPORAL) {
       count_launch();
       temporal_bwd_kernel<<<BT, 128, 0, s2>>>(use_tau ? dtau : nullptr, dtmap, tau, wA, P.t_w, C, dobar, G.t_w, G.t_b);

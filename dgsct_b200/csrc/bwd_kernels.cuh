@@ -342,8 +342,9 @@ __global__ void bwd_channel_mask_kernel(void* __restrict__ z1, int bf, int C, in
 // ---- small per-frame vector ops (BT x width) ---------------------------------------------------------------------
 enum { VOP_SIGMOID_BWD = 0, VOP_RELU_BWD = 1, VOP_MUL_SCALE = 2 };
 // out[i] = op(g[i], y[i]) : sigmoid bwd g*y*(1-y) ; relu bwd g*1[y>0] ; mul-scale g*y*alpha
+// (out16: optional bf16 copy with pitch out16_ld, the tensor-core operand of the per-frame-vector products)
 __global__ void vec_op_kernel(int op, const float* g, int g_ld, const float* __restrict__ y, int y_ld, float alpha,
-                              float* out, int out_ld, int rows, int cols) {
+                              float* out, int out_ld, int rows, int cols, bf16* __restrict__ out16 = nullptr, int out16_ld = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int r = i / cols, c = i % cols;
@@ -353,6 +354,7 @@ __global__ void vec_op_kernel(int op, const float* g, int g_ld, const float* __r
   else if (op == VOP_RELU_BWD) v = yv > 0.f ? gv : 0.f;
   else v = gv * yv * alpha;
   out[(size_t)r * out_ld + c] = v;
+  if (out16) out16[(size_t)r * out16_ld + c] = __float2bfloat16_rn(v);
 }
 
 // ---- token attention backward helpers ----------------------------------------------------------------------------
