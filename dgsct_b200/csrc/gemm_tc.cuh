@@ -13,6 +13,7 @@
 // resident per SM so the epilogue of one tile overlaps the main loop of another.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -548,7 +549,12 @@ inline cudaError_t launch(const Params& p, EPI epi, cudaStream_t st) {
   }
   const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) *
                           (p.kb_frames > 0 ? ceil_div(p.batch, p.kb_frames) : ceil_div(p.batch, p.fpack));
-  const long long slots = (long long)num_sms() * p.ctas_per_sm;
+  long long slots = (long long)num_sms() * p.ctas_per_sm;
+  // DGSCT_TC_SLOT_PCT (experiment): percentage of the CTA slots one GEMM may take.  Several streams run GEMMs side by side
+  // (the two adapters of a position, the weight-gradient stream): a persistent CTA that walks 2-3 tiles overlaps its own
+  // epilogues with the next main loop AND leaves SMs to the neighbour stream.
+  static const int slot_pct = [] { const char* e = getenv("DGSCT_TC_SLOT_PCT"); const int v = e ? atoi(e) : 100; return v < 10 || v > 100 ? 100 : v; }();
+  if (slot_pct < 100) { slots = slots * slot_pct / 100; if (slots < 1) slots = 1; }
   const int grid = (int)(tiles < slots ? tiles : slots);
   gemm_tc_kernel<EPI><<<grid, THREADS, smem, st>>>(p, epi);
   return cudaGetLastError();
