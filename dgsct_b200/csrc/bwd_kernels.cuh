@@ -662,9 +662,13 @@ __global__ void densify_grouped_kernel(const float* __restrict__ src, int out_ch
 
 // out = gate * LN_post(B2) [AVE] or LN_post(gate * B2) [AVS], B2 = uo*scale + shift.  Also accumulates the bn2-backward
 // column sums colA[c] += sum dB2, colB[c] += sum dB2*uo (NULL to skip) so that no separate reduction pass is needed.
-template <int LPR, int VPL>
+// SMACC (wide rows, VPL > 4: C = 1536): the per-lane column accumulators (4 x VPL x 8 registers) would not fit next to the row
+// data, so every element adds straight into the block's shared-memory partials instead (such shapes have few rows; round 1
+// sent them to the scalar kernel: 71 / 122 us for a 9 MB tensor).
+template <int LPR, int VPL, bool SMACC = (VPL > 4)>
 __global__ void __launch_bounds__(256, (VPL <= 1 ? 2 : 1)) bwd_out_vec_kernel(BwdOutArgs a, float* __restrict__ colA, float* __restrict__ colB) {
   extern __shared__ float sm[];                 // [4][C] block partials: d_lnw, d_lnb, colA, colB
+  constexpr int AV = SMACC ? 1 : VPL;
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR;
   const int C = a.C, nvec = C >> 3;
@@ -675,9 +679,9 @@ __global__ void __launch_bounds__(256, (VPL <= 1 ? 2 : 1)) bwd_out_vec_kernel(Bw
   bf16* db2 = reinterpret_cast<bf16*>(a.db2);
   const float g = a.gate ? a.gate[0] : 1.f;
   const float gpre = a.gate_before_ln ? g : 1.f, gpost = a.gate_before_ln ? 1.f : g;
-  float cw[VPL][8], cb[VPL][8], ca[VPL][8], cq[VPL][8];
+  float cw[AV][8], cb[AV][8], ca[AV][8], cq[AV][8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
+  for (int i = 0; i < AV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { cw[i][j] = 0.f; cb[i][j] = 0.f; ca[i][j] = 0.f; cq[i][j] = 0.f; }
   float gate_acc = 0.f;
@@ -755,8 +759,8 @@ __global__ void __launch_bounds__(256, (VPL <= 1 ? 2 : 1)) bwd_out_vec_kernel(Bw
             const float xhat = (v[i][j] - mean) * rstd;
             const float dL = dy[i][j] * gpost;
             if (!a.gate_before_ln && a.gate) gate_acc += dy[i][j] * fmaf(xhat, w[j], bb[j]);   // AVE: d_gate = sum dOut * L
-            cw[i][j] += dL * xhat;
-            cb[i][j] += dL;
+            if (SMACC) { atomicAdd(&sm[vi * 8 + j], dL * xhat); atomicAdd(&sm[C + vi * 8 + j], dL); }
+            else { cw[SMACC ? 0 : i][j] += dL * xhat; cb[SMACC ? 0 : i][j] += dL; }
             const float dxh = dL * w[j];
             s1 += dxh; s2 += dxh * xhat;
             v[i][j] = xhat; dy[i][j] = dxh;
@@ -796,13 +800,17 @@ __global__ void __launch_bounds__(256, (VPL <= 1 ? 2 : 1)) bwd_out_vec_kernel(Bw
         }
         *reinterpret_cast<uint4*>(db2 + row * C + vi * 8) = pack8(o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ca[i][j] += o[j]; cq[i][j] += o[j] * u[j]; }
+        for (int j = 0; j < 8; ++j) {
+          if (SMACC) { atomicAdd(&sm[2 * C + vi * 8 + j], o[j]); atomicAdd(&sm[3 * C + vi * 8 + j], o[j] * u[j]); }
+          else { ca[SMACC ? 0 : i][j] += o[j]; cq[SMACC ? 0 : i][j] += o[j] * u[j]; }
+        }
       }
     }
   }
   // flush: row groups of the warp -> block partials in shared memory -> one global atomic per column per block
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
+  for (int i = 0; i < AV; ++i) {
+    if (SMACC) break;
     const int vi = sub + LPR * i;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -831,9 +839,10 @@ __global__ void __launch_bounds__(256, (VPL <= 1 ? 2 : 1)) bwd_out_vec_kernel(Bw
 
 // LN_before + gate-combine backward; grid (row chunks, BT): a block stays inside one frame, so the channel-gate gradient
 // dm[b, c] is a per-lane register sum as well.
-template <int LPR, int VPL>
+template <int LPR, int VPL, bool SMACC = (VPL > 4)>
 __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kernel(BwdGateLnArgs a, int rows_per_chunk) {
   extern __shared__ float sm[];                 // [3][C] block partials: d_lnw, d_lnb, dm
+  constexpr int AV = SMACC ? 1 : VPL;           // (SMACC: see bwd_out_vec_kernel)
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % LPR, rsub = lane / LPR;
   const int C = a.C, nvec = C >> 3, b = blockIdx.y;
@@ -845,9 +854,9 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kerne
   bf16* dx1 = reinterpret_cast<bf16*>(a.dx1);
   const float* mrow = a.m + (size_t)b * C;
   const float tau_term = a.tau ? a.gamma * a.tau[b] : 0.f;
-  float cw[VPL][8], cb[VPL][8], cm[VPL][8];
+  float cw[AV][8], cb[AV][8], cm[AV][8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
+  for (int i = 0; i < AV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { cw[i][j] = 0.f; cb[i][j] = 0.f; cm[i][j] = 0.f; }
   float tau_acc = 0.f;
@@ -920,8 +929,8 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kerne
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float xhat = (v[i][j] - mean) * rstd;
-            cw[i][j] += dv[i][j] * xhat;
-            cb[i][j] += dv[i][j];
+            if (SMACC) { atomicAdd(&sm[vi * 8 + j], dv[i][j] * xhat); atomicAdd(&sm[C + vi * 8 + j], dv[i][j]); }
+            else { cw[SMACC ? 0 : i][j] += dv[i][j] * xhat; cb[SMACC ? 0 : i][j] += dv[i][j]; }
             const float dxh = dv[i][j] * w[j];
             s1 += dxh; s2 += dxh * xhat;
             v[i][j] = xhat; dv[i][j] = dxh;
@@ -947,7 +956,8 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kerne
         for (int j = 0; j < 8; ++j) {
           const float dgm = dv[i][j] * xr[j];
           rowdot += dgm;
-          cm[i][j] += dgm;
+          if (SMACC) atomicAdd(&sm[2 * C + vi * 8 + j], dgm);
+          else cm[SMACC ? 0 : i][j] += dgm;
           o[j] = dv[i][j] * fmaf(a.alpha, mm[j], gbase);
         }
         *reinterpret_cast<uint4*>(dx1 + row * C + vi * 8) = pack8(o);
@@ -960,7 +970,8 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kerne
     }
   }
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
+  for (int i = 0; i < AV; ++i) {
+    if (SMACC) break;
     const int vi = sub + LPR * i;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -988,11 +999,11 @@ __global__ void __launch_bounds__(256, (VPL <= 2 ? 2 : 1)) bwd_gate_ln_vec_kerne
 struct BwdOutLaunch {
   const BwdOutArgs& a; float* colA; float* colB; cudaStream_t st; bool* ok;
   template <int LPR, int VPL> void run() {
-    if (VPL > 4) { *ok = false; return; }
+    if (VPL > 6) { *ok = false; return; }
     const long long rows_per_block = 8LL * (32 / LPR);
     long long blocks = (a.rows + rows_per_block - 1) / rows_per_block;
     if (blocks > 2 * 148) blocks = 2 * 148;              // every block resident (1 or 2 per SM): one flush per block
-    bwd_out_vec_kernel<LPR, (VPL > 4 ? 1 : VPL)><<<(unsigned)blocks, 256, (size_t)4 * a.C * 4, st>>>(a, colA, colB);
+    bwd_out_vec_kernel<LPR, (VPL > 6 ? 1 : VPL)><<<(unsigned)blocks, 256, (size_t)4 * a.C * 4, st>>>(a, colA, colB);
     *ok = true;
   }
 };
@@ -1009,7 +1020,7 @@ inline bool launch_bwd_out_vec(const BwdOutArgs& a, float* colA, float* colB, cu
 struct BwdGateLnLaunch {
   const BwdGateLnArgs& a; int BT; cudaStream_t st; bool* ok;
   template <int LPR, int VPL> void run() {
-    if (VPL > 4) { *ok = false; return; }
+    if (VPL > 6) { *ok = false; return; }
     const int rows_per_iter = 8 * (32 / LPR);
     int chunks = (a.N + rows_per_iter - 1) / rows_per_iter;          // at least one block iteration per chunk
     const int want = (4 * 148 + BT - 1) / BT;                        // ~4 blocks per SM overall
@@ -1018,7 +1029,7 @@ struct BwdGateLnLaunch {
     int rpc = (a.N + chunks - 1) / chunks;
     rpc = (rpc + rows_per_iter - 1) / rows_per_iter * rows_per_iter;
     chunks = (a.N + rpc - 1) / rpc;
-    bwd_gate_ln_vec_kernel<LPR, (VPL > 4 ? 1 : VPL)><<<dim3(chunks, BT), 256, (size_t)3 * a.C * 4, st>>>(a, rpc);
+    bwd_gate_ln_vec_kernel<LPR, (VPL > 6 ? 1 : VPL)><<<dim3(chunks, BT), 256, (size_t)3 * a.C * 4, st>>>(a, rpc);
     *ok = true;
   }
 };

@@ -549,12 +549,9 @@ inline cudaError_t launch(const Params& p, EPI epi, cudaStream_t st) {
   }
   const long long tiles = (long long)ceil_div(p.N, p.BN) * ceil_div(p.M, BM) *
                           (p.kb_frames > 0 ? ceil_div(p.batch, p.kb_frames) : ceil_div(p.batch, p.fpack));
-  long long slots = (long long)num_sms() * p.ctas_per_sm;
-  // DGSCT_TC_SLOT_PCT (experiment): percentage of the CTA slots one GEMM may take.  Several streams run GEMMs side by side
-  // (the two adapters of a position, the weight-gradient stream): a persistent CTA that walks 2-3 tiles overlaps its own
-  // epilogues with the next main loop AND leaves SMs to the neighbour stream.
-  static const int slot_pct = [] { const char* e = getenv("DGSCT_TC_SLOT_PCT"); const int v = e ? atoi(e) : 100; return v < 10 || v > 100 ? 100 : v; }();
-  if (slot_pct < 100) { slots = slots * slot_pct / 100; if (slots < 1) slots = 1; }
+  // (measured in round 2: capping a GEMM at 75 / 50 / 35 % of the CTA slots to leave SMs to the neighbour streams costs
+  //  +3 / +6 / +13 ms per train step -- the small products are latency-bound and want every CTA they can get)
+  const long long slots = (long long)num_sms() * p.ctas_per_sm;
   const int grid = (int)(tiles < slots ? tiles : slots);
   gemm_tc_kernel<EPI><<<grid, THREADS, smem, st>>>(p, epi);
   return cudaGetLastError();

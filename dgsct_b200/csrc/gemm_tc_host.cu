@@ -120,6 +120,15 @@ int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B_in, int
   if (BN_hint > 0) BN = BN_hint;
   else if (N <= 256) BN = round_up(N, 16);
   else { const int nb = (N + 255) / 256; BN = round_up((N + nb - 1) / nb, 16); }
+  {   // Medium-K products take tiles of at most 128 columns: twice the CTAs of a 256-column tile and a double-buffered
+      // accumulator (epilogue under the next main loop).  Measured on the train step (B200, round 2): cap 256 -> 56.4 ms,
+      // 192 -> 56.8, 128 -> 54.3, 96 -> 54.2, 64 -> 55.2.  DGSCT_TC_BN_MAX overrides (256 = the old rule).
+    static const int bn_max = [] { const char* e = getenv("DGSCT_TC_BN_MAX"); const int v = e ? atoi(e) : 128; return (v >= 32 && v <= 256) ? v / 16 * 16 : 128; }();
+    if (BN_hint <= 0 && !sum_over_batch && BN > bn_max && (K + 63) / 64 <= 32) {
+      const int nb = (N + bn_max - 1) / bn_max;
+      BN = round_up((N + nb - 1) / nb, 16);
+    }
+  }
   if (BN < 16 || BN > 256 || BN % 16) return DGSCT_ERR_UNSUPPORTED;
   p.BN = BN;
   p.BK = (K > 32) ? 64 : 32;
@@ -195,6 +204,8 @@ int make_params(Params& p, const OperandDesc& A_in, const OperandDesc& B_in, int
     // TMA/MMA streams hide each other's barrier round trips (968 vs 713 TFLOP/s on the stage-0 resampler).
     int st = 0;
     const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+    // (tried in round 2: one big-smem CTA per SM with the deepest ring for grids that fit in one wave -- 56.4 ms against
+    //  55.5 ms per train step without it; two half-smem CTAs per SM stay the rule)
     if (2 * stage_bytes <= 104 * 1024 && plan(2, false, st)) { ctas = 2; stages = st; }
     else if (plan(1, false, st)) { ctas = 1; stages = st; }
     else return DGSCT_ERR_UNSUPPORTED;
