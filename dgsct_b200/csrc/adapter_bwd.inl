@@ -287,9 +287,9 @@ static BwdPlan make_bwd_plan(const dgsct_desc& d, bool have_saved = false) {
     p.gU = take(gu * es); }
   p.gQ = take(BT * N * (size_t)pad8((int)K) * es);   // dQraw -> dL2 ; later dL1 (bf16 rows padded to 16 bytes)
   p.gP = take(BT * N * K * 4);           // dP fp32
-  p.dTp = take(BT * K * C * 4);
   p.dTpB = take(BT * K * C * 2);
   p.zero_begin = off;
+  p.dTp = take(BT * K * C * 4);          // (zeroed: the fused attention backward accumulates into it)
   p.dm = take(BT * C * 4); p.dsig = take(BT * N * 4); p.ds = take(BT * N * 4); p.dtau = take(BT * 4);
   p.daq = take(BT * (C + H) * 4); p.dobar = take(BT * C * 4); p.dr1 = take(BT * C * 4);
   p.colA = take(C * 4); p.colB = take(C * 4); p.colA1 = take(C * 4); p.colB1 = take(C * 4);
@@ -713,59 +713,92 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   }
   // ---- 7. latent-token attention -----------------------------------------------------------------------------------
   {
-    // dQraw = G . Tp^T -> gQ ; dL2 (in place) ; d_gate_av
-    EpiOut e1 = eo(gQ, bf, ldq, sbq, OUT_STORE);
-    RC(run_gemm(G_TK, K_(gX1, N, C, C, (long long)N * C), bf, K_(TpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
-                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
-    { StageScope _sc(ST_ROW_SOFTMAX, st); count_launch();
-      row_softmax_bwd_kernel<<<rgrid, 256, 0, st>>>(gQ, Qm, bf, R, K, ldq, P.gate_av, G.gate_av);
-      KCHECK("row_softmax_bwd"); }
-    // dTp[b,k,c] = g sum_n Q G + sum_n dL2 x     (computed as D(c,k), written transposed)
-    EpiOut e2 = eo(dTp, 0, C, (long long)K * C, OUT_STORE); e2.transposed = 1; e2.alpha_ptr = P.gate_av;
-    RC(run_gemm(G_TK, MN_(gX1, N, C, C, (long long)N * C), bf, MN_(Qm, N, K, ldq, sbq), bf, C, K, N, BT,
-                to_tcT<tc::EpiOutT<OUT_STORE>>(e2), e2, AxIdentity{}, true));
-    EpiOut e3 = eo(dTp, 0, C, (long long)K * C, OUT_ADD); e3.transposed = 1;
-    RC(run_gemm(G_TK, MN_(x, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, ldq, sbq), bf, C, K, N, BT,
-                to_tcT<tc::EpiOutT<OUT_ADD>>(e3), e3, AxIdentity{}, true));
-    // dx = G + dL2 . Tp
-    EpiOut e4 = eo(dx, bf, C, (long long)N * C, OUT_STORE); e4.resid = gX1; e4.resid_bf16 = bf;
-    RC(run_gemm(G_TK, K_(gQ, N, K, ldq, sbq), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
-                to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
+    // Fused kernels (attn_fused.cuh) when the shape qualifies: x_attn_bwd replaces five launches (dQraw, row-softmax backward,
+    // two dT' products, dx), tok_attn_bwd six (dP, the split column-softmax backward, two dV products, the d-token product).
+    const fa::XAttnBwdPlan fb_b = fa::make_x_attn_bwd_plan(BT, N, C, K);
+    const bool fused_b = tcp && fb_b.ok && getenv("DGSCT_NO_FUSED_ATTN_BWD") == nullptr && getenv("DGSCT_NO_FUSED_ATTN") == nullptr &&
+                         (((uintptr_t)x | (uintptr_t)dx) & 15) == 0;
+    const fa::TokAttnBwdPlan fb_a = fa::make_tok_attn_bwd_plan(BT, N, C, K);
+    const bool fused_a = tcp && fb_a.ok && fused_attn_bwd_a_enabled(d, x, pp);
+    if (fused_b) {
+      fa::XAttnBwdArgs a{};
+      a.G = (const bf16*)gX1; a.x = (const bf16*)x; a.TpB = (const bf16*)TpOp; a.Qb = (const bf16*)Qm;
+      a.dx = (bf16*)dx; a.dTp = dTp; a.gate_av = P.gate_av; a.d_gate_av = G.gate_av; a.err_flag = timeout_flag_device_ptr();
+      a.N = N; a.C = C; a.K = K; a.Kp = ldq; a.R = fb_b.R; a.nchunks = fb_b.nchunks; a.splits = fb_b.splits; a.zcols = fb_b.zcols;
+      StageScope _sc(ST_BWD_TOKEN, st); count_launch();
+      cudaError_t e = fa::launch_x_attn_bwd(a, fb_b, BT, st);
+      if (e != cudaSuccess) { set_cuda_error(e, "x_attn_bwd_fused"); return DGSCT_ERR_CUDA; }
+    } else {
+      // dQraw = G . Tp^T -> gQ ; dL2 (in place) ; d_gate_av
+      EpiOut e1 = eo(gQ, bf, ldq, sbq, OUT_STORE);
+      RC(run_gemm(G_TK, K_(gX1, N, C, C, (long long)N * C), bf, K_(TpOp, K, C, C, (long long)K * C), wbf, N, K, C, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+      { StageScope _sc(ST_ROW_SOFTMAX, st); count_launch();
+        row_softmax_bwd_kernel<<<rgrid, 256, 0, st>>>(gQ, Qm, bf, R, K, ldq, P.gate_av, G.gate_av);
+        KCHECK("row_softmax_bwd"); }
+      // dTp[b,k,c] = g sum_n Q G + sum_n dL2 x     (computed as D(c,k), written transposed)
+      EpiOut e2 = eo(dTp, 0, C, (long long)K * C, OUT_STORE); e2.transposed = 1; e2.alpha_ptr = P.gate_av;
+      RC(run_gemm(G_TK, MN_(gX1, N, C, C, (long long)N * C), bf, MN_(Qm, N, K, ldq, sbq), bf, C, K, N, BT,
+                  to_tcT<tc::EpiOutT<OUT_STORE>>(e2), e2, AxIdentity{}, true));
+      EpiOut e3 = eo(dTp, 0, C, (long long)K * C, OUT_ADD); e3.transposed = 1;
+      RC(run_gemm(G_TK, MN_(x, N, C, C, (long long)N * C), bf, MN_(gQ, N, K, ldq, sbq), bf, C, K, N, BT,
+                  to_tcT<tc::EpiOutT<OUT_ADD>>(e3), e3, AxIdentity{}, true));
+      // dx = G + dL2 . Tp
+      EpiOut e4 = eo(dx, bf, C, (long long)N * C, OUT_STORE); e4.resid = gX1; e4.resid_bf16 = bf;
+      RC(run_gemm(G_TK, K_(gQ, N, K, ldq, sbq), bf, MN_(TpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, true, false, false>>(e4), e4, AxIdentity{}, true));
+    }
     // d tokens += sum_b dTp[b]
     RC(join_side2());                                                 // d obar (second vector chain) is needed from here on
     const void* dTpOp = dTp;
     long long dTp_bs = (long long)K * C;
     { StageScope _sc(ST_MISC, st); count_launch(2);
       sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, st>>>(dTp, BT, (size_t)K * C, G.tokens, G.fc_b, C, dobar);   // + d fc_b (exact)
-      if (tcp) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
+      if (tcp && !fused_a) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
       KCHECK("dtok_sum"); }
-    // dP = V . dTp^T (fp32) ; dL1 = P (dP - sum_n dP P) -> gQ
-    EpiOut e5 = eo(gP, 0, K, (long long)N * K, OUT_STORE);
-    RC(run_gemm(G_TK, K_(V, N, C, C, (long long)N * C), bf, K_(dTpOp, K, C, C, dTp_bs), wbf, N, K, C, BT,
-                to_tc_full<tc::EpiOut<false, OUT_STORE, false, false, false>>(e5), e5, AxIdentity{}, true));
-    { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
-      if (K > 256) return DGSCT_ERR_UNSUPPORTED;
-      { const dim3 grid(csm_num_chunks(N), BT);
-        float* part = (float*)(ws + bp.csm_part);
-        count_launch();
-        col_softmax_bwd_partial_kernel<<<grid, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, part, N, K, ldq);
-        col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K, ldq); }
-      KCHECK("col_softmax_bwd"); }
-    // dV = P . dTp + dL1 . T + dobar / N
-    EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
-    const void* dL1 = gQ; long long dL1_ld = ldq, dL1_bs = sbq;
-    {
-      RC(run_gemm(G_TK, K_(Pm, N, K, ldq, sbq), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
-                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
-      EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
-      RC(run_gemm(G_TK, K_(gQ, N, K, ldq, sbq), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
-                  to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
+    if (fused_a) {
+      float* Dv = (float*)(ws + bp.csm_part);               // D[b,k] = sum_n dP P  (BT x K)
+      { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
+        fa::dtp_prep_kernel<<<ceil_div(BT * K * 32, 256), 256, 0, st>>>(dTp, Tp, P.tokens, dTpB, Dv, BT, K, C);
+        KCHECK("dtp_prep"); }
+      fa::TokAttnBwdArgs a{};
+      a.V = (const bf16*)V; a.tokb = (const bf16*)Tok_op; a.dTpB = dTpB; a.stat_ml = (const float*)(fw + fp.fa_stat); a.D = Dv;
+      a.dobar = dobar; a.gV = (bf16*)gV; a.d_tok = G.tokens; a.err_flag = timeout_flag_device_ptr(); a.invN = invN;
+      a.N = N; a.C = C; a.K = K; a.Kp = ldq; a.ld_tok = ld_tok; a.R = fb_a.R; a.nchunks = fb_a.nchunks; a.splits = fb_a.splits;
+      a.zcols = fb_a.zcols;
+      StageScope _sc(ST_BWD_TOKEN, st); count_launch();
+      cudaError_t e = fa::launch_tok_attn_bwd(a, fb_a, BT, st);
+      if (e != cudaSuccess) { set_cuda_error(e, "tok_attn_bwd_fused"); return DGSCT_ERR_CUDA; }
+    } else {
+      // dP = V . dTp^T (fp32) ; dL1 = P (dP - sum_n dP P) -> gQ
+      EpiOut e5 = eo(gP, 0, K, (long long)N * K, OUT_STORE);
+      RC(run_gemm(G_TK, K_(V, N, C, C, (long long)N * C), bf, K_(dTpOp, K, C, C, dTp_bs), wbf, N, K, C, BT,
+                  to_tc_full<tc::EpiOut<false, OUT_STORE, false, false, false>>(e5), e5, AxIdentity{}, true));
+      { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();
+        if (K > 256) return DGSCT_ERR_UNSUPPORTED;
+        { const dim3 grid(csm_num_chunks(N), BT);
+          float* part = (float*)(ws + bp.csm_part);
+          count_launch();
+          col_softmax_bwd_partial_kernel<<<grid, 256, (size_t)(256 / K) * K * 4, st>>>(gP, Pm, bf, part, N, K, ldq);
+          col_softmax_bwd_apply_kernel<<<grid, 256, 0, st>>>(gP, Pm, bf, part, gQ, bf, N, K, ldq); }
+        KCHECK("col_softmax_bwd"); }
+      // dV = P . dTp + dL1 . T + dobar / N
+      EpiOut e6 = eo(gV, bf, C, (long long)N * C, OUT_STORE); e6.bcast = dobar; e6.bc_ld = C; e6.bc_scale = invN;
+      const void* dL1 = gQ; long long dL1_ld = ldq, dL1_bs = sbq;
+      {
+        RC(run_gemm(G_TK, K_(Pm, N, K, ldq, sbq), bf, MN_(dTpOp, K, C, C, (long long)K * C), wbf, N, C, K, BT,
+                    to_tc_full<tc::EpiOut<true, OUT_STORE, false, true, false>>(e6), e6, AxIdentity{}, true));
+        EpiOut e7 = eo(gV, bf, C, (long long)N * C, OUT_ADD);
+        RC(run_gemm(G_TK, K_(gQ, N, K, ldq, sbq), bf, MN_(Tok_op, K, C, ld_tok, 0), wbf, N, C, K, BT,
+                    to_tc_full<tc::EpiOut<true, OUT_ADD, false, false, false>>(e7), e7, AxIdentity{}, true));
+      }
+      // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
+      RC(fork_side());                                                  // dL1 is final; sum_frames already added its share
+      EpiOut e8 = eo(G.tokens, 0, C, 0, OUT_ATOMIC); e8.transposed = 1;
+      RC(run_gemm(S_TK, MN_(V, N, C, C, (long long)N * C), bf, MN_(dL1, N, K, dL1_ld, dL1_bs), bf, C, K, N, BT,
+                  to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true, 0, true));
+  
     }
-    // d tokens[k,c] += sum_b sum_n dL1[b,n,k] V[b,n,c]   (D(c,k) transposed, atomics over frames)
-    RC(fork_side());                                                  // dL1 is final; sum_frames already added its share
-    EpiOut e8 = eo(G.tokens, 0, C, 0, OUT_ATOMIC); e8.transposed = 1;
-    RC(run_gemm(S_TK, MN_(V, N, C, C, (long long)N * C), bf, MN_(dL1, N, K, dL1_ld, dL1_bs), bf, C, K, N, BT,
-                to_tcT<tc::EpiOutT<OUT_ATOMIC>>(e8), e8, AxIdentity{}, true, 0, true));
   }
   // ---- 8. token resampler ---------------------------------------------------------------------------------------------
   const bool fc_first = tcp && use_fc_first(d, P);

@@ -11,6 +11,7 @@
 #include "tc_epilogues.cuh"
 #include "rowwise.cuh"
 #include "side_stream.h"
+#include "attn_fused.cuh"
 
 namespace dgsct {
 
@@ -52,6 +53,7 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
   p.ssum = take(BT * N * 4);
   p.bn1_sum = take(Cd * 8); p.bn1_sq = take(Cd * 8);
   p.bn2_sum = take(C * 8); p.bn2_sq = take(C * 8);
+  p.fa_ticket = take(BT * 4);
   p.acc_end = off;
   p.aq1 = take(BT * C * 4); p.aq2 = take(BT * H * 4); p.h = take(BT * H * 4); p.m = take(BT * C * 4);
   p.tau = take(BT * 4); p.sig = take(BT * N * 4);
@@ -79,6 +81,11 @@ FwdPlan make_fwd_plan(const dgsct_desc& d, bool keep) {
     p.vec_bf_o = take(BT * (size_t)pad8((int)C) * 2);
     p.Qb = p.Pb;
     if (keep) { p.Qb = take(BT * N * Kp * 2); p.XcBuf = take(BT * N * C * 2); }
+    const fa::TokAttnPlan fp_ = fa::make_tok_attn_plan((int)BT, (int)N, (int)C, (int)K);
+    if (fp_.ok) {
+      p.fa_part_o = take(fp_.part_o_bytes); p.fa_part_ml = take(fp_.part_ml_bytes);
+      p.fa_mref = take(fp_.mref_bytes); p.fa_pfac = take(fp_.mref_bytes); p.fa_stat = take(BT * 2 * fa::KL * 4);
+    }
   }
   p.total = off;
   return p;
@@ -418,6 +425,20 @@ struct SimtAffineRelu {
 
 #define DGSCT_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
+// Fused latent-token attention (attn_fused.cuh): bf16 tensor-core path, shapes the kernels cover, 16-byte aligned rows.
+// DGSCT_NO_FUSED_ATTN=1 restores the six-launch GEMM chain (forward and backward), DGSCT_NO_FUSED_ATTN_BWD=1 only the backward's.
+static bool fused_attn_enabled(const dgsct_desc& d, const void* x, const PackPlan& pp) {
+  if (d.io_dtype != DGSCT_BF16 || (d.flags & DGSCT_F_FORCE_SIMT) || getenv("DGSCT_NO_FUSED_ATTN")) return false;
+  if (((uintptr_t)x & 15) != 0 || (pp.ld_c % 8) != 0) return false;
+  return fa::make_tok_attn_plan(d.BT, d.N, d.C, d.K).ok && fa::make_x_attn_plan(d.BT, d.N, d.C, d.K).ok;
+}
+// The backward of the token softmax recomputes P from the statistics only the fused forward leaves behind; when it cannot run
+// (very wide rows), the fused forward also writes P for the GEMM chain.
+static bool fused_attn_bwd_a_enabled(const dgsct_desc& d, const void* x, const PackPlan& pp) {
+  return fused_attn_enabled(d, x, pp) && getenv("DGSCT_NO_FUSED_ATTN_BWD") == nullptr &&
+         fa::make_tok_attn_bwd_plan(d.BT, d.N, d.C, d.K).ok;
+}
+
 int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packed_in, const void* x, const void* other,
                    void* out, void* smap, float* tmap, const dgsct_taps* taps, char* ws, cudaStream_t st, bool keep, const void* resid) {
   const FwdPlan pl = make_fwd_plan(d, keep);
@@ -531,8 +552,38 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     DGSCT_RC(c1_chain());
   }
   if (taps) DGSCT_RC(tap(V, 1, taps->V, (size_t)BT * N * C, st));
-  const bool tok_tc = true;                 // any K: P / Q pitches are padded, ragged N / K edges are TMA zero fill
+  // Latent-token attention: two fused kernels (attn_fused.cuh) when the shape qualifies, else the six-launch GEMM chain.
+  const fa::TokAttnPlan fa_a = fa::make_tok_attn_plan(BT, N, C, K);
+  const fa::XAttnPlan fa_b = fa::make_x_attn_plan(BT, N, C, K);
+  const bool fused_attn = fused_attn_enabled(d, x, pp);
+  const bool need_p = keep && !fused_attn_bwd_a_enabled(d, x, pp);     // (P is only read by the GEMM-chain backward)
   const int Kp = pad8(K);
+  if (fused_attn) {
+    {
+      fa::TokAttnArgs a{};
+      a.V = V; a.tokb = Wtok; a.tok32 = P.tokens; a.Pb = need_p ? Pb : nullptr;
+      a.part_o = (float*)(ws + pl.fa_part_o); a.part_ml = (float*)(ws + pl.fa_part_ml);
+      a.mref = (float*)(ws + pl.fa_mref); a.pfac = (float*)(ws + pl.fa_pfac); a.ticket = (unsigned*)(ws + pl.fa_ticket);
+      a.stat_ml = (float*)(ws + pl.fa_stat);
+      a.Tp = Tp; a.TpB = TpB; a.err_flag = timeout_flag_device_ptr();
+      a.N = N; a.C = C; a.K = K; a.Kp = Kp; a.ld_tok = pp.ld_c; a.R = fa_a.R; a.nchunks = fa_a.nchunks; a.splits = fa_a.splits;
+      a.zcols = fa_a.zcols; a.nbuf = fa_a.nbuf;
+      StageScope _sc(ST_TOK_UPDATE, st); count_launch();
+      cudaError_t e = fa::launch_tok_attn(a, fa_a, BT, st);
+      if (e != cudaSuccess) { set_cuda_error(e, "tok_attn_fused"); return DGSCT_ERR_CUDA; }
+    }
+    if (taps && taps->Tp) DGSCT_RC(tap(Tp, 0, taps->Tp, (size_t)BT * K * C, st));
+    {
+      fa::XAttnArgs a{};
+      a.x = (const bf16*)x; a.TpB = TpB; a.X1 = X1; a.Qb = Qb; a.Pb = need_p ? Pb : nullptr; a.pfac = (const float*)(ws + pl.fa_pfac);
+      a.gate_av = P.gate_av; a.err_flag = timeout_flag_device_ptr();
+      a.N = N; a.C = C; a.K = K; a.Kp = Kp; a.chunk_rows = fa_a.R; a.nchunks = fa_a.nchunks;
+      StageScope _sc(ST_X_UPDATE, st); count_launch();
+      cudaError_t e = fa::launch_x_attn(a, fa_b, BT, st);
+      if (e != cudaSuccess) { set_cuda_error(e, "x_attn_fused"); return DGSCT_ERR_CUDA; }
+    }
+  } else {
+  const bool tok_tc = true;                 // any K: P / Q pitches are padded, ragged N / K edges are TMA zero fill
   // (T1) L[b,n,k] = V[b,n,:] . tok[k,:]  (fp32) ; P = softmax over tokens (bf16)
   {
     auto te = tc_store<false>(L, K, (long long)N * K);
@@ -585,6 +636,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     EpiResidual se{X1, x, 1, C, (long long)N * C, P.gate_av};
     DGSCT_RC(gemm_auto(ST_X_UPDATE, "x_update", tok_tc, kmaj(Qb, N, K, Kp, (long long)N * Kp), mnmaj(TpB, K, C, C, (long long)K * C),
                        N, C, K, BT, te, se, st));
+  }
   }
   if (taps) DGSCT_RC(tap(X1, 1, taps->X1, (size_t)BT * N * C, st));
   // (C1) joins here: [aq1 | aq2] (and tau) were computed on the auxiliary stream underneath the token attention

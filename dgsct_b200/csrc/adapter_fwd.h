@@ -7,7 +7,7 @@ namespace dgsct {
 // byte offsets into the caller-provided workspace (all 256-B aligned)
 struct FwdPlan {
   size_t bufA, bufV, bufX1, bufL, Tp, Z;
-  size_t acc_begin, osum, qsum, ssum, bn1_sum, bn1_sq, bn2_sum, bn2_sq, acc_end;
+  size_t acc_begin, osum, qsum, ssum, bn1_sum, bn1_sq, bn2_sum, bn2_sq, fa_ticket, acc_end;
   size_t aq1, aq2, h, m, tau, sig, bn1_scale, bn1_shift, bn2_scale, bn2_shift;
   size_t csm_part;                                // column-softmax partials (BT, chunks, 2, K) fp32
   size_t fc_s;                                    // row sums of fc.weight (C) fp32 (re-associated resampler, DGSCT_FC_FIRST)
@@ -18,6 +18,9 @@ struct FwdPlan {
   size_t Ybuf, Qf, Qb, XcBuf;
   size_t r1sum, qvec;                             // sum_n relu(z1) (BT,C) ; q = aq1 * r1sum / N (BT,C) fp32
   size_t bn1_mean, bn1_rstd, bn2_mean, bn2_rstd;  // statistics used by the two BatchNorms (batch or running)
+  // fused latent-token attention (attn_fused.cuh): split partials (m, l, O), per-chunk reference maxima and the P rescale
+  // factors; fa_ticket (BT counters) lives in the zero-initialised region
+  size_t fa_part_o, fa_part_ml, fa_mref, fa_pfac, fa_stat;   // fa_stat (BT, 2, 32): final max / sum of the token softmax (backward)
   size_t total;
 };
 
