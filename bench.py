@@ -774,7 +774,7 @@ def stage_work(BT, cfg):
     Tensor-bound stages count EXECUTED flops (the re-associated resampler contracts over min(C, C') columns); HBM-bound row
     kernels count the bytes they must move (bf16 activations, fp32 up-sampler output)."""
     conv = dw = dwres = 0
-    gate_ln = out_ln = bwd_out = bwd_gate_ln = 0
+    gate_ln = out_ln = bwd_out = bwd_gate_ln = tok_attn = x_attn = bwd_attn = 0
     K, r = cfg["K"], cfg["r"]
     sparse = cfg["resampler"] == "bicubic"
     for kind, _, _, s in layer_list():
@@ -784,11 +784,18 @@ def stage_work(BT, cfg):
         conv += (2 * BT * N * No * cc) if not sparse else 0
         dwres += (2 * BT * N * No * cc) if not sparse else 0
         dw += 2 * BT * N * (2 * C * Cd + H * C + C * C + K * C) + 2 * BT * (No if (C < Co and not sparse) else N) * C * Co
+        tok_attn += BT * N * C * 2 + BT * K * C * 6
+        x_attn += BT * N * C * 4 + BT * N * 2 * ((K + 7) // 8 * 8) + BT * K * C * 2
+        bwd_attn += BT * N * C * 10 + BT * N * 2 * ((K + 7) // 8 * 8) + BT * K * C * 16
         gate_ln += BT * N * C * 4
         out_ln += BT * N * C * 6
         bwd_out += BT * N * C * 8
         bwd_gate_ln += BT * N * C * 6
-    w = {"gate_ln": (gate_ln, "hbm", "gate combine + ln_before row kernel (read X', write Y)"),
+    w = {"tok_update": (tok_attn, "hbm", "fused token attention, tokens over V: softmax_n(T V^T), T' = T + P V in one pass over V "
+                                        "(bulk-async staged tiles, warp-level MMAs; read V, write T')"),
+         "x_update": (x_attn, "hbm", "fused token attention, stream over tokens: softmax_k(X T'^T), X' = X + g Q T' (read X, write X' and Q)"),
+         "bwd_token": (bwd_attn, "hbm", "backward of the token attention, two fused kernels (read dX', X, V; write dX, dV; dT' in L2)"),
+         "gate_ln": (gate_ln, "hbm", "gate combine + ln_before row kernel (read X', write Y)"),
          "out_ln": (out_ln, "hbm", "bn2 + ln_post + gate row kernel (read fp32 up-sampler output, write out)"),
          "bwd_out": (bwd_out, "hbm", "backward of gate / ln_post / bn2 sums (read d_out + Uo, write dUo)"),
          "bwd_gate_ln": (bwd_gate_ln, "hbm", "backward of ln_before + gate combine (read dY + X', write dX')"),

@@ -155,21 +155,23 @@ __global__ void __launch_bounds__(256) tok_attn_fwd_kernel(const TokAttnArgs a) 
   }
   if (tid < KL) { m_run[tid] = -INFINITY; l_run[tid] = 0.f; }
   __syncthreads();
-  auto issue_chunk = [&](int chunk, int buf) {     // called by all lanes of ONE warp
+  // A bulk copy is issued by ONE lane at a time (the compiler serialises the per-lane copies of a warp through the uniform
+  // datapath, ~80 cycles each: ncu, round 2) -- the rows of a chunk are therefore dealt out over all eight warps (row r to warp
+  // r % 8), and one thread posts the byte count; copies that land before it only drive the transaction count negative.
+  const int rlane = lane * 8 + warp;                    // the row this thread copies (if < rows)
+  auto issue_chunk = [&](int chunk, int buf) {          // called by EVERY thread of the CTA
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
     const uint32_t bar = tc::smem_u32(&bars[1 + buf]);
-    if (lane == 0) tc::mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
-    __syncwarp();
+    if (tid == 0) tc::mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
     const uint32_t dst = tc::smem_u32(Vsm + (size_t)buf * R * pitch);
-    for (int r = lane; r < rows; r += 32) bulk_g2s(dst + (uint32_t)(r * pitch), Vb + (size_t)(n0 + r) * C, row_bytes, bar);
+    if (rlane < rows) bulk_g2s(dst + (uint32_t)(rlane * pitch), Vb + (size_t)(n0 + rlane) * C, row_bytes, bar);
   };
-  if (warp == 0) {
+  {
     const uint32_t bar = tc::smem_u32(&bars[0]);
-    if (lane == 0) tc::mbar_expect_tx(bar, (uint32_t)K * row_bytes);
-    __syncwarp();
-    if (lane < K) bulk_g2s(tc::smem_u32(Tsm) + (uint32_t)(lane * pitch), a.tokb + (size_t)lane * a.ld_tok, row_bytes, bar);
-  } else if (warp == 1) {
+    if (tid == 0) tc::mbar_expect_tx(bar, (uint32_t)K * row_bytes);
+    if (lane < 4 && lane * 8 + warp < K)
+      bulk_g2s(tc::smem_u32(Tsm) + (uint32_t)((lane * 8 + warp) * pitch), a.tokb + (size_t)(lane * 8 + warp) * a.ld_tok, row_bytes, bar);
     if (c_begin < c_end) issue_chunk(c_begin, 0);
   }
   if (K < KL) zero_rows(Tsm + (size_t)K * pitch, KL - K, pitch, (int)row_bytes, tid, 256);
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(256) tok_attn_fwd_kernel(const TokAttnArgs a) 
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
     uint8_t* Vc = Vsm + (size_t)buf * R * pitch;
-    if (a.nbuf == 2 && warp == 1 && chunk + 1 < c_end) issue_chunk(chunk + 1, buf ^ 1);   // (buffer released by the trailing sync)
+    if (a.nbuf == 2 && chunk + 1 < c_end) issue_chunk(chunk + 1, buf ^ 1);   // (buffer released by the trailing sync)
     if (rows < R) zero_rows(Vc + (size_t)rows * pitch, R - rows, pitch, (int)row_bytes, tid, 256);
     if (it == 0) ok = wait_bar(tc::smem_u32(&bars[0]), 0, a.err_flag);
     if (ok) ok = wait_bar(tc::smem_u32(&bars[1 + buf]), ph[buf], a.err_flag);
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(256) tok_attn_fwd_kernel(const TokAttnArgs a) 
       }
     }
     __syncthreads();                                   // V buffer, P~ tile and the per-warp statistics are free again
-    if (a.nbuf == 1 && warp == 1 && chunk + 1 < c_end) issue_chunk(chunk + 1, 0);
+    if (a.nbuf == 1 && chunk + 1 < c_end) issue_chunk(chunk + 1, 0);
   }
   ok = __syncthreads_and(ok);
   if (!ok) return;
@@ -740,19 +742,17 @@ __global__ void __launch_bounds__(128) x_attn_fwd_coop_kernel(const XAttnArgs a)
   __syncthreads();
   const uint32_t xs = tc::smem_u32(xw), ts = tc::smem_u32(Tsm), bar1 = tc::smem_u32(&bars[1]);
   const int ntiles = (N + 15) >> 4;
-  auto issue_tile = [&](int tile) {                   // warp 1
+  const int rlane = lane * 4 + warp;                  // bulk copies are dealt out over the four warps (see tok_attn_fwd_kernel)
+  auto issue_tile = [&](int tile) {                   // EVERY thread of the CTA
     const int n0 = tile << 4;
     const int rows = min(16, N - n0);
-    if (lane == 0) tc::mbar_expect_tx(bar1, (uint32_t)rows * row_bytes);
-    __syncwarp();
-    if (lane < rows) bulk_g2s(xs + (uint32_t)(lane * pitch), a.x + ((size_t)b * N + n0 + lane) * C, row_bytes, bar1);
+    if (tid == 0) tc::mbar_expect_tx(bar1, (uint32_t)rows * row_bytes);
+    if (rlane < rows) bulk_g2s(xs + (uint32_t)(rlane * pitch), a.x + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar1);
   };
-  if (warp == 0) {
+  {
     const uint32_t bar = tc::smem_u32(&bars[0]);
-    if (lane == 0) tc::mbar_expect_tx(bar, (uint32_t)K * row_bytes);
-    __syncwarp();
-    if (lane < K) bulk_g2s(ts + (uint32_t)(lane * pitch), a.TpB + ((size_t)b * K + lane) * C, row_bytes, bar);
-  } else if (warp == 1) {
+    if (tid == 0) tc::mbar_expect_tx(bar, (uint32_t)K * row_bytes);
+    if (rlane < K) bulk_g2s(ts + (uint32_t)(rlane * pitch), a.TpB + ((size_t)b * K + rlane) * C, row_bytes, bar);
     if ((int)blockIdx.x < ntiles) issue_tile(blockIdx.x);
   }
   if (K < KL) zero_rows(Tsm + (size_t)K * pitch, KL - K, pitch, (int)row_bytes, tid, 128);
@@ -797,14 +797,14 @@ __global__ void __launch_bounds__(128) x_attn_fwd_coop_kernel(const XAttnArgs a)
     q_times_tok_residual(aq, ts, xw, pitch, c_begin, c_end, gate, lane);
     fence_proxy_async();
     __syncthreads();                                   // every column range of the tile is final; sred is free again
-    if (warp == 1) {
-      if (lane < rows) {
-        bulk_s2g(a.X1 + (grow + lane) * C, xs + (uint32_t)(lane * pitch), row_bytes);
-        bulk_commit();
-        bulk_wait_read0();
-      }
-      __syncwarp();
-      if (tile + (int)gridDim.x < ntiles) issue_tile(tile + gridDim.x);
+    if (rlane < rows) {
+      bulk_s2g(a.X1 + (grow + rlane) * C, xs + (uint32_t)(rlane * pitch), row_bytes);
+      bulk_commit();
+      bulk_wait_read0();
+    }
+    if (tile + (int)gridDim.x < ntiles) {
+      __syncthreads();                                 // every row of the tile has left: the buffer may be overwritten
+      issue_tile(tile + gridDim.x);
     }
   }
 }
@@ -971,22 +971,21 @@ __global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
   }
   __syncthreads();
   const uint32_t ts = tc::smem_u32(Tsm), gs = tc::smem_u32(Gs), xs = tc::smem_u32(Xs), bar1 = tc::smem_u32(&bars[1]);
-  auto issue_chunk = [&](int chunk) {                   // all lanes of ONE warp
+  const int rlane = lane * 8 + warp;                    // the row this thread copies (see tok_attn_fwd_kernel)
+  auto issue_chunk = [&](int chunk) {                   // EVERY thread of the CTA
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
-    if (lane == 0) tc::mbar_expect_tx(bar1, 2u * (uint32_t)rows * row_bytes);
-    __syncwarp();
-    for (int r = lane; r < rows; r += 32) {
-      bulk_g2s(gs + (uint32_t)(r * pitch), a.G + ((size_t)b * N + n0 + r) * C, row_bytes, bar1);
-      bulk_g2s(xs + (uint32_t)(r * pitch), a.x + ((size_t)b * N + n0 + r) * C, row_bytes, bar1);
+    if (tid == 0) tc::mbar_expect_tx(bar1, 2u * (uint32_t)rows * row_bytes);
+    if (rlane < rows) {
+      bulk_g2s(gs + (uint32_t)(rlane * pitch), a.G + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar1);
+      bulk_g2s(xs + (uint32_t)(rlane * pitch), a.x + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar1);
     }
   };
-  if (warp == 0) {
+  {
     const uint32_t bar = tc::smem_u32(&bars[0]);
-    if (lane == 0) tc::mbar_expect_tx(bar, (uint32_t)K * row_bytes);
-    __syncwarp();
-    if (lane < K) bulk_g2s(ts + (uint32_t)(lane * pitch), a.TpB + ((size_t)b * K + lane) * C, row_bytes, bar);
-  } else if (warp == 1) {
+    if (tid == 0) tc::mbar_expect_tx(bar, (uint32_t)K * row_bytes);
+    if (lane < 4 && lane * 8 + warp < K)
+      bulk_g2s(ts + (uint32_t)((lane * 8 + warp) * pitch), a.TpB + ((size_t)b * K + lane * 8 + warp) * C, row_bytes, bar);
     if (c_begin < c_end) issue_chunk(c_begin);
   }
   if (K < KL) zero_rows(Tsm + (size_t)K * pitch, KL - K, pitch, (int)row_bytes, tid, 256);
@@ -1075,13 +1074,14 @@ __global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
     }
     fence_proxy_async();
     __syncthreads();
-    if (warp == 1) {
-      for (int r = lane; r < rows; r += 32)
-        bulk_s2g(a.dx + ((size_t)b * N + n0 + r) * C + zc0, gs + (uint32_t)(r * pitch + zc0 * 2), (uint32_t)zcols * 2);
+    if (rlane < rows) {
+      bulk_s2g(a.dx + ((size_t)b * N + n0 + rlane) * C + zc0, gs + (uint32_t)(rlane * pitch + zc0 * 2), (uint32_t)zcols * 2);
       bulk_commit();
       bulk_wait_read0();
-      __syncwarp();
-      if (chunk + 1 < c_end) issue_chunk(chunk + 1);
+    }
+    if (chunk + 1 < c_end) {
+      __syncthreads();                                 // every row of the tile has left: the buffers may be overwritten
+      issue_chunk(chunk + 1);
     }
   }
   if (!__syncthreads_and(ok)) return;
@@ -1222,22 +1222,21 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
   }
   __syncthreads();
   const uint32_t ts = tc::smem_u32(Tsm), ds = tc::smem_u32(Dsm), vs = tc::smem_u32(Vsm), bar1 = tc::smem_u32(&bars[1]);
-  auto issue_chunk = [&](int chunk) {
+  const int rlane = lane * 8 + warp;                    // the row this thread copies (see tok_attn_fwd_kernel)
+  auto issue_chunk = [&](int chunk) {                   // EVERY thread of the CTA
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
-    if (lane == 0) tc::mbar_expect_tx(bar1, (uint32_t)rows * row_bytes);
-    __syncwarp();
-    for (int r = lane; r < rows; r += 32) bulk_g2s(vs + (uint32_t)(r * pitch), a.V + ((size_t)b * N + n0 + r) * C, row_bytes, bar1);
+    if (tid == 0) tc::mbar_expect_tx(bar1, (uint32_t)rows * row_bytes);
+    if (rlane < rows) bulk_g2s(vs + (uint32_t)(rlane * pitch), a.V + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar1);
   };
-  if (warp == 0) {
+  {
     const uint32_t bar = tc::smem_u32(&bars[0]);
-    if (lane == 0) tc::mbar_expect_tx(bar, 2u * (uint32_t)K * row_bytes);
-    __syncwarp();
-    if (lane < K) {
-      bulk_g2s(ts + (uint32_t)(lane * pitch), a.tokb + (size_t)lane * a.ld_tok, row_bytes, bar);
-      bulk_g2s(ds + (uint32_t)(lane * pitch), a.dTpB + ((size_t)b * K + lane) * C, row_bytes, bar);
+    if (tid == 0) tc::mbar_expect_tx(bar, 2u * (uint32_t)K * row_bytes);
+    if (lane < 4 && lane * 8 + warp < K) {
+      const int k = lane * 8 + warp;
+      bulk_g2s(ts + (uint32_t)(k * pitch), a.tokb + (size_t)k * a.ld_tok, row_bytes, bar);
+      bulk_g2s(ds + (uint32_t)(k * pitch), a.dTpB + ((size_t)b * K + k) * C, row_bytes, bar);
     }
-  } else if (warp == 1) {
     if (c_begin < c_end) issue_chunk(c_begin);
   }
   if (K < KL) {
@@ -1354,13 +1353,14 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
     }
     fence_proxy_async();
     __syncthreads();
-    if (warp == 1) {
-      for (int r = lane; r < rows; r += 32)
-        bulk_s2g(a.gV + ((size_t)b * N + n0 + r) * C + zc0, vs + (uint32_t)(r * pitch + zc0 * 2), (uint32_t)zcols * 2);
+    if (rlane < rows) {
+      bulk_s2g(a.gV + ((size_t)b * N + n0 + rlane) * C + zc0, vs + (uint32_t)(rlane * pitch + zc0 * 2), (uint32_t)zcols * 2);
       bulk_commit();
       bulk_wait_read0();
-      __syncwarp();
-      if (chunk + 1 < c_end) issue_chunk(chunk + 1);
+    }
+    if (chunk + 1 < c_end) {
+      __syncthreads();                                 // every row of the tile has left: the buffer may be overwritten
+      issue_chunk(chunk + 1);
     }
   }
   if (!__syncthreads_and(ok)) return;
