@@ -724,7 +724,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       fa::XAttnBwdArgs a{};
       a.G = (const bf16*)gX1; a.x = (const bf16*)x; a.TpB = (const bf16*)TpOp; a.Qb = (const bf16*)Qm;
       a.dx = (bf16*)dx; a.dTp = dTp; a.gate_av = P.gate_av; a.d_gate_av = G.gate_av; a.err_flag = timeout_flag_device_ptr();
-      a.N = N; a.C = C; a.K = K; a.Kp = ldq; a.R = fb_b.R; a.nchunks = fb_b.nchunks; a.splits = fb_b.splits; a.zcols = fb_b.zcols;
+      a.N = N; a.C = C; a.K = K; a.Kp = ldq; a.R = fb_b.R; a.nchunks = fb_b.nchunks; a.splits = fb_b.splits; a.zcols = fb_b.zcols; a.nbuf = fb_b.nbuf;
       StageScope _sc(ST_BWD_TOKEN, st); count_launch();
       cudaError_t e = fa::launch_x_attn_bwd(a, fb_b, BT, st);
       if (e != cudaSuccess) { set_cuda_error(e, "x_attn_bwd_fused"); return DGSCT_ERR_CUDA; }
@@ -765,7 +765,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       a.V = (const bf16*)V; a.tokb = (const bf16*)Tok_op; a.dTpB = dTpB; a.stat_ml = (const float*)(fw + fp.fa_stat); a.D = Dv;
       a.dobar = dobar; a.gV = (bf16*)gV; a.d_tok = G.tokens; a.err_flag = timeout_flag_device_ptr(); a.invN = invN;
       a.N = N; a.C = C; a.K = K; a.Kp = ldq; a.ld_tok = ld_tok; a.R = fb_a.R; a.nchunks = fb_a.nchunks; a.splits = fb_a.splits;
-      a.zcols = fb_a.zcols;
+      a.zcols = fb_a.zcols; a.nbuf = fb_a.nbuf;
       StageScope _sc(ST_BWD_TOKEN, st); count_launch();
       cudaError_t e = fa::launch_tok_attn_bwd(a, fb_a, BT, st);
       if (e != cudaSuccess) { set_cuda_error(e, "tok_attn_bwd_fused"); return DGSCT_ERR_CUDA; }

@@ -12,6 +12,7 @@
 #include "rowwise.cuh"
 #include "side_stream.h"
 #include "attn_fused.cuh"
+#include "vec_linear.cuh"
 
 namespace dgsct {
 
@@ -425,6 +426,20 @@ struct SimtAffineRelu {
 
 #define DGSCT_RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
+
+// One launch of the lean per-frame-vector linear (vec_linear.cuh), or DGSCT_ERR_UNSUPPORTED (the caller then takes the GEMM)
+static int vec_linear(int stage, const char* name, const void* in, int ld_in, const void* W, int ld_w, int w_trans, const float* bias,
+                      int act, float* out32, int ld32, bf16* out16, int ld16, int M, int N, int K, int accumulate, cudaStream_t st) {
+  vl::VecLinArgs a{};
+  a.in = (const bf16*)in; a.ld_in = ld_in; a.W = (const bf16*)W; a.ld_w = ld_w; a.bias = bias; a.out32 = out32; a.ld32 = ld32;
+  a.out16 = out16; a.ld16 = ld16; a.M = M; a.N = N; a.K = K; a.act = act; a.w_trans = w_trans; a.accumulate = accumulate;
+  if (!vl::vec_linear_ok(a)) return DGSCT_ERR_UNSUPPORTED;
+  StageScope _sc(stage, st); count_launch();
+  cudaError_t e = vl::launch_vec_linear(a, st);
+  if (e != cudaSuccess) { set_cuda_error(e, name); return DGSCT_ERR_CUDA; }
+  return DGSCT_OK;
+}
+
 // Fused latent-token attention (attn_fused.cuh): bf16 tensor-core path, shapes the kernels cover, 16-byte aligned rows.
 // DGSCT_NO_FUSED_ATTN=1 restores the six-launch GEMM chain (forward and backward), DGSCT_NO_FUSED_ATTN_BWD=1 only the backward's.
 static bool fused_attn_enabled(const dgsct_desc& d, const void* x, const PackPlan& pp) {
@@ -535,8 +550,12 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     auto te = tc_store<false, false, false, ACT_RELU>(aq, aq_ld, 0);
     te.bias_n = (const float*)(pk + pp.cat1_bias);
     EpiBiasStore se = epi_store(aq, 0, aq_ld, 0); se.bias_n = te.bias_n; se.act = ACT_RELU;
-    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "aq12", true, kmaj(vecb_o, BT, C, C, 0), kmaj(pk + pp.cat1, C + H, C, pp.ld_c, 0),
-                       BT, C + H, C, 1, te, se, sx, 64));
+    int rcv = vec_linear(ST_SMALL_LINEAR, "aq12", vecb_o, C, pk + pp.cat1, pp.ld_c, 0, te.bias_n, ACT_RELU, aq, aq_ld, nullptr, 0,
+                         BT, C + H, C, 0, sx);
+    if (rcv == DGSCT_ERR_UNSUPPORTED)
+      rcv = gemm_auto(ST_SMALL_LINEAR, "aq12", true, kmaj(vecb_o, BT, C, C, 0), kmaj(pk + pp.cat1, C + H, C, pp.ld_c, 0),
+                      BT, C + H, C, 1, te, se, sx, 64);
+    DGSCT_RC(rcv);
     if (d.flags & DGSCT_F_TEMPORAL) {
       cudaStream_t st = sx;                       // (DGSCT_GEMM launches on `st`)
       GemmShape sh3{BT, 1, C, 1, 1};
@@ -663,13 +682,21 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     auto te = tc_store<true, false, false, ACT_RELU>(hb, pp.ld_h, 0);
     te.bias_n = P.bott_b;
     EpiBiasStore se = epi_store(hb, 1, pp.ld_h, 0); se.bias_n = P.bott_b; se.act = ACT_RELU;
-    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "channel_bottleneck", true, kmaj(vecb, BT, C, C, 0), kmaj(pk + pp.bott, H, C, pp.ld_c, 0),
-                       BT, H, C, 1, te, se, st, 64));
+    int rcv = vec_linear(ST_SMALL_LINEAR, "channel_bottleneck", vecb, C, pk + pp.bott, pp.ld_c, 0, P.bott_b, ACT_RELU, nullptr, 0, hb,
+                         pp.ld_h, BT, H, C, 0, st);
+    if (rcv == DGSCT_ERR_UNSUPPORTED)
+      rcv = gemm_auto(ST_SMALL_LINEAR, "channel_bottleneck", true, kmaj(vecb, BT, C, C, 0), kmaj(pk + pp.bott, H, C, pp.ld_c, 0),
+                      BT, H, C, 1, te, se, st, 64);
+    DGSCT_RC(rcv);
     auto te2 = tc_store<false, false, false, ACT_SIGMOID>(mvec, C, 0);
     te2.bias_n = P.c_b;
     EpiBiasStore se2 = epi_store(mvec, 0, C, 0); se2.bias_n = P.c_b; se2.act = ACT_SIGMOID;
-    DGSCT_RC(gemm_auto(ST_SMALL_LINEAR, "channel_gate", true, kmaj(hb, BT, H, pp.ld_h, 0), kmaj(pk + pp.catt, C, H, pp.ld_h, 0),
-                       BT, C, H, 1, te2, se2, st, 64));
+    rcv = vec_linear(ST_SMALL_LINEAR, "channel_gate", hb, pp.ld_h, pk + pp.catt, pp.ld_h, 0, P.c_b, ACT_SIGMOID, mvec, C, nullptr, 0,
+                     BT, C, H, 0, st);
+    if (rcv == DGSCT_ERR_UNSUPPORTED)
+      rcv = gemm_auto(ST_SMALL_LINEAR, "channel_gate", true, kmaj(hb, BT, H, pp.ld_h, 0), kmaj(pk + pp.catt, C, H, pp.ld_h, 0),
+                      BT, C, H, 1, te2, se2, st, 64);
+    DGSCT_RC(rcv);
   }
   if (taps && taps->m) DGSCT_RC(tap(mvec, 0, taps->m, (size_t)BT * C, st));
   // (S1) Xc = X1 (1+m) (bf16, in the U buffer) ; ssum[b,n] = sum_j ws[j] aq2[b,j] relu(Xc[b,n,:] . Wv2[j,:] + b)

@@ -477,6 +477,32 @@ inline cudaError_t set_max_dyn_smem(KernelT kernel) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa_.sharedSizeBytes);
 }
 
+// Column ranges per frame (grid.z).  Every CTA of a frame runs the full-width logits product, but the products that are cut by
+// output columns (P~^T V, dT', dx, dV, d tokens) split cleanly, and so do their accumulators: when a call has fewer CTAs than the
+// machine has SMs (deep stages: one split per frame), the frame is dealt out over up to four column ranges.  The arithmetic of a
+// column does not depend on the range it falls in, so this may follow the number of frames without touching a single bit.
+// Chosen by a two-term cost model: CTAs needed / CTAs resident (whole waves) x work per CTA, where `full` parts of the work are
+// repeated by every range and `sep` parts are divided among them.
+inline void fa_widen_z(int BT, int splits, int C, size_t smem, int full, int sep, int& Z, int& zcols, int& ntw) {
+  int best = Z;
+  double best_cost = 0.0;
+  for (int z = Z; z <= 4; ++z) {
+    if (z > Z && (C / 16) / z < 4) break;                     // at least 64 columns per range
+    const int zc = ((C / 16 + z - 1) / z) * 16;
+    const int nt = 2 * ((zc / 16 + 7) / 8);
+    int cps = (int)((227 * 1024) / (smem + 1024));
+    if (cps > 2) cps = 2;
+    if (nt >= 10 || cps < 1) cps = 1;                          // register budget: one CTA per SM for the widest accumulators
+    const long long ctas = (long long)BT * splits * z;
+    const long long waves = (ctas + 148LL * cps - 1) / (148LL * cps);
+    const double cost = (double)waves * ((double)full + (double)sep / z);
+    if (z == Z || cost < best_cost * 0.95) { best = z; best_cost = cost; }
+  }
+  Z = best;
+  zcols = ((C / 16 + Z - 1) / Z) * 16;
+  ntw = 2 * ((zcols / 16 + 7) / 8);
+}
+
 struct TokAttnPlan {
   bool ok; int R, nbuf, nchunks, splits, Z, zcols, ntw; size_t smem;
   size_t part_o_bytes, part_ml_bytes, mref_bytes, ticket_bytes;
@@ -499,6 +525,7 @@ inline TokAttnPlan make_tok_attn_plan(int BT, int N, int C, int K) {
   static const int cand_big[][2] = {{64, 2}, {32, 2}, {64, 1}, {32, 1}, {16, 2}, {16, 1}};
   const size_t small = 104 * 1024, big = 225 * 1024;
   int R = 0, nbuf = 0;
+  // (the chunk size must not depend on the number of frames: it fixes which rows share a reference maximum, i.e. the bits of P~)
   if (p.ntw < 10)
     for (auto& cnd : cand_small) if (tok_attn_smem(C, cnd[0], cnd[1]) <= small) { R = cnd[0]; nbuf = cnd[1]; break; }
   if (!R) for (auto& cnd : cand_big) if (tok_attn_smem(C, cnd[0], cnd[1]) <= big) { R = cnd[0]; nbuf = cnd[1]; break; }
@@ -518,6 +545,7 @@ inline TokAttnPlan make_tok_attn_plan(int BT, int N, int C, int K) {
     if (sp > 32) sp = 32;
     p.splits = sp;
   }
+  fa_widen_z(BT, p.splits, C, tok_attn_smem(C, p.R, nbuf), 1, 1, p.Z, p.zcols, p.ntw);
   p.nbuf = (nbuf == 2 && (p.nchunks + p.splits - 1) / p.splits > 1) ? 2 : 1;
   p.smem = tok_attn_smem(C, p.R, p.nbuf);
   p.part_o_bytes = (size_t)BT * p.splits * KL * C * 4;
@@ -944,20 +972,19 @@ struct XAttnBwdArgs {
   const bf16* G; const bf16* x; const bf16* TpB; const bf16* Qb;
   bf16* dx; float* dTp; const float* gate_av; float* d_gate_av;
   int* err_flag;
-  int N, C, K, Kp, R, nchunks, splits, zcols;
+  int N, C, K, Kp, R, nchunks, splits, zcols, nbuf;
 };
 
 template <int NTW>
-__global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
+__global__ void __launch_bounds__(256, (NTW <= 8 ? 2 : 1)) x_attn_bwd_kernel(const XAttnBwdArgs a) {
   extern __shared__ __align__(128) uint8_t fa_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int C = a.C, N = a.N, K = a.K, R = a.R;
   const int pitch = C * 2 + 16;
   const int b = blockIdx.y, split = blockIdx.x, z = blockIdx.z;
   uint8_t* Tsm = fa_smem;
-  uint8_t* Gs = Tsm + (size_t)KL * pitch;
-  uint8_t* Xs = Gs + (size_t)R * pitch;
-  uint8_t* Qs = Xs + (size_t)R * pitch;                 // [R][32] bf16 gate * Q
+  uint8_t* Gs0 = Tsm + (size_t)KL * pitch;              // nbuf x (G tile, X tile): the next chunk lands while this one is worked on
+  uint8_t* Qs = Gs0 + (size_t)a.nbuf * 2 * R * pitch;   // [R][32] bf16 gate * Q
   uint8_t* Ls = Qs + (size_t)R * PS_PITCH;              // [R][32] bf16 dL2
   float* sred = reinterpret_cast<float*>(Ls + (size_t)R * PS_PITCH);
   float* red = sred + 16 * 8 * 32;                      // [32]
@@ -965,20 +992,22 @@ __global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
   const int c_begin = (int)((long long)split * a.nchunks / a.splits), c_end = (int)((long long)(split + 1) * a.nchunks / a.splits);
   const uint32_t row_bytes = (uint32_t)C * 2;
   if (tid == 0) {
-    tc::mbar_init(tc::smem_u32(&bars[0]), 1);
-    tc::mbar_init(tc::smem_u32(&bars[1]), 1);
+    for (int i = 0; i < 3; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
     tc::fence_barrier_init();
   }
   __syncthreads();
-  const uint32_t ts = tc::smem_u32(Tsm), gs = tc::smem_u32(Gs), xs = tc::smem_u32(Xs), bar1 = tc::smem_u32(&bars[1]);
+  const uint32_t ts = tc::smem_u32(Tsm);
+  const uint32_t buf_bytes = 2u * (uint32_t)R * (uint32_t)pitch;
   const int rlane = lane * 8 + warp;                    // the row this thread copies (see tok_attn_fwd_kernel)
-  auto issue_chunk = [&](int chunk) {                   // EVERY thread of the CTA
+  auto issue_chunk = [&](int chunk, int buf) {          // EVERY thread of the CTA
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
-    if (tid == 0) tc::mbar_expect_tx(bar1, 2u * (uint32_t)rows * row_bytes);
+    const uint32_t bar = tc::smem_u32(&bars[1 + buf]);
+    const uint32_t gsb = tc::smem_u32(Gs0) + (uint32_t)buf * buf_bytes, xsb = gsb + (uint32_t)R * (uint32_t)pitch;
+    if (tid == 0) tc::mbar_expect_tx(bar, 2u * (uint32_t)rows * row_bytes);
     if (rlane < rows) {
-      bulk_g2s(gs + (uint32_t)(rlane * pitch), a.G + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar1);
-      bulk_g2s(xs + (uint32_t)(rlane * pitch), a.x + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar1);
+      bulk_g2s(gsb + (uint32_t)(rlane * pitch), a.G + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar);
+      bulk_g2s(xsb + (uint32_t)(rlane * pitch), a.x + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar);
     }
   };
   {
@@ -986,7 +1015,8 @@ __global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
     if (tid == 0) tc::mbar_expect_tx(bar, (uint32_t)K * row_bytes);
     if (lane < 4 && lane * 8 + warp < K)
       bulk_g2s(ts + (uint32_t)((lane * 8 + warp) * pitch), a.TpB + ((size_t)b * K + lane * 8 + warp) * C, row_bytes, bar);
-    if (c_begin < c_end) issue_chunk(c_begin);
+    if (c_begin < c_end) issue_chunk(c_begin, 0);
+    if (a.nbuf == 2 && c_begin + 1 < c_end) issue_chunk(c_begin + 1, 1);
   }
   if (K < KL) zero_rows(Tsm + (size_t)K * pitch, KL - K, pitch, (int)row_bytes, tid, 256);
   const float gate = a.gate_av[0];
@@ -1011,14 +1041,18 @@ __global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
   const int dsteps = ((zcols >> 4) + KS - 1) / KS;
   const int d_begin = zc0 + min(zcols, kpart * dsteps * 16), d_end = zc0 + min(zcols, (kpart + 1) * dsteps * 16);
   float gacc = 0.f;
-  uint32_t ph = 0;
+  uint32_t ph0 = 0, ph1 = 0;
   bool ok = true;
   for (int chunk = c_begin; chunk < c_end; ++chunk) {
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
+    const int buf = a.nbuf == 2 ? ((chunk - c_begin) & 1) : 0;
+    uint8_t* Gs = Gs0 + (size_t)buf * buf_bytes;
+    uint8_t* Xs = Gs + (size_t)R * pitch;
+    const uint32_t gs = tc::smem_u32(Gs), xs = tc::smem_u32(Xs);
     if (chunk == c_begin) ok = wait_bar(tc::smem_u32(&bars[0]), 0, a.err_flag);
-    if (ok) ok = wait_bar(bar1, ph, a.err_flag);
-    ph ^= 1;
+    if (ok) ok = wait_bar(tc::smem_u32(&bars[1 + buf]), buf ? ph1 : ph0, a.err_flag);
+    if (buf) ph1 ^= 1; else ph0 ^= 1;
     if (rows < R) {                                    // (after the wait: see x_attn_fwd_coop_kernel)
       zero_rows(Gs + (size_t)rows * pitch, R - rows, pitch, (int)row_bytes, tid, 256);
       zero_rows(Xs + (size_t)rows * pitch, R - rows, pitch, (int)row_bytes, tid, 256);
@@ -1079,9 +1113,9 @@ __global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
       bulk_commit();
       bulk_wait_read0();
     }
-    if (chunk + 1 < c_end) {
-      __syncthreads();                                 // every row of the tile has left: the buffers may be overwritten
-      issue_chunk(chunk + 1);
+    if (chunk + a.nbuf < c_end) {
+      __syncthreads();                                 // every row of the tile has left: this buffer may be overwritten
+      issue_chunk(chunk + a.nbuf, buf);
     }
   }
   if (!__syncthreads_and(ok)) return;
@@ -1098,10 +1132,10 @@ __global__ void __launch_bounds__(256) x_attn_bwd_kernel(const XAttnBwdArgs a) {
   }
 }
 
-struct XAttnBwdPlan { bool ok; int R, nchunks, splits, Z, zcols, ntw; size_t smem; };
-inline size_t x_attn_bwd_smem(int C, int R) {
+struct XAttnBwdPlan { bool ok; int R, nbuf, nchunks, splits, Z, zcols, ntw; size_t smem; };
+inline size_t x_attn_bwd_smem(int C, int R, int nbuf) {
   const size_t pitch = (size_t)C * 2 + 16;
-  return (size_t)KL * pitch + 2 * (size_t)R * pitch + 2 * (size_t)R * PS_PITCH + (size_t)(16 * 8 * 32 + 32) * 4 + 64;
+  return (size_t)KL * pitch + (size_t)nbuf * 2 * R * pitch + 2 * (size_t)R * PS_PITCH + (size_t)(16 * 8 * 32 + 32) * 4 + 64;
 }
 inline int fa_splits(int BT, int Z, int N, int nchunks, size_t smem, int ntw) {
   int cps = (int)((227 * 1024) / (smem + 1024));
@@ -1118,6 +1152,22 @@ inline int fa_splits(int BT, int Z, int N, int nchunks, size_t smem, int ntw) {
   if (sp > 32) sp = 32;
   return sp;
 }
+// (rows per chunk, buffers) of the backward kernels: two CTAs per SM (<= 104 KB) when the call has the CTAs to fill them, else
+// one CTA per SM with everything the 227 KB allow -- double-buffered whenever it fits (the chunk loads are exposed otherwise: a
+// third of the stall samples of the single-buffered kernels sat on the load barrier, ncu round 2)
+template <typename SmemFn>
+inline bool fa_bwd_tile(int BT, int N, int C, int ntw, SmemFn smem_of, int& R, int& nbuf) {
+  static const int small_c[][2] = {{128, 2}, {64, 2}, {32, 2}, {64, 1}, {32, 1}, {16, 2}, {16, 1}};
+  static const int big_c[][2] = {{64, 2}, {32, 2}, {16, 2}, {64, 1}, {32, 1}, {16, 1}};
+  const long long ctas_est = (long long)BT * ((N + 192) / 384 > 0 ? (N + 192) / 384 : 1);
+  R = 0;
+  if (ntw < 10 && ctas_est > 148)
+    for (auto& c : small_c) if (smem_of(C, c[0], c[1]) <= (size_t)104 * 1024) { R = c[0]; nbuf = c[1]; break; }
+  if (!R) for (auto& c : big_c) if (smem_of(C, c[0], c[1]) <= (size_t)225 * 1024) { R = c[0]; nbuf = c[1]; break; }
+  if (!R) return false;
+  while (R > 16 && R / 2 >= N) R /= 2;
+  return true;
+}
 inline XAttnBwdPlan make_x_attn_bwd_plan(int BT, int N, int C, int K) {
   XAttnBwdPlan p{};
   if (C % 32 || C < 32 || K > KL || K < 1 || N < 1) return p;
@@ -1125,16 +1175,12 @@ inline XAttnBwdPlan make_x_attn_bwd_plan(int BT, int N, int C, int K) {
   p.zcols = ((C / 16 + p.Z - 1) / p.Z) * 16;
   p.ntw = 2 * ((p.zcols / 16 + 7) / 8);
   if (p.ntw > 12) return p;
-  static const int cand[] = {128, 64, 32, 16};
-  int R = 0;
-  if (p.ntw < 10) for (int r : cand) if (x_attn_bwd_smem(C, r) <= 104 * 1024) { R = r; break; }
-  if (!R) for (int r : cand) if (r <= 64 && x_attn_bwd_smem(C, r) <= 225 * 1024) { R = r; break; }
-  if (!R) return p;
-  while (R > 16 && R / 2 >= N) R /= 2;
-  p.R = R;
-  p.nchunks = (N + R - 1) / R;
-  p.smem = x_attn_bwd_smem(C, R);
-  p.splits = fa_splits(BT, p.Z, N, p.nchunks, p.smem, p.ntw);
+  if (!fa_bwd_tile(BT, N, C, p.ntw, x_attn_bwd_smem, p.R, p.nbuf)) return p;
+  p.nchunks = (N + p.R - 1) / p.R;
+  p.splits = fa_splits(BT, p.Z, N, p.nchunks, x_attn_bwd_smem(C, p.R, p.nbuf), p.ntw);
+  if ((p.nchunks + p.splits - 1) / p.splits < 2) p.nbuf = 1;
+  p.smem = x_attn_bwd_smem(C, p.R, p.nbuf);
+  fa_widen_z(BT, p.splits, C, p.smem, 1, 3, p.Z, p.zcols, p.ntw);
   p.ok = true;
   return p;
 }
@@ -1189,11 +1235,11 @@ struct TokAttnBwdArgs {
   bf16* gV; float* d_tok;
   int* err_flag;
   float invN;
-  int N, C, K, Kp, ld_tok, R, nchunks, splits, zcols;
+  int N, C, K, Kp, ld_tok, R, nchunks, splits, zcols, nbuf;
 };
 
 template <int NTW>
-__global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs a) {
+__global__ void __launch_bounds__(256, (NTW <= 8 ? 2 : 1)) tok_attn_bwd_kernel(const TokAttnBwdArgs a) {
   extern __shared__ __align__(128) uint8_t fa_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int C = a.C, N = a.N, K = a.K, R = a.R;
@@ -1201,8 +1247,8 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
   const int b = blockIdx.y, split = blockIdx.x, z = blockIdx.z;
   uint8_t* Tsm = fa_smem;                                // latent tokens T
   uint8_t* Dsm = Tsm + (size_t)KL * pitch;               // dT'[b]
-  uint8_t* Vsm = Dsm + (size_t)KL * pitch;
-  uint8_t* Ps = Vsm + (size_t)R * pitch;                 // [R][32] bf16 P
+  uint8_t* Vsm0 = Dsm + (size_t)KL * pitch;              // nbuf V tiles: the next chunk lands while this one is worked on
+  uint8_t* Ps = Vsm0 + (size_t)a.nbuf * R * pitch;       // [R][32] bf16 P
   uint8_t* Ls = Ps + (size_t)R * PS_PITCH;               // [R][32] bf16 dL1
   float* sred = reinterpret_cast<float*>(Ls + (size_t)R * PS_PITCH);
   float* dvec = sred + 16 * 8 * 32;                      // [32] D, [32] M, [32] 1 / L
@@ -1210,8 +1256,7 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
   const int c_begin = (int)((long long)split * a.nchunks / a.splits), c_end = (int)((long long)(split + 1) * a.nchunks / a.splits);
   const uint32_t row_bytes = (uint32_t)C * 2;
   if (tid == 0) {
-    tc::mbar_init(tc::smem_u32(&bars[0]), 1);
-    tc::mbar_init(tc::smem_u32(&bars[1]), 1);
+    for (int i = 0; i < 3; ++i) tc::mbar_init(tc::smem_u32(&bars[i]), 1);
     tc::fence_barrier_init();
   }
   if (tid < KL) {
@@ -1221,13 +1266,16 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
     dvec[2 * KL + tid] = (tid < K && L > 0.f) ? 1.f / L : 0.f;
   }
   __syncthreads();
-  const uint32_t ts = tc::smem_u32(Tsm), ds = tc::smem_u32(Dsm), vs = tc::smem_u32(Vsm), bar1 = tc::smem_u32(&bars[1]);
+  const uint32_t ts = tc::smem_u32(Tsm), ds = tc::smem_u32(Dsm);
+  const uint32_t buf_bytes = (uint32_t)R * (uint32_t)pitch;
   const int rlane = lane * 8 + warp;                    // the row this thread copies (see tok_attn_fwd_kernel)
-  auto issue_chunk = [&](int chunk) {                   // EVERY thread of the CTA
+  auto issue_chunk = [&](int chunk, int buf) {          // EVERY thread of the CTA
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
-    if (tid == 0) tc::mbar_expect_tx(bar1, (uint32_t)rows * row_bytes);
-    if (rlane < rows) bulk_g2s(vs + (uint32_t)(rlane * pitch), a.V + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar1);
+    const uint32_t bar = tc::smem_u32(&bars[1 + buf]);
+    const uint32_t vsb = tc::smem_u32(Vsm0) + (uint32_t)buf * buf_bytes;
+    if (tid == 0) tc::mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
+    if (rlane < rows) bulk_g2s(vsb + (uint32_t)(rlane * pitch), a.V + ((size_t)b * N + n0 + rlane) * C, row_bytes, bar);
   };
   {
     const uint32_t bar = tc::smem_u32(&bars[0]);
@@ -1237,7 +1285,8 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
       bulk_g2s(ts + (uint32_t)(k * pitch), a.tokb + (size_t)k * a.ld_tok, row_bytes, bar);
       bulk_g2s(ds + (uint32_t)(k * pitch), a.dTpB + ((size_t)b * K + k) * C, row_bytes, bar);
     }
-    if (c_begin < c_end) issue_chunk(c_begin);
+    if (c_begin < c_end) issue_chunk(c_begin, 0);
+    if (a.nbuf == 2 && c_begin + 1 < c_end) issue_chunk(c_begin + 1, 1);
   }
   if (K < KL) {
     zero_rows(Tsm + (size_t)K * pitch, KL - K, pitch, (int)row_bytes, tid, 256);
@@ -1262,14 +1311,17 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
   const int k_begin = min(C, kpart * ksteps * 16), k_end = min(C, k_begin + ksteps * 16);
   const int dsteps = ((zcols >> 4) + KS - 1) / KS;
   const int d_begin = zc0 + min(zcols, kpart * dsteps * 16), d_end = zc0 + min(zcols, (kpart + 1) * dsteps * 16);
-  uint32_t ph = 0;
+  uint32_t ph0 = 0, ph1 = 0;
   bool ok = true;
   for (int chunk = c_begin; chunk < c_end; ++chunk) {
     const int n0 = chunk * R;
     const int rows = min(R, N - n0);
+    const int buf = a.nbuf == 2 ? ((chunk - c_begin) & 1) : 0;
+    uint8_t* Vsm = Vsm0 + (size_t)buf * buf_bytes;
+    const uint32_t vs = tc::smem_u32(Vsm);
     if (chunk == c_begin) ok = wait_bar(tc::smem_u32(&bars[0]), 0, a.err_flag);
-    if (ok) ok = wait_bar(bar1, ph, a.err_flag);
-    ph ^= 1;
+    if (ok) ok = wait_bar(tc::smem_u32(&bars[1 + buf]), buf ? ph1 : ph0, a.err_flag);
+    if (buf) ph1 ^= 1; else ph0 ^= 1;
     if (rows < R) zero_rows(Vsm + (size_t)rows * pitch, R - rows, pitch, (int)row_bytes, tid, 256);
     ok = __syncthreads_and(ok);
     if (!ok) break;
@@ -1358,19 +1410,19 @@ __global__ void __launch_bounds__(256) tok_attn_bwd_kernel(const TokAttnBwdArgs 
       bulk_commit();
       bulk_wait_read0();
     }
-    if (chunk + 1 < c_end) {
-      __syncthreads();                                 // every row of the tile has left: the buffer may be overwritten
-      issue_chunk(chunk + 1);
+    if (chunk + a.nbuf < c_end) {
+      __syncthreads();                                 // every row of the tile has left: this buffer may be overwritten
+      issue_chunk(chunk + a.nbuf, buf);
     }
   }
   if (!__syncthreads_and(ok)) return;
   if (p_begin < npairs && a.d_tok) atomic_flush_tokens<NTW>(o, a.d_tok, C, K, zc0, p_begin, npairs, g, t);
 }
 
-struct TokAttnBwdPlan { bool ok; int R, nchunks, splits, Z, zcols, ntw; size_t smem; };
-inline size_t tok_attn_bwd_smem(int C, int R) {
+struct TokAttnBwdPlan { bool ok; int R, nbuf, nchunks, splits, Z, zcols, ntw; size_t smem; };
+inline size_t tok_attn_bwd_smem(int C, int R, int nbuf) {
   const size_t pitch = (size_t)C * 2 + 16;
-  return 2 * (size_t)KL * pitch + (size_t)R * pitch + 2 * (size_t)R * PS_PITCH + (size_t)(16 * 8 * 32 + 96) * 4 + 64;
+  return 2 * (size_t)KL * pitch + (size_t)nbuf * R * pitch + 2 * (size_t)R * PS_PITCH + (size_t)(16 * 8 * 32 + 96) * 4 + 64;
 }
 inline TokAttnBwdPlan make_tok_attn_bwd_plan(int BT, int N, int C, int K) {
   TokAttnBwdPlan p{};
@@ -1379,16 +1431,12 @@ inline TokAttnBwdPlan make_tok_attn_bwd_plan(int BT, int N, int C, int K) {
   p.zcols = ((C / 16 + p.Z - 1) / p.Z) * 16;
   p.ntw = 2 * ((p.zcols / 16 + 7) / 8);
   if (p.ntw > 12) return p;
-  static const int cand[] = {128, 64, 32, 16};
-  int R = 0;
-  if (p.ntw < 10) for (int r : cand) if (tok_attn_bwd_smem(C, r) <= 104 * 1024) { R = r; break; }
-  if (!R) for (int r : cand) if (r <= 64 && tok_attn_bwd_smem(C, r) <= 225 * 1024) { R = r; break; }
-  if (!R) return p;
-  while (R > 16 && R / 2 >= N) R /= 2;
-  p.R = R;
-  p.nchunks = (N + R - 1) / R;
-  p.smem = tok_attn_bwd_smem(C, R);
-  p.splits = fa_splits(BT, p.Z, N, p.nchunks, p.smem, p.ntw);
+  if (!fa_bwd_tile(BT, N, C, p.ntw, tok_attn_bwd_smem, p.R, p.nbuf)) return p;
+  p.nchunks = (N + p.R - 1) / p.R;
+  p.splits = fa_splits(BT, p.Z, N, p.nchunks, tok_attn_bwd_smem(C, p.R, p.nbuf), p.ntw);
+  if ((p.nchunks + p.splits - 1) / p.splits < 2) p.nbuf = 1;
+  p.smem = tok_attn_bwd_smem(C, p.R, p.nbuf);
+  fa_widen_z(BT, p.splits, C, p.smem, 2, 3, p.Z, p.zcols, p.ntw);
   p.ok = true;
   return p;
 }
