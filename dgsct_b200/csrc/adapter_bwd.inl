@@ -471,7 +471,7 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     const int wpb = C <= 768 ? 8 : 4;
     static PerDeviceOnce attr1;
     if (attr1.first()) DGSCT_CUDA_CHECK(cudaFuncSetAttribute(bwd_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    StageScope _sc(ST_OUT_LN, st); count_launch();
+    StageScope _sc(ST_BWD_OUT, st); count_launch();
     { cudaError_t pre = cudaGetLastError(); if (pre != cudaSuccess) { set_cuda_error(pre, "before bwd_out"); return DGSCT_ERR_CUDA; } }
     // vectorised kernel: also produces the bn2-backward column sums (colA = sum dB2, colB = sum dB2*Uo)
     bn2_sums_done = launch_bwd_out_vec(a, use_bn ? colA : nullptr, use_bn ? colB : nullptr, st);
