@@ -497,6 +497,18 @@ class VisualAdapter(nn.Module):
             raise ValueError("expected x (BT,C,N,1) and vis_token (BT,C',N',1)")
         xt = x.squeeze(-1).permute(0, 2, 1)            # (BT,N,C): a view of the caller's contiguous buffer
         ot = vis_token.squeeze(-1).permute(0, 2, 1)
+        # fp32 callers (the reference trains in fp32, main_trans.py:92) reach the tensor-core pipeline the way they would reach
+        # torch's own bf16 kernels: under torch.autocast(dtype=bfloat16), or with module.compute_dtype = torch.bfloat16 -- the
+        # tokens are cast at the boundary (differentiably) and the outputs come back in the caller's dtype.  Without either,
+        # fp32 tensors take the exact-fp32 SIMT path.
+        io_dtype = x.dtype
+        low = getattr(self, "compute_dtype", None)
+        if low is None and x.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+            low = torch.bfloat16
+        if low == torch.bfloat16 and xt.dtype == torch.float32:
+            xt, ot = xt.to(torch.bfloat16), ot.to(torch.bfloat16)
+        elif low not in (None, torch.bfloat16, torch.float32):
+            raise TypeError(f"compute_dtype must be None, torch.float32 or torch.bfloat16 (got {low})")
         if xt.shape[1] != self.conv_dim_out or ot.shape[1] != self.conv_dim_in:
             raise RuntimeError(f"token counts ({xt.shape[1]}, {ot.shape[1]}) do not match conv_dim_out/conv_dim_in "
                                f"({self.conv_dim_out}, {self.conv_dim_in})")
@@ -515,6 +527,8 @@ class VisualAdapter(nn.Module):
         if self.training and self.use_bn:
             self.bn1.num_batches_tracked += 1
             self.bn2.num_batches_tracked += 1
+        if out.dtype != io_dtype:
+            out, smap = out.to(io_dtype), smap.to(io_dtype)
         output = out.permute(0, 2, 1).unsqueeze(-1)
         spatial_att_maps = smap.unsqueeze(1)
         if VARIANT_DEFAULTS[self.variant]["temporal"]:
@@ -654,13 +668,16 @@ def adapter_pair(audio_adapter: "VisualAdapter", vis_adapter: "VisualAdapter", f
     return out_a, out_v, sm_a.unsqueeze(1), sm_v.unsqueeze(1)
 
 
-def patch(module, variant: str = "ave"):
+def patch(module, variant: str = "ave", compute_dtype=None):
     """Replace ``module.VisualAdapter`` (a reference task module such as ``nets.net_trans``) by the engine class
-    bound to ``variant`` so the task script builds engine adapters without further changes."""
+    bound to ``variant`` so the task script builds engine adapters without further changes.  ``compute_dtype=torch.bfloat16``
+    sends an fp32 training script (the reference's default) through the bf16 tensor-core kernels."""
     import functools
 
     class _Bound(VisualAdapter):
         __init__ = functools.partialmethod(VisualAdapter.__init__, variant=variant)
+
+    _Bound.compute_dtype = compute_dtype
 
     _Bound.__name__ = "VisualAdapter"
     module.VisualAdapter = _Bound

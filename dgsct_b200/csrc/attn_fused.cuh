@@ -521,8 +521,10 @@ inline TokAttnPlan make_tok_attn_plan(int BT, int N, int C, int K) {
   p.ntw = 2 * ppw;
   if (p.ntw > 12) return p;
   // rows per chunk / V buffers: two CTAs per SM (<= 104 KB each) when the register budget allows two, else one big CTA
-  static const int cand_small[][2] = {{128, 2}, {64, 2}, {64, 1}, {32, 2}, {32, 1}, {16, 1}};
-  static const int cand_big[][2] = {{64, 2}, {32, 2}, {64, 1}, {32, 1}, {16, 2}, {16, 1}};
+  // (order from a sweep on B200, profiles/r02_fused_attention_chunk_sweep.txt: the phases of a chunk are latency-bound, so more
+  //  rows per chunk beat a second buffer -- C = 192: (128,1) 53.6 us vs (64,2) 63.7; C = 768: (64,1) 44.7 vs (32,2) 47.8)
+  static const int cand_small[][2] = {{128, 2}, {128, 1}, {64, 2}, {64, 1}, {32, 2}, {32, 1}, {16, 1}};
+  static const int cand_big[][2] = {{128, 1}, {64, 1}, {32, 1}, {16, 1}};
   const size_t small = 104 * 1024, big = 225 * 1024;
   int R = 0, nbuf = 0;
   // (the chunk size must not depend on the number of frames: it fixes which rows share a reference maximum, i.e. the bits of P~)
@@ -1153,12 +1155,12 @@ inline int fa_splits(int BT, int Z, int N, int nchunks, size_t smem, int ntw) {
   return sp;
 }
 // (rows per chunk, buffers) of the backward kernels: two CTAs per SM (<= 104 KB) when the call has the CTAs to fill them, else
-// one CTA per SM with everything the 227 KB allow -- double-buffered whenever it fits (the chunk loads are exposed otherwise: a
-// third of the stall samples of the single-buffered kernels sat on the load barrier, ncu round 2)
+// one CTA per SM with what the 227 KB allow.  The kernels can double-buffer their chunks (nbuf = 2), but the sweep on B200
+// (profiles/r02_fused_attention_chunk_sweep.txt) never preferred it to twice the rows per chunk: single buffers, largest R.
 template <typename SmemFn>
 inline bool fa_bwd_tile(int BT, int N, int C, int ntw, SmemFn smem_of, int& R, int& nbuf) {
-  static const int small_c[][2] = {{128, 2}, {64, 2}, {32, 2}, {64, 1}, {32, 1}, {16, 2}, {16, 1}};
-  static const int big_c[][2] = {{64, 2}, {32, 2}, {16, 2}, {64, 1}, {32, 1}, {16, 1}};
+  static const int small_c[][2] = {{128, 1}, {64, 1}, {32, 1}, {16, 1}};
+  static const int big_c[][2] = {{64, 1}, {32, 1}, {16, 1}};
   const long long ctas_est = (long long)BT * ((N + 192) / 384 > 0 ? (N + 192) / 384 : 1);
   R = 0;
   if (ntw < 10 && ctas_est > 148)

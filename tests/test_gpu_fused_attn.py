@@ -26,6 +26,8 @@ CASES = [
     ("ave", 320, 100, 128, 49, 5, {}),             # PVT width: 20 column pairs over 8 warps
     ("avqa", 768, 144, 384, 256, 6, dict(K=2, g=4, use_bn=False, use_gate=False)),   # K = 2: masked latent tokens
     ("s4", 192, 576, 96, 1024, 5, dict(use_bn=False, use_gate=False)),
+    ("ave", 64, 10, 32, 7, 1, dict(K=17)),         # one frame, fewer rows than a tile, odd token count (second m-tile half masked)
+    ("ave", 128, 300, 64, 20, 2, dict(K=5)),       # K = 5, ragged last chunk, two frames
 ]
 
 
@@ -104,3 +106,41 @@ def test_fused_attention_is_repeatable_in_the_forward():
         if ref is not None:
             assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])
         ref = cur
+
+
+def test_fp32_caller_reaches_the_bf16_kernels_under_autocast_or_compute_dtype():
+    """An fp32 training script (the reference's default, main_trans.py:92) runs the tensor-core pipeline when it asks for it
+    the torch way (autocast) or through module.compute_dtype: same values as an explicit bf16 call, fp32 tensors in and out,
+    fp32 gradients for the caller's fp32 leaves."""
+    import types
+    import dgsct_b200
+    opt = types.SimpleNamespace(is_multimodal=1, num_conv_group=2, is_before_layernorm=1, is_post_layernorm=1)
+    C, N, Co, No = 384, 64, 192, 36
+    ad = dgsct_b200.VisualAdapter(C, C, "bottleneck", reduction_factor=8, opt=opt, num_tk=32, conv_dim_in=No, conv_dim_out=N,
+                                  linear_in=Co, linear_out=C).cuda().eval()
+    cfg = O.make_config("ave", C, N, Co, No)
+    ad.load_state_dict(O.random_params(cfg, seed=7), strict=False)
+    f_v = torch.randn(6, N, C, device="cuda")
+    f_a = torch.randn(6, No, Co, device="cuda")
+    xv, xa = f_v.permute(0, 2, 1).unsqueeze(-1), f_a.permute(0, 2, 1).unsqueeze(-1)
+    with torch.no_grad():
+        ref_out, ref_map = ad(xv.bfloat16(), xa.bfloat16())                       # explicit bf16 call
+        exact_out, _ = ad(xv, xa)                                                 # fp32 tensors, no request: exact-fp32 path
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ac_out, ac_map = ad(xv, xa)
+        ad.compute_dtype = torch.bfloat16
+        cd_out, cd_map = ad(xv, xa)
+    assert ac_out.dtype == torch.float32 and cd_out.dtype == torch.float32 and ac_map.dtype == torch.float32
+    # (same kernels, same inputs; the forward's per-frame column sums are fp32 atomics, so not bit-for-bit)
+    for got in (ac_out, cd_out):
+        assert rel_l2(got.cpu(), ref_out.float().cpu()) < 1e-3
+    assert rel_l2(cd_map.cpu(), ref_map.float().cpu()) < 1e-3 and rel_l2(ac_map.cpu(), ref_map.float().cpu()) < 1e-3
+    assert 1e-4 < rel_l2(cd_out.cpu(), exact_out.cpu()) < 1e-2                     # really the bf16 pipeline, within its bar
+    # gradients reach fp32 leaves through the boundary cast
+    ad.train()
+    lv, la = f_v.clone().requires_grad_(True), f_a.clone().requires_grad_(True)
+    out, smap = ad(lv.permute(0, 2, 1).unsqueeze(-1), la.permute(0, 2, 1).unsqueeze(-1))
+    (out.sum() + smap.sum()).backward()
+    assert lv.grad is not None and lv.grad.dtype == torch.float32 and la.grad.dtype == torch.float32
+    assert ad.fc.weight.grad is not None and float(ad.fc.weight.grad.abs().max()) > 0
+    assert L.lib().dgsct_tc_error_flag(1) == 0
