@@ -232,6 +232,20 @@ static int run_tc_only(const Gemm& g, const tc::OperandDesc& A, const tc::Operan
   return DGSCT_OK;
 }
 
+// same, for functors that keep per-CTA column partials in shared memory (kBlockStats)
+template <typename TE>
+static int run_tc_only_stats(const Gemm& g, const tc::OperandDesc& A, const tc::OperandDesc& B, int M, int N, int K, int batch, TE te) {
+  tc::Params p;
+  const int rc = tc::make_params(p, A, B, M, N, K, batch, 0, 0, false, tc::epi_row_independent<TE>::value,
+                                 tc::epi_stage_bytes<TE>::value, 1);
+  if (rc != DGSCT_OK) return rc;
+  StageScope _sc(g.stage, g.st);
+  count_launch();
+  cudaError_t e = tc::launch(p, te, g.st);
+  if (e != cudaSuccess) { set_cuda_error(e, g.name); return DGSCT_ERR_CUDA; }
+  return DGSCT_OK;
+}
+
 static tc::OperandDesc K_(const void* p, int rows, int cols, long long ld, long long bs) { return tc::OperandDesc{p, 0, ld, bs, rows, cols}; }
 static tc::OperandDesc MN_(const void* p, int k_rows, int mn_cols, long long ld, long long bs) { return tc::OperandDesc{p, 1, ld, bs, k_rows, mn_cols}; }
 
@@ -649,12 +663,22 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   {
     // z1 = X1 . Wv1^T (pre-bias) -> S1 ; dz1 = dr1 * 1[z1+b>0] ; dX1 += dz1 . Wv1 ; dWv1 += dz1^T X1
     {
-      EpiOut e1 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
-      RC(run_gemm(G_CH, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
-                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
-      StageScope _sc(ST_CHANNEL_QUERY, st); count_launch();
-      bwd_channel_mask_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, bf, C, N, P.v1_b, dr1, G.v1_b);
-      KCHECK("bwd_channel_mask");
+      // tensor-core path: the ReLU mask, dr1 broadcast and d_b1 column sums are the GEMM's epilogue (no pass over (BT,N,C))
+      int rcm = DGSCT_ERR_UNSUPPORTED;
+      if (tcp && getenv("DGSCT_NO_FUSED_BWD_EPI") == nullptr) {
+        tc::EpiMaskBcast te{};
+        te.out = (bf16*)S1; te.ld = C; te.sb = (long long)N * C; te.bias = P.v1_b; te.bc = dr1; te.bc_ld = C; te.dbias = G.v1_b;
+        rcm = run_tc_only_stats(G_CH, K_(X1, N, C, C, (long long)N * C), K_(Wv1_op, C, C, ld_v, 0), N, C, C, BT, te);
+        if (rcm != DGSCT_OK && rcm != DGSCT_ERR_UNSUPPORTED) return rcm;
+      }
+      if (rcm == DGSCT_ERR_UNSUPPORTED) {
+        EpiOut e1 = eo(S1, bf, C, (long long)N * C, OUT_STORE);
+        RC(run_gemm(G_CH, K_(X1, N, C, C, (long long)N * C), bf, K_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,
+                    to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+        StageScope _sc(ST_CHANNEL_QUERY, st); count_launch();
+        bwd_channel_mask_kernel<<<dim3(ceil_div(C, 32), BT, N >= 512 ? 8 : 1), 256, 0, st>>>(S1, bf, C, N, P.v1_b, dr1, G.v1_b);
+        KCHECK("bwd_channel_mask");
+      }
     }
     EpiOut e2 = eo(gX1, bf, C, (long long)N * C, OUT_ADD);
     RC(run_gemm(G_CH, K_(S1, N, C, C, (long long)N * C), bf, MN_(Wv1_op, C, C, ld_v, 0), wbf, N, C, C, BT,

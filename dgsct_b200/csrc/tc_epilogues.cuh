@@ -443,6 +443,46 @@ struct EpiSpatialRowsum {
   }
 };
 
+// ---- backward epilogue that absorbs the row kernel which used to follow its GEMM (round 2) -----------------------------------
+// (Measured on B200, scripts/gpu_r2w.sh: this one saves 13-16 us per call.  The same treatment of the spatial gate's dXc product
+//  -- read-modify-write of dX1, a load of X1 and per-frame column sums in the epilogue -- cost 4-29 us MORE per call than the
+//  separate bwd_xc_kernel and was removed again: a TMEM-drain epilogue is a poor place for three extra memory streams.)
+// Channel gate: z1 = X1 . Wv1^T is only needed as a ReLU mask.  out[b,m,n] = (acc + bias[n] > 0) ? bc[b,n] : 0 (bf16) is dz1
+// directly (bwd_channel_mask_kernel read and rewrote the whole (BT,N,C) tensor); d bias[n] += column sums through the CTA's
+// shared-memory partials (one global atomic per column per CTA).
+struct EpiMaskBcast {
+  static constexpr bool kRowIndependent = true;
+  static constexpr bool kBlockStats = true;
+  bf16* out; long long ld, sb; const float* bias; const float* bc; int bc_ld; float* dbias; float* blk;
+  __device__ __forceinline__ void flush_block(const float* b, int N, int tid, int nthreads) const {
+    if (!dbias) return;
+    for (int c = tid; c < N; c += nthreads) {
+      const float s = b[c];
+      if (s != 0.f) atomicAdd(&dbias[c], s);
+    }
+  }
+  __device__ __forceinline__ void begin(int, int, bool) {}
+  __device__ __forceinline__ void end(int, int, bool) {}
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    float bn[16], d[16];
+    load16_guard(bias + n0, bn, nvalid);
+    load16_guard(bc + (long long)(row_ok ? b : 0) * bc_ld + n0, d, nvalid);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (row_ok && j < nvalid && v[j] + bn[j] > 0.f) ? d[j] : 0.f;
+    if (row_ok && nvalid > 0) store_row16<true>(out, (size_t)((long long)b * sb + (long long)m * ld + n0), v, nvalid);
+    if (dbias) {
+      const float s = warp_colsum16(v);
+      const int lane = threadIdx.x & 31;
+      const int col = n0 + colsum16_owner_col(lane);
+      if (((lane & 1) == 0) && col < N) {
+        if (blk) atomicAdd(&blk[col], s);
+        else atomicAdd(&dbias[col], s);
+      }
+    }
+  }
+};
+
 // Q[b,m,0:32] = softmax_k(acc[0:32])    (N == 32, one N-block), bf16
 struct EpiRowSoftmax32 {
   static constexpr bool kWholeRow = true;
