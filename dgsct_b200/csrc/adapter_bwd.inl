@@ -496,13 +496,18 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   if (use_bn) {
     StageScope _sc(ST_BN_FINALIZE, st); count_launch(3);
     if (!bn2_sums_done) col_reduce_kernel<<<dim3(ceil_div(C, 32), 64), 256, 0, st>>>(gUo, bf, C, Uo, 0, C, R, C, colA, colB);
-    bn_bwd_coeffs_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, 1, train, colA, colB, (const float*)(fw + fp.bn2_mean),
-                                                           (const float*)(fw + fp.bn2_rstd), P.bn2_w, (double)R, coefA, coefB, coefC,
-                                                           G.bn2_w, G.bn2_b);
-    launch_affine_combine(gUo, bf, C, Uo, C, coefA, coefB, coefC, R, C, ew_grid, st);
+    // coefficients + combine in one pass when the vector kernel applies (P.bn2_w may sit at any 4-byte offset: checked inside)
+    if (!launch_bn_bwd_apply(gUo, bf, C, Uo, C, colA, colB, (const float*)(fw + fp.bn2_mean), (const float*)(fw + fp.bn2_rstd), P.bn2_w,
+                             (double)R, train, G.bn2_w, G.bn2_b, R, C, st)) {
+      bn_bwd_coeffs_kernel<<<ceil_div(C, 128), 128, 0, st>>>(C, 1, train, colA, colB, (const float*)(fw + fp.bn2_mean),
+                                                             (const float*)(fw + fp.bn2_rstd), P.bn2_w, (double)R, coefA, coefB, coefC,
+                                                             G.bn2_w, G.bn2_b);
+      launch_affine_combine(gUo, bf, C, Uo, C, coefA, coefB, coefC, R, C, ew_grid, st);
+    }
     KCHECK("bn2_bwd");
   }
   // ---- 2. up projection: dZr = dUo . Wup ; dWup += dUo^T . Zr ---------------------------------------------------
+  bool relu_bn1_sums_done = false;
   {
     // Zr = relu(Z*sc1+sh1) as a GEMM operand: the tensor-core forward kept it (bf16, pitch ldz); the fp32 path
     // rebuilds it into S2 (free until step 5)
@@ -513,9 +518,21 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       KCHECK("zr_f32");
       Zr = S2;
     }
-    EpiOut e1 = eo(gZ, bf, ldz, (long long)N * ldz, OUT_STORE);
-    RC(run_gemm(G_UD, K_(gUo, N, C, C, (long long)N * C), bf, MN_(Wup_op, C, Cd, ld_up, 0), wbf, N, Cd, C, BT,
-                to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    // tensor-core path: ReLU mask of bn1 and the bn1-backward column sums are this product's epilogue
+    int rcz = DGSCT_ERR_UNSUPPORTED;
+    if (tcp && getenv("DGSCT_NO_FUSED_BWD_EPI") == nullptr) {
+      tc::EpiReluMaskStats te{};
+      te.out = (bf16*)gZ; te.ld = ldz; te.sb = (long long)N * ldz; te.z = Z; te.zld = Cd; te.zsb = (long long)N * Cd; te.sc = sc1; te.sh = sh1;
+      te.colA = use_bn ? colA1 : nullptr; te.colB = use_bn ? colB1 : nullptr;
+      rcz = run_tc_only_stats(G_UD, K_(gUo, N, C, C, (long long)N * C), MN_(Wup_op, C, Cd, ld_up, 0), N, Cd, C, BT, te);
+      if (rcz != DGSCT_OK && rcz != DGSCT_ERR_UNSUPPORTED) return rcz;
+      relu_bn1_sums_done = (rcz == DGSCT_OK);
+    }
+    if (rcz == DGSCT_ERR_UNSUPPORTED) {
+      EpiOut e1 = eo(gZ, bf, ldz, (long long)N * ldz, OUT_STORE);
+      RC(run_gemm(G_UD, K_(gUo, N, C, C, (long long)N * C), bf, MN_(Wup_op, C, Cd, ld_up, 0), wbf, N, Cd, C, BT,
+                  to_tc_full<tc::EpiOut<true, OUT_STORE, false, false, false>>(e1), e1, AxIdentity{}, true));
+    }
     RC(fork_side());                                                  // gUo is final; Zr is a saved/recomputed activation
     EpiOut e2 = eo(dWup_d, 0, ldz, 0, OUT_ATOMIC);
     RC(run_gemm(S_UD, MN_(gUo, N, C, C, (long long)N * C), bf, MN_(Zr, N, Cd, ldz, (long long)N * ldz), bf, C, Cd, N, BT,
@@ -526,18 +543,22 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   }
   // relu + bn1 backward on dZr -> dZ (in place in gZ)
   {
-    StageScope _sc(ST_BN_FINALIZE, st); count_launch(4);
-    relu_mask_kernel<<<ew_grid, 256, 0, st>>>(gZ, bf, ldz, Z, Cd, sc1, sh1, R, Cd);
+    StageScope _sc(ST_BN_FINALIZE, st); count_launch(relu_bn1_sums_done ? 1 : 4);
+    if (!relu_bn1_sums_done) relu_mask_kernel<<<ew_grid, 256, 0, st>>>(gZ, bf, ldz, Z, Cd, sc1, sh1, R, Cd);
     if (use_bn) {
+      if (!relu_bn1_sums_done)
       { const int gx = ceil_div(Cd, 32);                      // narrow (C/r columns): spread the rows over ~4 blocks per SM
         long long gy = (R + 255) / 256;
         if (gy > (148 * 4) / gx) gy = (148 * 4) / gx;
         if (gy < 1) gy = 1;
         col_reduce_kernel<<<dim3(gx, (unsigned)gy), 256, 0, st>>>(gZ, bf, ldz, Z, 0, Cd, R, Cd, colA1, colB1); }
-      bn_bwd_coeffs_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, 1, train, colA1, colB1, (const float*)(fw + fp.bn1_mean),
-                                                              (const float*)(fw + fp.bn1_rstd), P.bn1_w, (double)R, coefA, coefB, coefC,
-                                                              G.bn1_w, G.bn1_b);
-      launch_affine_combine(gZ, bf, ldz, Z, Cd, coefA, coefB, coefC, R, Cd, ew_grid, st);
+      if (!launch_bn_bwd_apply(gZ, bf, ldz, Z, Cd, colA1, colB1, (const float*)(fw + fp.bn1_mean), (const float*)(fw + fp.bn1_rstd), P.bn1_w,
+                               (double)R, train, G.bn1_w, G.bn1_b, R, Cd, st)) {
+        bn_bwd_coeffs_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, 1, train, colA1, colB1, (const float*)(fw + fp.bn1_mean),
+                                                                (const float*)(fw + fp.bn1_rstd), P.bn1_w, (double)R, coefA, coefB, coefC,
+                                                                G.bn1_w, G.bn1_b);
+        launch_affine_combine(gZ, bf, ldz, Z, Cd, coefA, coefB, coefC, R, Cd, ew_grid, st);
+      }
     }
     KCHECK("bn1_bwd");
   }
@@ -829,13 +850,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   if (fc_first) {
     // forward was V = Wres . O' + b_res (x) s + b_fc with O' = other . Wfc^T kept in the U buffer, s = rowsum(Wfc)
     const void* Op = U;
-    float* fcs = (float*)(ws + bp.fc_s); float* fct = (float*)(ws + bp.fc_t);
+    const float* fcs = (const float*)(pk + pp.fc_s); float* fct = (float*)(ws + bp.fc_t);   // (row sums of fc.weight: from the pack launch)
     const bool has_bias = !(d.flags & DGSCT_F_NO_CONV_BIAS) && P.resample_b;
-    if (has_bias) {
-      StageScope _sc(ST_MISC, st); count_launch();
-      fc_rowsum_kernel<<<ceil_div(C, 8), 256, 0, st>>>((const bf16*)Wfc_op, C, Co, ld_fc, fcs);
-      KCHECK("fc_rowsum");
-    }
     RC(fork_side());                                                  // gV is final (d fc_b: see sum_frames_kernel)
     // dO'[b] (No,C) = Wres^T . dV[b]  -> gU
     EpiOut e1 = eo(gU, bf, C, (long long)No * C, OUT_STORE);

@@ -336,6 +336,7 @@ int pack_params(const dgsct_desc& d, const dgsct_params& P, char* packed, cudaSt
   seg(2, P.a1_b, P.a2_b, pp.cat1_bias, C, H, 0, 1);
   seg(1, P.down_w, nullptr, pp.down, Cd, C, pp.ld_c, d.g);
   seg(1, P.up_w, nullptr, pp.up, C, Cd, pp.ld_up, d.g);
+  seg(3, P.fc_w, nullptr, pp.fc_s, C, Co, 32, 1);                  // (ld = 32 only sizes the x extent: a warp per row)
   count_launch();
   // the x extent covers the LARGEST segment with ~8 elements per thread; small segments finish in their first blocks
   size_t bx = (biggest + 256 * 8 - 1) / (256 * 8);
@@ -495,10 +496,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     // (R1') O'[b] (No,C) = other[b] (No,Co) . Wfc^T          (frames flattened, Wfc resident)
     // (R2') V[b] (N,C)  = Wres (N,No) . O'[b] + b_res[n] * s[c] + b_fc[c],  s = rowsum(Wfc) ; osum[b,c] = sum_n V
     bf16* Op = U;
-    float* fcs = (float*)(ws + pl.fc_s);
-    { StageScope _sc(ST_RESAMPLE_FC, st); count_launch();
-      fc_rowsum_kernel<<<ceil_div(C, 8), 256, 0, st>>>(Wfc, C, Co, pp.ld_fc, fcs);
-      DGSCT_LAUNCH_CHECK("fc_rowsum"); }
+    const float* fcs = (const float*)(pk + pp.fc_s);          // row sums of the bf16 fc.weight copy, made by the pack launch
     {
       auto te = tc_store<true>(Op, C, (long long)No * C);
       DGSCT_RC(gemm_tc_only(ST_RESAMPLE_FC, "resample_fc_first", kmaj(other, No, Co, Co, (long long)No * Co),
@@ -751,11 +749,18 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
       DGSCT_RC(gemm_auto(ST_DOWN, "down_sampler", true, kmaj(Yb, N, C, C, (long long)N * C), kmaj(Wdn, Cd, C, pp.ld_c, 0),
                          N, Cd, C, BT, te, se, st));
       if (taps && taps->Z) DGSCT_RC(tap(Z, 0, taps->Z, (size_t)BT * N * Cd, st));
-      StageScope _sc(ST_BN_FINALIZE, st); count_launch(2);
-      bn_finalize_kernel<<<ceil_div(Cd, 128), 128, 0, st>>>(Cd, use_bn, (train && use_bn) ? 1 : 0, bn1_sum, bn1_sq, count, P.bn1_w, P.bn1_b, P.bn1_rm,
-                                                             P.bn1_rv, d.eps_bn, d.bn_momentum, bn1_scale, bn1_shift,
-                                                             (float*)(ws + pl.bn1_mean), (float*)(ws + pl.bn1_rstd), upd);
-      bn_relu_kernel<<<2048, 256, 0, st>>>(Z, bn1_scale, bn1_shift, Zr, rowsBT, Cd, ldz);
+      StageScope _sc(ST_BN_FINALIZE, st); count_launch();
+      {   // finalize + bn1 + ReLU in one launch (the running-stat race: only block 0 reads-modifies-writes rm / rv, nobody reads them
+          // in train mode; in eval mode they are read-only)
+        const long long tot = rowsBT * Cd;
+        long long blocks = (tot + 255) / 256;
+        if (blocks > 2048) blocks = 2048;
+        if (blocks < 1) blocks = 1;
+        bn_finalize_relu_kernel<<<(unsigned)blocks, 256, (size_t)2 * Cd * 4, st>>>(Z, Zr, rowsBT, Cd, ldz, use_bn, (train && use_bn) ? 1 : 0, bn1_sum,
+                                                                                 bn1_sq, count, P.bn1_w, P.bn1_b, P.bn1_rm, P.bn1_rv, d.eps_bn,
+                                                                                 d.bn_momentum, bn1_scale, bn1_shift, (float*)(ws + pl.bn1_mean),
+                                                                                 (float*)(ws + pl.bn1_rstd), upd);
+      }
       DGSCT_LAUNCH_CHECK("bn1_finalize");
     }
   }

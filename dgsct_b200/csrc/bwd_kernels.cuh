@@ -445,6 +445,58 @@ __global__ void __launch_bounds__(256) affine_combine_vec_kernel(bf16* __restric
 inline void launch_affine_combine(void* g, int g_bf16, long long g_ld, const float* x, long long x_ld, const float* A, const float* B,
                                   const float* Cc, long long rows, int C, int ew_grid, cudaStream_t st);
 
+// BatchNorm backward in ONE pass: the per-channel coefficients of bn_bwd_coeffs_kernel are a handful of flops from five C-sized
+// vectors, so every thread derives them for its 8 channels instead of waiting for a 1-block kernel to publish them; the threads
+// of row 0 also add the parameter gradients (each channel exactly once).  g = A g + B x + Cc in place (bf16 g, fp32 x).
+__global__ void __launch_bounds__(256) bn_bwd_apply_vec_kernel(bf16* __restrict__ g, long long g_ld, const float* __restrict__ x, long long x_ld,
+                                                               const float* __restrict__ sum_dy, const float* __restrict__ sum_dyx,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const float* __restrict__ w, float inv_count, int train,
+                                                               float* __restrict__ dW, float* __restrict__ dB, long long rows, int C) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i - r * nvec) * 8;
+    const uint4 raw = *reinterpret_cast<const uint4*>(g + r * g_ld + c);
+    float v[8], xv[8], sdy[8], sdx[8], mu[8], rs[8], ww[8];
+    unpack8(raw, v);
+    ldf8(x + r * x_ld + c, xv);
+    ldf8(sum_dy + c, sdy); ldf8(sum_dyx + c, sdx); ldf8(mean + c, mu); ldf8(rstd + c, rs); ldf8(w + c, ww);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float db = sdy[j];
+      const float dw = (sdx[j] - mu[j] * db) * rs[j];
+      const float wr = ww[j] * rs[j];
+      if (r == 0) {
+        if (dW) atomicAdd(&dW[c + j], dw);
+        if (dB) atomicAdd(&dB[c + j], db);
+      }
+      const float a = wr;
+      const float b = train ? -wr * rs[j] * dw * inv_count : 0.f;
+      const float cc = train ? (-wr * db * inv_count + wr * rs[j] * mu[j] * dw * inv_count) : 0.f;
+      v[j] = fmaf(a, v[j], fmaf(b, xv[j], cc));
+    }
+    *reinterpret_cast<uint4*>(g + r * g_ld + c) = pack8(v);
+  }
+}
+// true when the fused pass ran (bf16 g, 8-channel vectors, 16-byte aligned rows); else the caller runs coeffs + combine
+inline bool launch_bn_bwd_apply(void* g, int g_bf16, long long g_ld, const float* x, long long x_ld, const float* sum_dy, const float* sum_dyx,
+                                const float* mean, const float* rstd, const float* w, double count, int train, float* dW, float* dB,
+                                long long rows, int C, cudaStream_t st) {
+  if (!(g_bf16 && C % 8 == 0 && g_ld % 8 == 0 && x_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((reinterpret_cast<uintptr_t>(sum_dy) | reinterpret_cast<uintptr_t>(sum_dyx) |
+        reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(rstd) | reinterpret_cast<uintptr_t>(w)) & 15) == 0))
+    return false;
+  const long long total = rows * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks < 1) blocks = 1;
+  bn_bwd_apply_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<bf16*>(g), g_ld, x, x_ld, sum_dy, sum_dyx, mean, rstd, w,
+                                                            (float)(1.0 / count), train, dW, dB, rows, C);
+  return true;
+}
+
 // out[k,c] += sum_b in[b,k,c]     (gradient of the shared latent tokens through T' = T + ...)
 // out[i] += sum_b in[b, i]  (i < per_frame = K*C).  With d_fcb != NULL the same sums also feed the gradient of fc.bias:
 //   d fc_b[c] = sum_{b,n} dV[b,n,c]  with  dV = P dT' + dL1 T + dobar/N .

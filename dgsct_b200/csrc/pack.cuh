@@ -8,6 +8,7 @@ namespace dgsct {
 struct PackPlan {
   size_t res, fc, tok, v1, v2, down, up, total;
   size_t cat1, bott, catt, cat1_bias;    // [a1_w; a2_w] (C+H, C), bottleneck (H, C), channel gate (C, H), [a1_b; a2_b] fp32
+  size_t fc_s;                           // row sums of the bf16 fc.weight copy (C) fp32: rank-1 bias factor of the re-associated resampler
   int ld_res, ld_fc, ld_c, ld_up, ld_h;
 };
 
@@ -30,6 +31,7 @@ inline PackPlan make_pack_plan(const dgsct_desc& d) {
   p.bott = take(H * p.ld_c * 2);
   p.catt = take(C * p.ld_h * 2);
   p.cat1_bias = take((C + H) * 4);
+  p.fc_s = take(C * 4);
   p.total = off;
   return p;
 }
@@ -64,9 +66,10 @@ struct PackSeg {
   void* dst;
   int kind;                              // 0: rows fp32 -> bf16 (pad columns zeroed); 1: grouped 1x1 conv -> dense block-diagonal bf16;
                                          // 2: fp32 concat [src (rows) ; src2 (cols)] -> fp32
+                                         // 3: dst[r] = sum_c bf16(src[r, c])  (fp32; a warp per row)
   int rows, cols, ld, groups;
 };
-constexpr int PACK_MAX_SEGS = 12;
+constexpr int PACK_MAX_SEGS = 13;
 struct PackTable { PackSeg seg[PACK_MAX_SEGS]; int n; };
 
 __global__ void __launch_bounds__(256) pack_all_kernel(const PackTable t) {
@@ -90,9 +93,19 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackTable t) {
       if (c < g.cols && c / ipg == o / opg) v = g.src[(size_t)o * ipg + (c - (o / opg) * ipg)];
       dst[i] = __float2bfloat16_rn(v);
     }
-  } else {
+  } else if (g.kind == 2) {
     float* dst = reinterpret_cast<float*>(g.dst);
     for (size_t i = i0; i < (size_t)(g.rows + g.cols); i += stride) dst[i] = i < (size_t)g.rows ? g.src[i] : g.src2[i - g.rows];
+  } else {
+    if (!g.src) return;
+    float* dst = reinterpret_cast<float*>(g.dst);
+    const int lane = threadIdx.x & 31;
+    for (size_t r = i0 >> 5; r < (size_t)g.rows; r += stride >> 5) {
+      float acc = 0.f;
+      for (int c = lane; c < g.cols; c += 32) acc += __bfloat162float(__float2bfloat16_rn(g.src[r * g.cols + c]));
+      acc = warp_sum(acc);
+      if (lane == 0) dst[r] = acc;
+    }
   }
 }
 
@@ -200,6 +213,51 @@ __global__ void bn_relu_kernel(const float* __restrict__ z, const float* __restr
     const long long row = i / Cd;
     const int c = (int)(i % Cd);
     zr[row * ldz + c] = __float2bfloat16_rn(fmaxf(fmaf(z[i], scale[c], shift[c]), 0.f));
+  }
+}
+
+// bn1 finalize + bn1 + ReLU in one launch (train-mode forward): every block derives the per-channel affine from the fp64 batch
+// moments into shared memory (C/r <= a few hundred channels: cheaper than waiting for a one-block kernel to publish them),
+// block 0 also publishes scale / shift / mean / rstd for the backward and updates the running statistics.
+// Same arithmetic as bn_finalize_kernel (rowwise.cuh).
+__global__ void __launch_bounds__(256) bn_finalize_relu_kernel(const float* __restrict__ z, bf16* __restrict__ zr, long long rows, int Cd, int ldz,
+                                                               int use_bn, int train, const double* __restrict__ sum, const double* __restrict__ sq,
+                                                               double count, const float* __restrict__ w, const float* __restrict__ bias,
+                                                               float* __restrict__ rm, float* __restrict__ rv, float eps, float momentum,
+                                                               float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out, int update_running) {
+  extern __shared__ float bn_sm[];                 // [2][Cd]
+  float* s_sc = bn_sm; float* s_sh = bn_sm + Cd;
+  for (int c = threadIdx.x; c < Cd; c += blockDim.x) {
+    float sc = 1.f, sh = 0.f, mo = 0.f, ro = 1.f;
+    if (use_bn) {
+      double mean, var;
+      if (train) {
+        mean = sum[c] / count;
+        var = sq[c] / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (update_running && blockIdx.x == 0) {
+          const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+          rm[c] = (float)((1.0 - momentum) * rm[c] + momentum * mean);
+          rv[c] = (float)((1.0 - momentum) * rv[c] + momentum * unb);
+        }
+      } else {
+        mean = rm[c];
+        var = rv[c];
+      }
+      const double rstd = 1.0 / sqrt(var + (double)eps);
+      const double scd = (double)w[c] * rstd;
+      sc = (float)scd; sh = (float)((double)bias[c] - mean * scd); mo = (float)mean; ro = (float)rstd;
+    }
+    s_sc[c] = sc; s_sh[c] = sh;
+    if (blockIdx.x == 0) { scale[c] = sc; shift[c] = sh; mean_out[c] = mo; rstd_out[c] = ro; }
+  }
+  __syncthreads();
+  const long long total = rows * Cd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / Cd;
+    const int c = (int)(i % Cd);
+    zr[row * ldz + c] = __float2bfloat16_rn(fmaxf(fmaf(z[i], s_sc[c], s_sh[c]), 0.f));
   }
 }
 

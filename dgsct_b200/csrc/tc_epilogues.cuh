@@ -483,6 +483,49 @@ struct EpiMaskBcast {
   }
 };
 
+// Bottleneck: dZr = dUo . Wup must pass the ReLU of bn1 and feed bn1's backward sums.  out[b,m,n] = (z sc[n] + sh[n] > 0) ?
+// acc : 0 (bf16), colA[n] += out, colB[n] += out z  (z = the forward's fp32 pre-BN activation) -- relu_mask_kernel and
+// col_reduce_kernel each made a pass over the (BT,N,C/r) tensors for this.
+struct EpiReluMaskStats {
+  static constexpr bool kRowIndependent = true;
+  static constexpr bool kBlockStats = true;
+  bf16* out; long long ld, sb; const float* z; long long zld, zsb; const float* sc; const float* sh; float* colA; float* colB; float* blk;
+  __device__ __forceinline__ void flush_block(const float* b, int N, int tid, int nthreads) const {
+    if (!colA) return;
+    for (int c = tid; c < N; c += nthreads) {
+      if (b[c] != 0.f) atomicAdd(&colA[c], b[c]);
+      if (b[N + c] != 0.f) atomicAdd(&colB[c], b[N + c]);
+    }
+  }
+  __device__ __forceinline__ void begin(int, int, bool) {}
+  __device__ __forceinline__ void end(int, int, bool) {}
+  __device__ __forceinline__ void chunk(int b, int m, int n0, float (&v)[16], bool row_ok, int N) {
+    const int nvalid = nvalid16(n0, N);
+    float zz[16];
+    {
+      float s1[16], s2[16];
+      load16_guard(sc + n0, s1, nvalid);
+      load16_guard(sh + n0, s2, nvalid);
+      load16_guard(z + (long long)(row_ok ? b : 0) * zsb + (long long)(row_ok ? m : 0) * zld + n0, zz, nvalid);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (row_ok && j < nvalid && fmaf(zz[j], s1[j], s2[j]) > 0.f) ? v[j] : 0.f;
+    }
+    if (row_ok && nvalid > 0) store_row16<true>(out, (size_t)((long long)b * sb + (long long)m * ld + n0), v, nvalid);
+    if (colA) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) zz[j] *= v[j];
+      const float sa = warp_colsum16(v);
+      const float sbz = warp_colsum16(zz);
+      const int lane = threadIdx.x & 31;
+      const int col = n0 + colsum16_owner_col(lane);
+      if (((lane & 1) == 0) && col < N) {
+        if (blk) { atomicAdd(&blk[col], sa); atomicAdd(&blk[N + col], sbz); }
+        else { atomicAdd(&colA[col], sa); atomicAdd(&colB[col], sbz); }
+      }
+    }
+  }
+};
+
 // Q[b,m,0:32] = softmax_k(acc[0:32])    (N == 32, one N-block), bf16
 struct EpiRowSoftmax32 {
   static constexpr bool kWholeRow = true;
