@@ -676,9 +676,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
       RC(run_gemm(GS, K_(vB, BT, H, H, 0), 0, MN_(P.bott_w, H, C, C, 0), 0, BT, C, H, 1, tc::EpiNone{}, e4, AxIdentity{}, true, 0, false, true));
     } else if (rcv) return rcv;
     // q = aq1 * r1sum / N : daq1 = dq * r1sum / N ; dr1 = dq * aq1 / N
-    count_launch(2);
-    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_MUL_SCALE, vC, C, r1sum, C, invN, daq1, daq_ld, BT, C);
-    vec_op_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(VOP_MUL_SCALE, vC, C, aq1, aq_ld, invN, dr1, C, BT, C);
+    count_launch();
+    dq_split_kernel<<<ceil_div(BT * C, 256), 256, 0, st>>>(vC, r1sum, aq1, aq_ld, invN, daq1, daq_ld, dr1, BT, C);
     KCHECK("dq_split");
   }
   {

@@ -708,13 +708,25 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
     DGSCT_RC(gemm_auto(ST_SPATIAL_QUERY, "spatial_query", true, kmaj(Xc, N, C, C, (long long)N * C), kmaj(Wv2, H, C, pp.ld_c, 0),
                        N, H, C, BT, te, se, st));
   }
-  { StageScope _sc(ST_SPATIAL_MAP, st); count_launch();
-    spatial_map_kernel<<<BT, 256, 0, st>>>(ssum, P.s_b, N, sig, smap, 1, taps ? taps->s : nullptr);
-    DGSCT_LAUNCH_CHECK("spatial_map"); }
+  // The spatial map (softmax_n tanh s: an output, and the sigmoid gate the backward reads) is off the critical path: gate_ln
+  // derives the gate from the logits itself, so the map kernel runs on the auxiliary stream beside gate_ln / the bottleneck.
+  const bool map_aside = side != nullptr;
+  {
+    const cudaStream_t sm_st = map_aside ? side->s : st;
+    if (map_aside) {
+      DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, st));
+      DGSCT_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->ev, 0));
+    }
+    StageScope _sc(ST_SPATIAL_MAP, sm_st); count_launch();
+    spatial_map_kernel<<<BT, 256, 0, sm_st>>>(ssum, P.s_b, N, sig, smap, 1, taps ? taps->s : nullptr);
+    DGSCT_LAUNCH_CHECK("spatial_map");
+    if (map_aside) DGSCT_CUDA_CHECK(cudaEventRecord(side->ev, side->s));
+  }
   // (B1) Y = LN_before(X1 * (alpha m + beta sig + gamma tau + 1 - alpha))  -> V buffer
   {
     GateLnArgs a{};
     a.x1 = X1; a.in_bf16 = 1; a.y = Yb; a.out_bf16 = 1; a.m = mvec; a.sig = sig;
+    if (map_aside) { a.ssum = ssum; a.s_bias = P.s_b; }
     a.tau = ((d.flags & DGSCT_F_TEMPORAL) && d.gamma != 0.f) ? tau : nullptr;
     const bool lnb = d.flags & DGSCT_F_LN_BEFORE;
     a.ln_w = lnb ? P.lnb_w : nullptr; a.ln_b = lnb ? P.lnb_b : nullptr;
@@ -797,6 +809,7 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
       out_ln_kernel<<<(unsigned)((a.rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * C * 4, st>>>(a);
     DGSCT_LAUNCH_CHECK("out_ln");
   }
+  if (map_aside) DGSCT_CUDA_CHECK(cudaStreamWaitEvent(st, side->ev, 0));   // the spatial map is an output of the call
   return DGSCT_OK;
 }
 

@@ -339,6 +339,17 @@ __global__ void bwd_channel_mask_kernel(void* __restrict__ z1, int bf, int C, in
   }
 }
 
+// q = aq1 * r1sum / N  =>  d aq1 = dq * r1sum / N ,  d r1 = dq * aq1 / N   (both products of one pass; they were two launches)
+__global__ void dq_split_kernel(const float* __restrict__ dq, const float* __restrict__ r1sum, const float* __restrict__ aq1, int aq_ld,
+                                float inv_n, float* __restrict__ daq1, int daq_ld, float* __restrict__ dr1, int BT, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BT * C) return;
+  const int b = i / C, c = i - b * C;
+  const float g = dq[i] * inv_n;
+  daq1[(size_t)b * daq_ld + c] = g * r1sum[i];
+  dr1[i] = g * aq1[(size_t)b * aq_ld + c];
+}
+
 // ---- small per-frame vector ops (BT x width) ---------------------------------------------------------------------
 enum { VOP_SIGMOID_BWD = 0, VOP_RELU_BWD = 1, VOP_MUL_SCALE = 2 };
 // out[i] = op(g[i], y[i]) : sigmoid bwd g*y*(1-y) ; relu bwd g*1[y>0] ; mul-scale g*y*alpha

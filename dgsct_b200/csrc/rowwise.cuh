@@ -64,6 +64,8 @@ struct GateLnArgs {
   void* y; int out_bf16;                 // (rows, C)
   const float* m;                        // (BT, C)   channel gate
   const float* sig;                      // (rows)    sigmoid spatial gate
+  const float* ssum; const float* s_bias; // non-NULL ssum: the gate is derived here as sigmoid(ssum[row] + s_bias[0]) (same expression
+                                         // as spatial_map_kernel, which then runs beside this kernel instead of in front of it)
   const float* tau;                      // (BT) or NULL
   const float* ln_w; const float* ln_b;  // NULL => no LayerNorm
   float alpha, beta, gamma, eps;
@@ -80,7 +82,8 @@ __global__ void gate_ln_kernel(GateLnArgs a) {
   if (row >= a.rows) return;
   float* buf = smem + (size_t)warp * a.C;
   const int b = (int)(row / a.N);
-  const float base = a.beta * a.sig[row] + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha;
+  const float sgv = a.ssum ? 1.f / (1.f + expf(-(a.ssum[row] + (a.s_bias ? a.s_bias[0] : 0.f)))) : a.sig[row];
+  const float base = a.beta * sgv + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha;
   const float* mrow = a.m + (size_t)b * a.C;
   float sum = 0.f;
   for (int c = lane; c < a.C; c += 32) {
@@ -242,7 +245,8 @@ __global__ void __launch_bounds__(256) gate_ln_vec_kernel(GateLnArgs a) {
     const long long row = base + rsub;
     const bool rv = row < a.rows;
     const int b = rv ? (int)(row / a.N) : 0;
-    const float gbase = rv ? (a.beta * a.sig[row] + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha) : 0.f;
+    const float sgv = !rv ? 0.f : (a.ssum ? 1.f / (1.f + expf(-(a.ssum[row] + (a.s_bias ? a.s_bias[0] : 0.f)))) : a.sig[row]);
+    const float gbase = rv ? (a.beta * sgv + (a.tau ? a.gamma * a.tau[b] : 0.f) + 1.f - a.alpha) : 0.f;
     float v[VPL][8];
     uint4 raw[VPL];
 #pragma unroll
