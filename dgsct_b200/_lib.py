@@ -52,7 +52,7 @@ EXPORTS = ["dgsct_version", "dgsct_status_string", "dgsct_last_cuda_error", "dgs
            "dgsct_packed_bytes", "dgsct_pack_params", "dgsct_bwd_workspace_bytes", "dgsct_adapter_bwd",
            "dgsct_bwd_saved_workspace_bytes", "dgsct_adapter_bwd_saved",
            "dgsct_adapter_fwd", "dgsct_bicubic_matrix", "dgsct_num_stages", "dgsct_stage_name",
-           "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16",
+           "dgsct_profile_enable", "dgsct_profile_collect", "dgsct_launch_count", "dgsct_debug_gemm_bf16", "dgsct_debug_attn_plan",
            "dgsct_tc_error_flag", "dgsct_bicubic_csr_capacity", "dgsct_bicubic_csr",
            "dgsct_adam_tick", "dgsct_adam_flat", "dgsct_cast_bucket_bf16",
            "dgsct_adapter_pair_fwd", "dgsct_adapter_pair_bwd_saved",
@@ -136,6 +136,8 @@ def lib() -> C.CDLL:
     L.dgsct_profile_enable.argtypes = [C.c_int]
     L.dgsct_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]
     L.dgsct_launch_count.restype = C.c_longlong
+    L.dgsct_debug_attn_plan.restype = C.c_int
+    L.dgsct_debug_attn_plan.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int)]
     L.dgsct_debug_gemm_bf16.restype = C.c_int
     L.dgsct_debug_gemm_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_longlong] * 4 + [C.c_int] * 3 + [C.c_void_p]
     L.dgsct_tc_error_flag.argtypes = [C.c_int]

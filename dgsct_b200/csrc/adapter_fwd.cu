@@ -816,3 +816,29 @@ int adapter_fwd_tc(const dgsct_desc& d, const dgsct_params& P, const void* packe
 }  // namespace dgsct
 
 #include "adapter_bwd.inl"
+
+using namespace dgsct;
+extern "C" {
+// launch geometry of the fused attention kernels (host only; see include/dgsct.h)
+int dgsct_debug_attn_plan(int kernel, int BT, int N, int C, int K, int* out8) {
+  if (!out8) return DGSCT_ERR_NULL;
+  if (BT < 1 || N < 1 || C < 1 || K < 1) return DGSCT_ERR_BAD_DESC;
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (kernel == 0) {
+    const fa::TokAttnPlan p = fa::make_tok_attn_plan(BT, N, C, K);
+    if (p.ok) { out8[0] = 1; out8[1] = p.R; out8[2] = p.nbuf; out8[3] = p.nchunks; out8[4] = p.splits; out8[5] = p.Z; out8[6] = p.zcols; out8[7] = (int)p.smem; }
+  } else if (kernel == 1) {
+    const fa::XAttnPlan p = fa::make_x_attn_plan(BT, N, C, K);
+    if (p.ok) { out8[0] = 1; out8[1] = p.WB; out8[2] = p.coop ? 1 : 0; out8[4] = p.gx; out8[5] = 1; out8[6] = C; out8[7] = (int)p.smem; }
+  } else if (kernel == 2) {
+    const fa::XAttnBwdPlan p = fa::make_x_attn_bwd_plan(BT, N, C, K);
+    if (p.ok) { out8[0] = 1; out8[1] = p.R; out8[2] = p.nbuf; out8[3] = p.nchunks; out8[4] = p.splits; out8[5] = p.Z; out8[6] = p.zcols; out8[7] = (int)p.smem; }
+  } else if (kernel == 3) {
+    const fa::TokAttnBwdPlan p = fa::make_tok_attn_bwd_plan(BT, N, C, K);
+    if (p.ok) { out8[0] = 1; out8[1] = p.R; out8[2] = p.nbuf; out8[3] = p.nchunks; out8[4] = p.splits; out8[5] = p.Z; out8[6] = p.zcols; out8[7] = (int)p.smem; }
+  } else {
+    return DGSCT_ERR_BAD_DESC;
+  }
+  return DGSCT_OK;
+}
+}  // extern "C"

@@ -235,6 +235,14 @@ int dgsct_debug_gemm_bf16(const void *A, const void *B, float *D, int M, int N, 
  * return DGSCT_ERR_TIMEOUT once it is set. */
 int dgsct_tc_error_flag(int reset);
 
+/* Host helper (no device work): launch geometry of the fused latent-token attention kernels (attn_fused.cuh) for one adapter
+ * call of BT frames, N tokens x C channels, K latent tokens.  kernel: 0 = tokens over V (forward), 1 = stream over tokens
+ * (forward), 2 = backward of 1, 3 = backward of 0.  out[8] = {supported, rows_per_chunk, buffers, chunks, splits,
+ * column_ranges, columns_per_range, dynamic_smem_bytes} (kernel 1: {supported, warps_per_cta, cooperative, 0, ctas_per_frame,
+ * 1, C, smem}).  Tests pin the properties the bit-for-bit batch == clips guarantee rests on (chunk rows and splits of the
+ * forward depend on the frame's shape only). */
+int dgsct_debug_attn_plan(int kernel, int BT, int N, int C, int K, int *out8);
+
 /* Host helper: dense (n_out^2, n_in^2) matrix of bicubic (A=-0.75, align_corners=False) interpolation
  * on a square token grid, written to HOST memory `w` (row-major).  Used for the AVS-S4 resampler
  * (PVT_AVSModel.py:190-197). */

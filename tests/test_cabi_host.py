@@ -159,3 +159,35 @@ def test_keep_and_saved_workspace_sizes(lib):
     assert full - saved >= keep - 4096          # the difference is the recompute region (the keep plan)
     bad = _desc(C=191)
     assert lib.dgsct_bwd_saved_workspace_bytes(C.byref(bad)) == 0
+
+
+def test_fused_attention_launch_geometry_is_a_function_of_the_frame_shape():
+    """Host logic of attn_fused.cuh (no device work): the forward's chunk rows and splits -- the quantities the bit-for-bit
+    'a batch equals its clips' property rests on -- depend on (N, C, K) only; every plan fits the 227 KB of an SM; unsupported
+    shapes are reported, not launched."""
+    import ctypes as C
+    lib = L.lib()
+
+    def plan(kernel, BT, N, Cc, K=32):
+        out = (C.c_int * 8)()
+        assert lib.dgsct_debug_attn_plan(kernel, BT, N, Cc, K, out) == 0
+        return list(out)
+
+    shapes = [(192, 2304), (96, 4096), (384, 576), (192, 1024), (768, 144), (384, 256), (1536, 36), (768, 64), (320, 100), (1024, 49), (64, 10)]
+    for Cc, N in shapes:
+        ref = plan(0, 80, N, Cc)
+        assert ref[0] == 1, (Cc, N)
+        for BT in (1, 7, 10, 20, 80, 480):
+            p = plan(0, BT, N, Cc)
+            assert p[1:5] == ref[1:5], ("rows per chunk / buffers / chunks / splits must not depend on BT", Cc, N, BT, p, ref)
+            assert p[1] % 16 == 0 and p[1] * p[3] >= N and p[4] <= p[3] and p[6] % 16 == 0 and p[5] * p[6] >= Cc
+            for k in (0, 1, 2, 3):
+                q = plan(k, BT, N, Cc)
+                if q[0]:
+                    assert 0 < q[7] <= 227 * 1024, (k, Cc, N, BT, q)
+            assert plan(1, BT, N, Cc)[0] == 1 and plan(2, BT, N, Cc)[0] == 1
+    # the token-softmax backward needs two 32 x C operand tiles next to a chunk: C = 1536 does not fit and is reported unsupported
+    assert plan(3, 80, 36, 1536)[0] == 0 and plan(3, 80, 144, 768)[0] == 1
+    # shapes outside the kernels' reach: channel count not a multiple of 32, more than 32 latent tokens
+    assert plan(0, 8, 100, 100)[0] == 0 and plan(0, 8, 100, 96, 33)[0] == 0
+    assert lib.dgsct_debug_attn_plan(9, 8, 100, 96, 32, (C.c_int * 8)()) < 0
