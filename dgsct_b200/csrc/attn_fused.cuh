@@ -541,7 +541,7 @@ inline TokAttnPlan make_tok_attn_plan(int BT, int N, int C, int K) {
   // sums, hence every bit of T', is the same for a batch and for its clips (tests/test_gpu_zfullsize.py).
   (void)BT;
   {
-    int sp = (N + 192) / 384;
+    int sp = (N + 192) / 384;        // (sweep 256 .. 2304 rows per split on B200: flat around 384, profiles/r02_fused_attention_chunk_sweep.txt)
     if (sp < 1) sp = 1;
     if (sp > p.nchunks) sp = p.nchunks;
     if (sp > 32) sp = 32;
