@@ -371,11 +371,15 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
   const float* sc2 = (const float*)(fw + fp.bn2_scale); const float* sh2 = (const float*)(fw + fp.bn2_shift);
   // h: fp32 (BT,H) in the SIMT path, bf16 (BT, ld_h) in the tensor-core path -> fp32 copy for the small products
   float* hf = (float*)(ws + bp.vD);
-  if (tcp) {
+  bool hf_ready = !tcp;
+  auto ensure_h_f32 = [&]() -> int {      // only the SIMT fallbacks of the channel-gate chain read h as fp32: converted on demand
+    if (hf_ready) return DGSCT_OK;
     StageScope _sc(ST_MISC, st); count_launch();
     tap_copy_kernel<<<64, 256, 0, st>>>(fw + fp.h, 1, hf, (size_t)BT * pp.ld_h);   // (BT, ld_h) bf16 -> fp32, same pitch
     KCHECK("h_f32");
-  }
+    hf_ready = true;
+    return DGSCT_OK;
+  };
   const float* hsrc = tcp ? hf : (const float*)(fw + fp.h);
   const int h_ld = tcp ? pp.ld_h : H;
 
@@ -651,6 +655,8 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     col_reduce_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, sst>>>(vA, 0, C, nullptr, 0, 0, BT, C, G.c_b, nullptr);
     int rcv = vec_tc ? vec_gemm(GSW, MN_(vAb, BT, C, ldcb, 0), MN_(hb, BT, H, pp.ld_h, 0), C, H, BT, G.c_w, H, OUT_ATOMIC) : DGSCT_ERR_UNSUPPORTED;
     if (rcv == DGSCT_ERR_UNSUPPORTED) {
+      RC(ensure_h_f32());
+      if (side) { RC(fork_side()); }                                  // (the conversion ran on the caller's stream)
       EpiOut e1 = eo(G.c_w, 0, H, 0, OUT_ADD);
       RC(run_gemm(GSW, MN_(vA, BT, C, C, 0), 0, MN_(hsrc, BT, H, h_ld, 0), 0, C, H, BT, 1, tc::EpiNone{}, e1, AxIdentity{}, true));
     } else if (rcv) return rcv;
@@ -661,7 +667,9 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     } else if (rcv) return rcv;
     // dph = dh * 1[h>0] -> vB in place ; d_bb += colsum ; dWb (H,C) += dph^T q ; dq = dph . Wb -> vC (BT,C)
     count_launch(2);
-    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, vB, H, hsrc, h_ld, 0.f, vB, H, BT, H, vec_tc ? vBb : nullptr, ldhb);
+    if (!tcp || !vec_tc) { RC(ensure_h_f32()); }
+    vec_op_kernel<<<ceil_div(BT * H, 256), 256, 0, st>>>(VOP_RELU_BWD, vB, H, hsrc, h_ld, 0.f, vB, H, BT, H, vec_tc ? vBb : nullptr, ldhb,
+                                                         (tcp && vec_tc) ? hb : nullptr);
     RC(fork_side());                                                  // vB = dph is final
     col_reduce_kernel<<<dim3(ceil_div(H, 32), 1), 256, 0, sst>>>(vB, 0, H, nullptr, 0, 0, BT, H, G.bott_b, nullptr);
     KCHECK("dph");
@@ -796,10 +804,15 @@ int adapter_bwd(const dgsct_desc& d_in, const dgsct_params& P, const void* packe
     RC(join_side2());                                                 // d obar (second vector chain) is needed from here on
     const void* dTpOp = dTp;
     long long dTp_bs = (long long)K * C;
-    { StageScope _sc(ST_MISC, st); count_launch(2);
-      sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, st>>>(dTp, BT, (size_t)K * C, G.tokens, G.fc_b, C, dobar);   // + d fc_b (exact)
-      if (tcp && !fused_a) { cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB; }
+    RC(fork_side());                                                  // dT' and d obar are final: the frame sums are parameter gradients
+    { StageScope _sc(ST_MISC, sst); count_launch();
+      sum_frames_kernel<<<ceil_div(K * C, 256), 256, 0, sst>>>(dTp, BT, (size_t)K * C, G.tokens, G.fc_b, C, dobar);  // + d fc_b (exact)
       KCHECK("dtok_sum"); }
+    if (tcp && !fused_a) {
+      StageScope _sc(ST_MISC, st); count_launch();
+      cast_scale_kernel<<<ew_grid, 256, 0, st>>>(dTp, 1.f, dTpB, 1, (size_t)BT * K * C); dTpOp = dTpB;
+      KCHECK("dtp_cast");
+    }
     if (fused_a) {
       float* Dv = (float*)(ws + bp.csm_part);               // D[b,k] = sum_n dP P  (BT x K)
       { StageScope _sc(ST_COL_SOFTMAX, st); count_launch();

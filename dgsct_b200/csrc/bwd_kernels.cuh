@@ -355,11 +355,13 @@ enum { VOP_SIGMOID_BWD = 0, VOP_RELU_BWD = 1, VOP_MUL_SCALE = 2 };
 // out[i] = op(g[i], y[i]) : sigmoid bwd g*y*(1-y) ; relu bwd g*1[y>0] ; mul-scale g*y*alpha
 // (out16: optional bf16 copy with pitch out16_ld, the tensor-core operand of the per-frame-vector products)
 __global__ void vec_op_kernel(int op, const float* g, int g_ld, const float* __restrict__ y, int y_ld, float alpha,
-                              float* out, int out_ld, int rows, int cols, bf16* __restrict__ out16 = nullptr, int out16_ld = 0) {
+                              float* out, int out_ld, int rows, int cols, bf16* __restrict__ out16 = nullptr, int out16_ld = 0,
+                              const bf16* __restrict__ y16 = nullptr) {       // y16: read y as bf16 (same pitch) instead of fp32
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int r = i / cols, c = i % cols;
-  const float gv = g[(size_t)r * g_ld + c], yv = y[(size_t)r * y_ld + c];
+  const float gv = g[(size_t)r * g_ld + c];
+  const float yv = y16 ? __bfloat162float(y16[(size_t)r * y_ld + c]) : y[(size_t)r * y_ld + c];
   float v;
   if (op == VOP_SIGMOID_BWD) v = gv * yv * (1.f - yv);
   else if (op == VOP_RELU_BWD) v = yv > 0.f ? gv : 0.f;
@@ -520,7 +522,7 @@ __global__ void sum_frames_kernel(const float* __restrict__ in, int BT, size_t p
   if (i >= per_frame) return;
   float s = 0.f;
   for (int b = 0; b < BT; ++b) s += in[(size_t)b * per_frame + i];
-  out[i] += s;
+  atomicAdd(&out[i], s);          // (atomic: runs on the auxiliary stream beside the kernels that add the other half of d tokens)
   if (d_fcb) {
     const int c = (int)(i % (size_t)C);
     if (i < (size_t)C)                      // first token row also carries sum_b dobar[b, c]
