@@ -69,6 +69,14 @@ def test_stage_work_models_match_the_survey_totals():
     # row kernels: bytes = rows x C x bytes per element moved
     rows_c = sum(80 * b.dims(k, s)[1] * b.dims(k, s)[0] for k, _, _, s in b.layer_list())
     assert w["gate_ln"] == (rows_c * 4, "hbm", w["gate_ln"][2]) and w["bwd_out"][0] == rows_c * 8
+    # fused latent-token attention: the token side reads V once (+ the 32 x C latent tokens in / out per frame), the stream side
+    # reads X and writes X' and Q, the backward reads dX', X, V and writes dX, dV
+    kc = sum(80 * 32 * b.dims(k, s)[0] for k, _, _, s in b.layer_list())
+    rows = sum(80 * b.dims(k, s)[1] for k, _, _, s in b.layer_list())
+    assert w["tok_update"][0] == rows_c * 2 + kc * 6 and w["tok_update"][1] == "hbm"
+    assert w["x_update"][0] == rows_c * 4 + rows * 2 * 32 + kc * 2
+    assert w["bwd_token"][0] == rows_c * 10 + rows * 2 * 32 + kc * 16
+    assert w["tok_update"][0] + w["x_update"][0] < 0.3 * 4.193e9 * 4          # a fraction of the forward's 4.19 GB, by construction
     b._WL["name"] = "s4"
     ws = b.stage_work(20, b.WORKLOADS["s4"]["cfg"])
     assert "resample_conv" not in ws and "bwd_dw" in ws          # the stencil is a gather, not a GEMM
